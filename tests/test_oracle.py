@@ -1,0 +1,115 @@
+"""The CPU oracle (oracle/dpx_oracle.c) against (1) the committed golden fixtures produced by the
+compiled, unmodified reference classes, (2) the live reference binary when it is present,
+(3) the pins of the repaired banded semantics."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from dpx_gpu_genomics_project_b200 import synth
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SETS = sorted(os.path.basename(p)[:-7] for p in glob.glob(os.path.join(GOLD, "*.in.txt")))
+KW = {ol.LNW: dict(gap_open=-2), ol.LSW: dict(gap_open=-2), ol.ANW: dict(gap_open=-3, gap_extend=-1)}
+
+
+def oracle_text(algo, img, **kw):
+    blob, pairs = ol.parse_image(img)
+    scores, _, strs = ol.align_batch(ol.params(algo, **kw), blob, pairs)
+    return ol.format_text(scores, strs)
+
+
+@pytest.mark.parametrize("name", SETS)
+@pytest.mark.parametrize("algo", [ol.LNW, ol.LSW, ol.ANW])
+def test_oracle_matches_golden(name, algo):
+    img = open(os.path.join(GOLD, f"{name}.in.txt"), "rb").read()
+    want = open(os.path.join(GOLD, f"{name}.{ol.ALGO_NAMES[algo]}.out.txt"), "rb").read()
+    assert oracle_text(algo, img, **KW[algo]) == want
+
+
+@pytest.mark.skipif(not ol.have_ref_binary(), reason="oracle/_ref/ref_align not built")
+@pytest.mark.parametrize("algo,weights", [
+    (ol.LNW, dict(match=3, mismatch=-1, gap_open=-2)), (ol.LNW, dict(match=1, mismatch=-3, gap_open=-1)),
+    (ol.LSW, dict(match=3, mismatch=-1, gap_open=-2)), (ol.LSW, dict(match=2, mismatch=-2, gap_open=-1)),
+    (ol.ANW, dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1)), (ol.ANW, dict(match=2, mismatch=-1, gap_open=0, gap_extend=-2)),
+    (ol.ANW, dict(match=5, mismatch=-4, gap_open=-10, gap_extend=-1)),
+])
+def test_oracle_matches_live_reference(tmp_path, algo, weights):
+    rng = synth.Rng(0xABCD00 + algo * 17 + weights["match"])
+    pairs = []
+    for k in range(150):
+        alpha = [b"0", b"01", b"0123", b"01234"][k % 4]
+        R = int(rng.below(1, 70)[0])
+        r = synth.random_seq(rng, R, alpha)
+        q = synth.mutate(rng, r, 0.1, 0.05, 0.05, alpha) if k % 2 else synth.random_seq(rng, int(rng.below(1, 70)[0]), alpha)
+        pairs.append((r, q))
+    img = synth.pairs_to_file_bytes(pairs)
+    path = tmp_path / "in.txt"
+    path.write_bytes(img)
+    want = ol.run_reference(algo, str(path), **weights)
+    assert oracle_text(algo, img, **weights) == want
+
+
+def test_threaded_batch_equals_sequential():
+    img = open(os.path.join(GOLD, "cfg1_small.in.txt"), "rb").read()
+    blob, pairs = ol.parse_image(img)
+    p = ol.params(ol.ANW, gap_open=-3, gap_extend=-1)
+    a = ol.align_batch(p, blob, pairs, threads=1)
+    b = ol.align_batch(p, blob, pairs, threads=4)
+    assert (a[0] == b[0]).all() and a[2] == b[2]
+
+
+# ---- banded pins ------------------------------------------------------------------------------
+
+def test_bsw_full_band_equals_lsw():
+    """Pin (i): W >= max(Q,R) => byte-identical to the pinned LSW oracle."""
+    for name in ("adversarial", "shapes"):
+        img = open(os.path.join(GOLD, f"{name}.in.txt"), "rb").read()
+        blob, pairs = ol.parse_image(img)
+        W = int(max(pairs["referenceSize"].max(), pairs["querySize"].max()))
+        s0, e0, t0 = ol.align_batch(ol.params(ol.LSW), blob, pairs)
+        s1, e1, t1 = ol.align_batch(ol.params(ol.BSW, band=W), blob, pairs)
+        assert (s0 == s1).all() and (e0 == e1).all() and t0 == t1
+        want = open(os.path.join(GOLD, f"{name}.LSW.out.txt"), "rb").read()
+        assert ol.format_text(s1, t1) == want
+
+
+def test_bsw_scores_equal_python_prototype():
+    """Pin (ii): scores equal python/LinearBandedSmithWaterman.py with BAND = W+1 (committed fixture)."""
+    cases = json.load(open(os.path.join(GOLD, "bsw_python_scores.json")))
+    assert len(cases) >= 50
+    for c in cases:
+        img = synth.pairs_to_file_bytes([(c["ref"].encode(), c["qry"].encode())])
+        blob, pairs = ol.parse_image(img)
+        s, _, _ = ol.align_batch(ol.params(ol.BSW, band=c["band"]), blob, pairs, strings=False)
+        assert int(s[0]) == c["score"], c
+
+
+def test_bsw_bandmem_and_linear_memory_agree_with_full_matrix():
+    """Pin (iii): band-only-memory and rolling-row restatements == full-matrix restatement."""
+    rng = synth.Rng(77)
+    pairs = []
+    for k in range(40):
+        R = 50 + int(rng.below(1, 700)[0])
+        r = synth.random_seq(rng, R)
+        pairs.append((r, synth.mutate(rng, r, 0.05, 0.02, 0.02)))
+    blob, idx = ol.parse_image(synth.pairs_to_file_bytes(pairs))
+    for W in (0, 1, 7, 64):
+        p = ol.params(ol.BSW, band=W)
+        a = ol.align_batch(p, blob, idx)
+        b = ol.align_batch(p, blob, idx, bandmem=True)
+        assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2]
+        for k, (r, q) in enumerate(pairs[:10]):
+            assert ol.lsw_score_only(p, r, q, band=W) == (int(a[0][k]), int(a[1][k][0]), int(a[1][k][1]))
+    p = ol.params(ol.LSW)
+    a = ol.align_batch(p, blob, idx, strings=False)
+    for k, (r, q) in enumerate(pairs):
+        assert ol.lsw_score_only(p, r, q) == (int(a[0][k]), int(a[1][k][0]), int(a[1][k][1]))
+
+
+def test_parse_image_rejects_bad_line_count():
+    with pytest.raises(ValueError):
+        ol.parse_image(b"0\n0123\n")

@@ -1,0 +1,292 @@
+"""Python mirror of the reference's alignment interface on top of the C ABI (include/dpxalign.h).
+
+Same names and argument order as the reference's C++ classes so that parity tests read like the
+reference's own usage (c++/main.cpp:237-252):
+
+    LinearNeedlemanWunsch(ref, query, pairNum, match, mismatch, gap).align()      c++/LinearNeedlemanWunsch.h:42-47
+    AffineNeedlemanWunsch(ref, query, pairNum, match, mismatch, open, extend)     c++/AffineNeedlemanWunsch.h:59-66
+    LinearSmithWaterman(ref, query, pairNum, match, mismatch, gap)                c++/LinearSmithWaterman.h:51-57
+    BandedSmithWaterman(ref, query, match, mismatch, gap, pairNum, band_width)    c++/BandedSmithWaterman.h:51-57
+                                         (pairNum last as in the reference; band_width is the parameter
+                                          the reference forgot to initialise, .h:16)
+
+``align()`` writes exactly the bytes the reference prints (``"<i> | <score>\\nREF\\nREL\\nQRY\\n"``).
+Everything computes on the GPU through libdpxalign.so; there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+LNW, ANW, LSW, BSW = 0, 1, 2, 3
+OUT_SCORE, OUT_END_COORDS, OUT_STRINGS = 1, 2, 4
+PAIR_DTYPE = np.dtype([("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
+
+
+class DpxError(RuntimeError):
+    def __init__(self, status: int, detail: str = ""):
+        self.status = status
+        msg = _lib.lib().dpx_strerror(status).decode()
+        super().__init__(f"dpxalign status {status}: {msg}" + (f" ({detail})" if detail else ""))
+
+
+def _check(st: int, ctx=None):
+    if st != 0:
+        detail = _lib.lib().dpx_last_error(ctx).decode() if ctx else ""
+        raise DpxError(st, detail)
+
+
+@dataclass
+class ParsedInput:
+    """parseInput's outputs (c++/parseInput.h:9-35): blob with newlines -> NUL, seqPair index, inputInfo."""
+    sequences: np.ndarray     # uint8[numBytes]
+    pairs: np.ndarray         # PAIR_DTYPE[numPairs]
+    info: dict
+
+
+def parse_input(path: str) -> ParsedInput:
+    L = _lib.lib()
+    pairs_p, seq_p, info = C.c_void_p(), C.c_void_p(), _lib.InputInfo()
+    _check(L.dpx_parse_input(path.encode(), C.byref(pairs_p), C.byref(seq_p), C.byref(info)))
+    try:
+        n, nb = info.numPairs, info.numBytes
+        seqs = np.ctypeslib.as_array(C.cast(seq_p, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb].copy()
+        pairs = np.frombuffer(C.string_at(pairs_p, n * PAIR_DTYPE.itemsize), dtype=PAIR_DTYPE).copy() if n else np.zeros(0, PAIR_DTYPE)
+    finally:
+        L.dpx_free(pairs_p); L.dpx_free(seq_p)
+    return ParsedInput(seqs, pairs, {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_})
+
+
+@dataclass
+class BatchResult:
+    scores: np.ndarray                    # int32[n]
+    end_row_col: np.ndarray | None        # int32[n,2]
+    strings: list | None                  # [(REF, REL, QRY)] bytes
+
+    def text(self, first_index: int = 0) -> bytes:
+        """The reference's stdout blocks for these pairs (c++/LinearNeedlemanWunsch.cpp:207-213)."""
+        parts = []
+        for i, s in enumerate(self.scores):
+            a, b, c = self.strings[i]
+            parts.append(b"%d | %d\n" % (first_index + i, int(s)))
+            parts.append(a + b"\n" + b + b"\n" + c + b"\n")
+        return b"".join(parts)
+
+
+def make_params(algo, match=3, mismatch=-1, gap_open=-2, gap_extend=-1, band=0, flags=OUT_SCORE) -> _lib.Params:
+    return _lib.Params(algo, match, mismatch, gap_open, gap_extend, band, flags)
+
+
+class Engine:
+    """One device context (dpx_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.lib()
+        self.ctx = C.c_void_p()
+        _check(self.L.dpx_create(C.byref(self.ctx), device))
+
+    def close(self):
+        if self.ctx:
+            self.L.dpx_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(self.L.dpx_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), self.ctx)
+
+    # ---- one call: host buffers in, host buffers out ---------------------------------------------
+    def align_batch(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray) -> BatchResult:
+        n = len(pairs)
+        sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        scores = np.zeros(n, dtype=np.int32)
+        end_rc = np.zeros((n, 2), dtype=np.int32)
+        sb, so = C.c_void_p(), C.c_void_p()
+        want = bool(params.flags & OUT_STRINGS)
+        _check(self.L.dpx_align_batch(self.ctx, C.byref(params), sequences.ctypes.data, sequences.size,
+                                      pairs.ctypes.data, n, scores.ctypes.data, end_rc.ctypes.data,
+                                      C.byref(sb) if want else None, C.byref(so) if want else None), self.ctx)
+        return BatchResult(scores, end_rc, self._take_strings(sb, so, n) if want else None)
+
+    def _take_strings(self, sb, so, n):
+        try:
+            offs = np.frombuffer(C.string_at(so, 3 * n * C.sizeof(C.c_size_t)), dtype=np.uint64) if n else []
+            base = sb.value
+            out = []
+            for i in range(n):
+                out.append(tuple(C.string_at(base + int(offs[3 * i + k])) for k in range(3)))
+            return out
+        finally:
+            self.L.dpx_free(sb); self.L.dpx_free(so)
+
+    # ---- staged ----------------------------------------------------------------------------------
+    def upload(self, sequences: np.ndarray, pairs: np.ndarray) -> "Batch":
+        return Batch(self, sequences, pairs)
+
+    def dpx_eval(self, op: int, a, b, c):
+        a = np.ascontiguousarray(a, dtype=np.uint32); b = np.ascontiguousarray(b, dtype=np.uint32); c = np.ascontiguousarray(c, dtype=np.uint32)
+        n = len(a)
+        out = np.zeros(n, np.uint32); ph = np.zeros(n, np.uint8); pl = np.zeros(n, np.uint8)
+        _check(self.L.dpx_dpx_eval(self.ctx, op, a.ctypes.data, b.ctypes.data, c.ctypes.data, n,
+                                   out.ctypes.data, ph.ctypes.data, pl.ctypes.data), self.ctx)
+        return out, ph, pl
+
+    def selftest(self) -> int:
+        return self.L.dpx_selftest_dpx(self.ctx)
+
+    def align_long_pair(self, params: _lib.Params, ref: bytes, qry: bytes):
+        s = C.c_int32(); r = C.c_int64(); c = C.c_int64()
+        _check(self.L.dpx_align_long_pair(self.ctx, C.byref(params), ref, len(ref), qry, len(qry),
+                                          C.byref(s), C.byref(r), C.byref(c)), self.ctx)
+        return s.value, r.value, c.value
+
+
+class Batch:
+    """Pairs resident in HBM (dpx_batch): upload once, run any number of times, fetch."""
+
+    def __init__(self, eng: Engine, sequences: np.ndarray, pairs: np.ndarray):
+        self.eng = eng
+        self.n = len(pairs)
+        self._seq = np.ascontiguousarray(sequences, dtype=np.uint8)
+        self._pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        self.h = C.c_void_p()
+        _check(eng.L.dpx_batch_upload(eng.ctx, self._seq.ctypes.data, self._seq.size, self._pairs.ctypes.data, self.n,
+                                      C.byref(self.h)), eng.ctx)
+        self.params = None
+
+    def run(self, params: _lib.Params):
+        self.params = params
+        _check(self.eng.L.dpx_batch_run(self.h, C.byref(params)), self.eng.ctx)
+
+    def sync(self):
+        _check(self.eng.L.dpx_batch_sync(self.h), self.eng.ctx)
+
+    def stats(self) -> dict:
+        s = _lib.RunStats()
+        _check(self.eng.L.dpx_batch_stats(self.h, C.byref(s)), self.eng.ctx)
+        return {f: getattr(s, f) for f, _ in _lib.RunStats._fields_}
+
+    def fetch(self, scores: np.ndarray | None = None, end_rc: np.ndarray | None = None) -> BatchResult:
+        n = self.n
+        scores = np.zeros(n, dtype=np.int32) if scores is None else scores
+        end_rc = np.zeros((n, 2), dtype=np.int32) if end_rc is None else end_rc
+        sb, so = C.c_void_p(), C.c_void_p()
+        want = bool(self.params.flags & OUT_STRINGS)
+        _check(self.eng.L.dpx_batch_fetch(self.h, scores.ctypes.data, end_rc.ctypes.data,
+                                          C.byref(sb) if want else None, C.byref(so) if want else None), self.eng.ctx)
+        return BatchResult(scores, end_rc, self.eng._take_strings(sb, so, n) if want else None)
+
+    def free(self):
+        if self.h:
+            self.eng.L.dpx_batch_free(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+# ---- the reference's per-pair classes -----------------------------------------------------------------
+_default_engine = None
+
+
+def default_engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0)
+    return _default_engine
+
+
+def _as_bytes(s) -> bytes:
+    return s.encode() if isinstance(s, str) else bytes(s)
+
+
+class SequenceAligner:
+    """c++/SequenceAligner.h:6-28: holds reference_str, query_str, pairNum; subclasses implement align()."""
+    _algo = None
+
+    def __init__(self, input_reference, input_query, pairNum: int):
+        self.reference_str = _as_bytes(input_reference)
+        self.query_str = _as_bytes(input_query)
+        self.pairNum = int(pairNum)
+        self.score = None
+        self.end_row_col = None
+        self.reference_sequence = self.pair_relation = self.query_sequence = None
+        self.out = sys.stdout
+
+    def _params(self) -> _lib.Params:
+        raise NotImplementedError
+
+    # the reference's six virtuals; on the GPU the first three are one fused batch call
+    def init_matrix(self): pass
+    def print_matrix(self): raise NotImplementedError("matrices never leave the GPU")
+    def score_matrix(self): self._run()
+    def backtrack(self):
+        if self.score is None: self._run()
+    def print_results(self):
+        w = getattr(self.out, "buffer", self.out)
+        w.write(self.text())
+
+    def _run(self):
+        r, q = self.reference_str, self.query_str
+        blob = np.frombuffer(r + b"\0" + q + b"\0", dtype=np.uint8)
+        pairs = np.array([(0, len(r), len(r) + 1, len(q))], dtype=PAIR_DTYPE)
+        res = default_engine().align_batch(self._params(), blob, pairs)
+        self.score = int(res.scores[0])
+        self.end_row_col = (int(res.end_row_col[0][0]), int(res.end_row_col[0][1]))
+        self.reference_sequence, self.pair_relation, self.query_sequence = res.strings[0]
+
+    def text(self) -> bytes:
+        return b"%d | %d\n" % (self.pairNum, self.score) + self.reference_sequence + b"\n" + self.pair_relation + b"\n" + self.query_sequence + b"\n"
+
+    def align(self):
+        self.init_matrix(); self.score_matrix(); self.backtrack(); self.print_results()
+
+
+class LinearNeedlemanWunsch(SequenceAligner):
+    def __init__(self, input_reference, input_query, pairNum, match_weight, mismatch_weight, gap_weight):
+        super().__init__(input_reference, input_query, pairNum)
+        self.w = (match_weight, mismatch_weight, gap_weight)
+
+    def _params(self):
+        return make_params(LNW, self.w[0], self.w[1], self.w[2], 0, 0, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)
+
+
+class LinearSmithWaterman(SequenceAligner):
+    def __init__(self, input_reference, input_query, pairNum, match_weight, mismatch_weight, gap_weight):
+        super().__init__(input_reference, input_query, pairNum)
+        self.w = (match_weight, mismatch_weight, gap_weight)
+
+    def _params(self):
+        return make_params(LSW, self.w[0], self.w[1], self.w[2], 0, 0, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)
+
+
+class AffineNeedlemanWunsch(SequenceAligner):
+    def __init__(self, input_reference, input_query, pairNum, matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight):
+        super().__init__(input_reference, input_query, pairNum)
+        self.w = (matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight)
+
+    def _params(self):
+        return make_params(ANW, self.w[0], self.w[1], self.w[2], self.w[3], 0, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)
+
+
+class BandedSmithWaterman(SequenceAligner):
+    def __init__(self, input_reference, input_query, match_weight, mismatch_weight, gap_weight, pairNum, band_width=64):
+        super().__init__(input_reference, input_query, pairNum)
+        self.w = (match_weight, mismatch_weight, gap_weight)
+        self.band_width = int(band_width)
+
+    def _params(self):
+        return make_params(BSW, self.w[0], self.w[1], self.w[2], 0, self.band_width, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)

@@ -1,0 +1,118 @@
+// backtrack.cuh — GPU traceback: walks the packed direction slab written by the fill kernels and emits
+// the three alignment strings (REF / REL / QRY) exactly as the reference prints them.
+//
+// Walk rules restate the reference:
+//   LNW  c++/LinearNeedlemanWunsch.cpp:137-223 (= backtrackNW, c++/backtrack.cpp:21-81): from (Q,R)
+//        while (i != 0 || j != 0); row 0 => QUERY_INSERTION, column 0 => QUERY_DELETION (init_matrix :31-41).
+//   ANW  c++/AffineNeedlemanWunsch.cpp:242-403 (= backtrackANW, c++/backtrack.cpp:214-356): 3-state walk
+//        while (i != 0 && j != 0), then pad rows as deletions, then columns as insertions (:366-378).
+//   LSW  c++/LinearSmithWaterman.cpp:163-226 (= backtrackSW, c++/backtrack.cpp:83-144): from the first-max
+//        cell, apply the cell's direction, stop when the next cell's H is 0; score 0 => three empty strings.
+// Characters: '*' match, '|' mismatch, ' ' gap in REL, '_' gap symbol.
+//
+// One thread walks one pair (the walk is a chain of dependent 4-byte loads from an L2-resident slab, so
+// parallelism comes from walking many pairs at once).  Strings are written right-to-left into the pair's
+// slot: three fields of F = Q+R+1 bytes, each ending in NUL; str_start[pid] = offset of the first
+// character inside each field.
+#pragma once
+#include "common.cuh"
+
+namespace dpx {
+
+struct BtArgs {
+    const uint8_t* blob;
+    const dpx_seq_pair* pairs;
+    const int32_t* order;
+    int first, count;
+    int K, band;                         // geometry of the slab that was written (band < 0 = unbanded)
+    const int32_t* scores;
+    const int32_t* end_rc;               // SW start cells
+    const uint32_t* tb;
+    const unsigned long long* tb_off;
+    char* strings;                       // output slab
+    const unsigned long long* str_off;   // [n_pairs] byte offset of the pair's slot
+    int32_t* str_start;                  // [n_pairs] out
+};
+
+template <int CB>
+__device__ __forceinline__ uint32_t wf_code(const uint32_t* __restrict__ tb, const WfGeom& g, int i, int j) {
+    const int ii = i - 1;
+    const int s = ii / g.rows_per_stripe;
+    const int rem = ii - s * g.rows_per_stripe;
+    const int lane = rem / g.K, r = rem - lane * g.K;
+    const int js = g.jstart(s);
+    if (j < js || j > g.jend(s)) return C_STOP;           // banded: outside the stripe's column window => H == 0
+    const int step = j - js + lane;
+    const int grp = step / g.SPW, sub = step - grp * g.SPW;
+    const uint32_t w = __ldg(tb + ((size_t)s * g.ngroups + grp) * 32 + lane);
+    return (w >> ((sub * g.K + r) * CB)) & ((1u << CB) - 1u);
+}
+
+template <int ALGO>
+__global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
+    constexpr int CB = (ALGO == DPX_ALGO_ANW) ? 4 : 2;
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= a.count) return;
+    const int pid = a.order ? a.order[a.first + pos] : (a.first + pos);
+    const dpx_seq_pair pr = a.pairs[pid];
+    const int R = pr.referenceSize, Q = pr.querySize;
+    const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
+    const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
+    const WfGeom geo = WfGeom::make(a.K, CB, Q, R, ALGO == DPX_ALGO_BSW ? a.band : -1);
+    const uint32_t* __restrict__ tb = a.tb + a.tb_off[pid];
+
+    const size_t F = (size_t)Q + R + 1;
+    char* __restrict__ o0 = a.strings + a.str_off[pid];
+    char* __restrict__ o1 = o0 + F;
+    char* __restrict__ o2 = o1 + F;
+    long long p = (long long)F - 1;
+    o0[p] = 0; o1[p] = 0; o2[p] = 0;
+
+    auto emit_diag = [&](int i, int j) { const char rc = ref[j - 1], qc = qry[i - 1]; --p; o0[p] = rc; o1[p] = (rc == qc) ? '*' : '|'; o2[p] = qc; };
+    auto emit_up   = [&](int i)        { --p; o0[p] = '_'; o1[p] = ' '; o2[p] = qry[i - 1]; };
+    auto emit_left = [&](int j)        { --p; o0[p] = ref[j - 1]; o1[p] = ' '; o2[p] = '_'; };
+
+    if (ALGO == DPX_ALGO_LNW) {
+        int i = Q, j = R;
+        while (i != 0 || j != 0) {
+            const uint32_t c = (i == 0) ? C_LEFT : (j == 0) ? C_UP : wf_code<CB>(tb, geo, i, j);
+            if (c == C_DIAG) { emit_diag(i, j); --i; --j; }
+            else if (c == C_UP) { emit_up(i); --i; }
+            else { emit_left(j); --j; }
+        }
+    } else if (ALGO == DPX_ALGO_ANW) {
+        int i = Q, j = R, state = 0;     // 0 SCORING, 1 INSERTION, 2 DELETION
+        while (i != 0 && j != 0) {
+            const uint32_t c = wf_code<CB>(tb, geo, i, j);
+            if (state == 0) {
+                const uint32_t d = c & 3u;
+                if (d == C_DIAG) { emit_diag(i, j); --i; --j; }
+                else if (d == C_UP) state = 2;
+                else state = 1;
+            } else if (state == 1) {
+                state = (c & C_IOPEN) ? 0 : 1;
+                emit_left(j); --j;
+            } else {
+                state = (c & C_DOPEN) ? 0 : 2;
+                emit_up(i); --i;
+            }
+        }
+        while (i > 0) { emit_up(i); --i; }
+        while (j > 0) { emit_left(j); --j; }
+    } else {
+        if (a.scores[pid] > 0) {
+            int i = a.end_rc[2 * pid], j = a.end_rc[2 * pid + 1];
+            uint32_t c = wf_code<CB>(tb, geo, i, j);
+            while (c != C_STOP) {
+                if (c == C_DIAG) { emit_diag(i, j); --i; --j; }
+                else if (c == C_UP) { emit_up(i); --i; }
+                else { emit_left(j); --j; }
+                if (i == 0 || j == 0) break;
+                c = wf_code<CB>(tb, geo, i, j);
+            }
+        }
+    }
+    a.str_start[pid] = (int32_t)p;
+}
+
+}  // namespace dpx

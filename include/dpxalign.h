@@ -1,0 +1,184 @@
+/* dpxalign.h — C ABI of libdpxalign.so, the B200 (sm_100a) pairwise-alignment engine.
+ *
+ * The reference (mickgordinier/DPX_GPU_Genomics_Project) has no FFI seam: its boundary is
+ * the C++ class interface + parser + stdout format.  Each entry point below names the
+ * reference interface it replaces (file:line relative to the reference tree).  The C++
+ * shims in dpx_gpu_genomics_project_b200/host/ (SequenceAligner subclasses, parseInput,
+ * drop-in main) and the Python ctypes mirror are built ONLY on this header.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; no stdout/stderr writes and
+ * no exit() inside the library (the reference exit(1)s: c++/parseInput.cpp:14,28,40,58,63);
+ * every function returns 0 on success or a negative dpx_status; results come back in pair
+ * order; calls on one dpx_ctx must be serialised by the caller (one ctx per host thread).
+ * There is NO CPU fallback: without a CUDA device dpx_create fails with DPX_ERR_NO_DEVICE.
+ */
+#ifndef DPXALIGN_H
+#define DPXALIGN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPX_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------- */
+typedef enum {
+    DPX_OK               = 0,
+    DPX_ERR_INVALID      = -1,   /* bad argument (NULL, unknown algo, negative size, ...) */
+    DPX_ERR_NO_DEVICE    = -2,   /* no usable CUDA device / driver */
+    DPX_ERR_CUDA         = -3,   /* a CUDA runtime call or kernel failed; see dpx_last_error */
+    DPX_ERR_NOMEM        = -4,   /* host or device allocation failed */
+    DPX_ERR_IO           = -5,   /* dpx_parse_input: cannot open / read the file */
+    DPX_ERR_FORMAT       = -6,   /* dpx_parse_input: number of lines not a multiple of 3 */
+    DPX_ERR_RANGE        = -7,   /* a sequence / score does not fit the selected kernel's range */
+    DPX_ERR_UNSUPPORTED  = -8
+} dpx_status;
+
+/* ---- algorithms: one per reference SequenceAligner subclass ------------------------ */
+typedef enum {
+    DPX_ALGO_LNW = 0,   /* LinearNeedlemanWunsch   c++/LinearNeedlemanWunsch.{h,cpp}  */
+    DPX_ALGO_ANW = 1,   /* AffineNeedlemanWunsch   c++/AffineNeedlemanWunsch.{h,cpp}  */
+    DPX_ALGO_LSW = 2,   /* LinearSmithWaterman     c++/LinearSmithWaterman.{h,cpp}    */
+    DPX_ALGO_BSW = 3    /* BandedSmithWaterman     c++/BandedSmithWaterman.{h,cpp} (repaired semantics) */
+} dpx_algo;
+
+/* ---- output selection ------------------------------------------------------------ */
+#define DPX_OUT_SCORE      0x1u   /* scores[]                      (always produced) */
+#define DPX_OUT_END_COORDS 0x2u   /* end_row_col[]: SW first-max cell (1-based matrix indices); NW: (Q,R) */
+#define DPX_OUT_STRINGS    0x4u   /* full traceback + the three alignment strings REF / REL / QRY */
+
+/* Weights exactly as the reference constructors take them
+ * (c++/LinearNeedlemanWunsch.h:42-47, c++/AffineNeedlemanWunsch.h:59-66,
+ *  c++/LinearSmithWaterman.h:51-57, c++/BandedSmithWaterman.h:51-57).
+ * Linear aligners use gap_open as their single gap weight (c++/main.cpp:238,244). */
+typedef struct {
+    int32_t  algo;          /* dpx_algo */
+    int32_t  match;
+    int32_t  mismatch;
+    int32_t  gap_open;      /* linear: the gap weight */
+    int32_t  gap_extend;    /* ANW only */
+    int32_t  band;          /* BSW only: |i-j| <= band */
+    uint32_t flags;         /* DPX_OUT_* */
+} dpx_params;
+
+/* Same layout as the reference's seqPair (c++/parseInput.h:22-29). */
+typedef struct {
+    int32_t referenceIdx;
+    int32_t referenceSize;
+    int32_t queryIdx;
+    int32_t querySize;
+} dpx_seq_pair;
+
+/* Same fields as the reference's inputInfo (c++/parseInput.h:9-20). */
+typedef struct {
+    size_t numPairs;
+    size_t numBytes;
+    size_t numCells;
+    size_t minReferenceLength;
+    size_t minQueryLength;
+    size_t maxReferenceLength;
+    size_t maxQueryLength;
+    double avgReferenceLength;
+    double avgQueryLength;
+} dpx_input_info;
+
+typedef struct dpx_ctx   dpx_ctx;     /* one device, its streams and workspaces */
+typedef struct dpx_batch dpx_batch;   /* a set of pairs resident in HBM + its results */
+
+/* ---- library ------------------------------------------------------------------------ */
+int         dpx_abi_version(void);
+const char* dpx_strerror(int status);
+/* Number of visible CUDA devices (0 without a driver/GPU; never fails). */
+int         dpx_device_count(void);
+
+/* ---- context -------------------------------------------------------------------------
+ * dpx_create: device = CUDA ordinal.  Replaces nothing in the reference (it has no device
+ * management: cuda/LNW/LinearNeedlemanWunschV19.cu:362-376 only prints the device count). */
+int         dpx_create(dpx_ctx** out, int device);
+void        dpx_destroy(dpx_ctx* ctx);
+/* Last CUDA / internal error text of this ctx (valid until the next call on it). */
+const char* dpx_last_error(const dpx_ctx* ctx);
+/* Optional: run on an externally owned cudaStream_t (e.g. torch's current stream) so that the
+ * caller's CUDA events bracket the kernels.  NULL restores the ctx's own stream. */
+int         dpx_set_stream(dpx_ctx* ctx, void* cuda_stream);
+
+/* ---- parser: replaces parseInput / cleanupParsedFile (c++/parseInput.cpp:9-119,140-143) --
+ * Same file format and outputs (blob with '\n' -> '\0', seqPair index, inputInfo) but returns
+ * DPX_ERR_IO / DPX_ERR_FORMAT instead of exit(1).  Both arrays are malloc'ed; release them with
+ * dpx_free.  numCells is accumulated in 64-bit (the reference multiplies two ints, :100). */
+int         dpx_parse_input(const char* path, dpx_seq_pair** pairs, char** sequences, dpx_input_info* info);
+void        dpx_free(void* p);
+
+/* ---- one-call alignment: replaces the per-pair `Aligner a(ref, query, i, weights); a.align();`
+ * loop of c++/main.cpp:237-252 for a whole batch.  Host buffers in, host buffers out
+ * (H2D, kernels, D2H inside).
+ *   sequences/n_bytes, pairs/n_pairs : the parseInput blob and index (borrowed)
+ *   scores       [n_pairs]    caller-owned
+ *   end_row_col  [2*n_pairs]  caller-owned or NULL
+ *   strings_blob, string_offsets : NULL unless DPX_OUT_STRINGS; library-allocated (dpx_free):
+ *       string k (0 REF, 1 REL, 2 QRY) of pair i is the NUL-terminated C string at
+ *       (*strings_blob) + (*string_offsets)[3*i + k]  — the exact bytes the reference prints on
+ *       the three lines after "<i> | <score>" (c++/LinearNeedlemanWunsch.cpp:207-213). */
+int         dpx_align_batch(dpx_ctx* ctx, const dpx_params* params,
+                            const char* sequences, size_t n_bytes,
+                            const dpx_seq_pair* pairs, size_t n_pairs,
+                            int32_t* scores, int32_t* end_row_col,
+                            char** strings_blob, size_t** string_offsets);
+
+/* ---- staged form of the same call (what bench.py times stage by stage) ------------------
+ * upload : H2D of blob + index, alphabet scan, 2-bit (4-bit escape) pack, length bucketing.
+ * run    : fill kernels (+ GPU backtrack when DPX_OUT_STRINGS) on the ctx stream; asynchronous.
+ * fetch  : waits for run, D2H of the selected outputs (same meaning as dpx_align_batch). */
+int         dpx_batch_upload(dpx_ctx* ctx, const char* sequences, size_t n_bytes,
+                             const dpx_seq_pair* pairs, size_t n_pairs, dpx_batch** out);
+int         dpx_batch_run(dpx_batch* b, const dpx_params* params);
+int         dpx_batch_sync(dpx_batch* b);
+int         dpx_batch_fetch(dpx_batch* b, int32_t* scores, int32_t* end_row_col,
+                            char** strings_blob, size_t** string_offsets);
+void        dpx_batch_free(dpx_batch* b);
+
+/* Statistics of the last dpx_batch_run on this batch (after dpx_batch_sync). */
+typedef struct {
+    double   fill_ms;          /* CUDA-event time of the fill kernel(s) */
+    double   backtrack_ms;     /* CUDA-event time of the backtrack kernel(s) (0 if none) */
+    double   total_ms;         /* first kernel -> last result byte resident on device */
+    uint64_t cells;            /* sum of Q*R (BSW: in-band cells) */
+    uint64_t traceback_bytes;  /* packed direction bytes written */
+    uint32_t kernel_launches;  /* our kernels launched by the run */
+    uint32_t kernel_id;        /* which fill kernel family ran (DPX_KERNEL_*) */
+} dpx_run_stats;
+int         dpx_batch_stats(const dpx_batch* b, dpx_run_stats* out);
+
+#define DPX_KERNEL_WAVEFRONT_S32  1u  /* warp-per-pair anti-diagonal wavefront, int32 */
+#define DPX_KERNEL_SHORT_S16X2    2u  /* thread-per-2-pairs, packed int16x2 DPX */
+#define DPX_KERNEL_BAND_S32       3u  /* banded anti-diagonal, band mapped onto one warp */
+#define DPX_KERNEL_TILED_S32      4u  /* multi-CTA tiled wavefront for one long pair */
+
+/* ---- one very long pair, score + end cell only (BASELINE config 5) ----------------------
+ * The reference cannot run this (8 B/cell full matrix). */
+int         dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params,
+                                const char* ref, size_t R, const char* qry, size_t Q,
+                                int32_t* score, int64_t* end_row, int64_t* end_col);
+
+/* ---- device self-test: the FakeDPX known-answer vectors (c++/testFakeDPX.cpp:10-113) run
+ * against the real sm_100a DPX instructions.  Returns the number of failing vectors (0 = pass)
+ * or a negative dpx_status. */
+int         dpx_selftest_dpx(dpx_ctx* ctx);
+/* Evaluates one DPX intrinsic (op = index into the list below) element-wise on the device:
+ * out[i] = op(a[i], b[i], c[i]); pred_hi/pred_lo receive the predicate outputs of the __vib* forms
+ * (pred_hi only for 32-bit forms).  Lets tests replay every FakeDPX vector on real hardware.
+ * op order: vimax3 {s32,s16x2,u32,u16x2}, vimin3 {same}, vimax_relu {s32,s16x2}, vimin_relu {s32,s16x2},
+ * vimax3_relu {s32,s16x2}, vimin3_relu {s32,s16x2}, vibmax {s32,u32}, vibmin {s32,u32},
+ * vibmax {s16x2,u16x2}, vibmin {s16x2,u16x2}, viaddmax {s32,u32}, viaddmin {s32,u32},
+ * viaddmax {s16x2,u16x2}, viaddmin {s16x2,u16x2}, viaddmax_relu s32, viaddmin_relu s32,
+ * viaddmax_relu s16x2, viaddmin_relu s16x2   (36 ops; c++/FakeDPX.hpp). */
+int         dpx_dpx_eval(dpx_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, int n,
+                         uint32_t* out, uint8_t* pred_hi, uint8_t* pred_lo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPXALIGN_H */

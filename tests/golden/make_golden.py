@@ -113,5 +113,26 @@ def main():
     print("done")
 
 
+
+
+def fakedpx_vectors():
+    """Known-answer vectors of the reference's only unit test (c++/testFakeDPX.cpp:10-113), extracted as
+    data: [{"fn": "__vimax3_s32", "args": [1,2,3], "want": 3, "preds": {"pred_hi": false, ...}}, ...]."""
+    import re
+    src = open("/root/reference/c++/testFakeDPX.cpp").read()
+    out = []
+    for m in re.finditer(r"assert\(FakeDPX::(\w+)\(([^)]*)\)\s*==\s*([-0-9a-fA-FxX]+)((?:\s*&&\s*!?\w+)*)\);", src):
+        fn, args, want, preds = m.groups()
+        vals = [int(a.strip(), 0) for a in args.split(",") if not a.strip().startswith("&")]
+        pm = {}
+        for t in re.findall(r"&&\s*(!?)(\w+)", preds):
+            pm[t[1]] = (t[0] != "!")
+        out.append({"fn": fn, "args": vals, "want": int(want, 0), "preds": pm})
+    return out
+
+
 if __name__ == "__main__":
     main()
+    with open(os.path.join(HERE, "fakedpx_vectors.json"), "w") as f:
+        json.dump(fakedpx_vectors(), f, indent=0)
+    print("fakedpx vectors:", len(fakedpx_vectors()))

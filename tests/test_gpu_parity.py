@@ -1,0 +1,182 @@
+"""GPU parity (the tests proper): libdpxalign through its C ABI against
+  (1) the golden fixtures produced by the compiled, unmodified reference classes (byte-identical text),
+  (2) the CPU oracle on seeded random / adversarial inputs (scores, end cells, strings),
+  (3) the reference's FakeDPX known-answer vectors replayed on the hardware DPX instructions.
+Integer work: the bar is bit-exact."""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from dpx_gpu_genomics_project_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SETS = sorted(os.path.basename(p)[:-7] for p in glob.glob(os.path.join(GOLD, "*.in.txt")))
+ALL = api.OUT_SCORE | api.OUT_END_COORDS | api.OUT_STRINGS
+KW = {api.LNW: dict(gap_open=-2), api.LSW: dict(gap_open=-2), api.ANW: dict(gap_open=-3, gap_extend=-1)}
+NAMES = {api.LNW: "LNW", api.ANW: "ANW", api.LSW: "LSW", api.BSW: "BSW"}
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = api.Engine(0)
+    yield e
+    e.close()
+
+
+def gpu_vs_oracle(eng, algo, blob, pairs, **w):
+    res = eng.align_batch(api.make_params(algo, flags=ALL, **w), blob, pairs)
+    s, e, t = ol.align_batch(ol.params(algo, **w), blob, pairs)
+    bad = np.flatnonzero(res.scores != s)
+    assert len(bad) == 0, f"score mismatch at pairs {bad[:10]}: gpu {res.scores[bad[:10]]} oracle {s[bad[:10]]}"
+    if algo in (api.LSW, api.BSW):
+        bad = np.flatnonzero((res.end_row_col != e).any(axis=1))
+        assert len(bad) == 0, f"end-cell mismatch at {bad[:10]}: gpu {res.end_row_col[bad[:5]]} oracle {e[bad[:5]]}"
+    for i, (a, b) in enumerate(zip(res.strings, t)):
+        assert a == b, f"pair {i}: strings differ\n gpu {a}\n orc {b}"
+    # score-only mode must give the same scores / end cells
+    res2 = eng.align_batch(api.make_params(algo, flags=api.OUT_SCORE | api.OUT_END_COORDS, **w), blob, pairs)
+    assert (res2.scores == s).all()
+    if algo in (api.LSW, api.BSW):
+        assert (res2.end_row_col == e).all()
+
+
+@pytest.mark.parametrize("name", SETS)
+@pytest.mark.parametrize("algo", [api.LNW, api.LSW, api.ANW])
+def test_golden_text_is_byte_identical(eng, name, algo):
+    p = api.parse_input(os.path.join(GOLD, f"{name}.in.txt"))
+    res = eng.align_batch(api.make_params(algo, flags=ALL, **KW[algo]), p.sequences, p.pairs)
+    want = open(os.path.join(GOLD, f"{name}.{NAMES[algo]}.out.txt"), "rb").read()
+    assert res.text() == want
+
+
+def random_pairs(seed, n, maxlen, alphabets=(b"0", b"01", b"0123", b"01234")):
+    rng = synth.Rng(seed)
+    pairs = []
+    for k in range(n):
+        alpha = alphabets[k % len(alphabets)]
+        R = int(rng.below(1, maxlen + 1)[0])
+        r = synth.random_seq(rng, R, alpha)
+        q = synth.mutate(rng, r, 0.08, 0.03, 0.03, alpha) if k % 2 else synth.random_seq(rng, int(rng.below(1, maxlen + 1)[0]), alpha)
+        pairs.append((r, q))
+    return ol.parse_image(synth.pairs_to_file_bytes(pairs))
+
+
+@pytest.mark.parametrize("algo,w", [
+    (api.LNW, dict(match=3, mismatch=-1, gap_open=-2)), (api.LNW, dict(match=1, mismatch=-3, gap_open=-1)),
+    (api.LSW, dict(match=3, mismatch=-1, gap_open=-2)), (api.LSW, dict(match=2, mismatch=-2, gap_open=-1)),
+    (api.ANW, dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1)), (api.ANW, dict(match=2, mismatch=-1, gap_open=0, gap_extend=-2)),
+    (api.ANW, dict(match=5, mismatch=-4, gap_open=-10, gap_extend=-1)),
+])
+def test_random_pairs_vs_oracle(eng, algo, w):
+    blob, pairs = random_pairs(0xC0FFEE + algo, 300, 90)
+    gpu_vs_oracle(eng, algo, blob, pairs, **w)
+
+
+@pytest.mark.parametrize("algo", [api.LNW, api.LSW, api.ANW])
+def test_multi_stripe_lengths_vs_oracle(eng, algo):
+    """Lengths that cross several 128/256-row stripes and are not multiples of 32."""
+    blob, pairs = random_pairs(0xBEEF + algo, 24, 700, alphabets=(b"0123", b"01"))
+    gpu_vs_oracle(eng, algo, blob, pairs, **KW[algo])
+
+
+@pytest.mark.parametrize("band", [0, 1, 3, 17, 64, 1000])
+def test_banded_vs_oracle(eng, band):
+    blob, pairs = random_pairs(0xBA9D + band, 120, 200, alphabets=(b"0123", b"01", b"0"))
+    gpu_vs_oracle(eng, api.BSW, blob, pairs, match=3, mismatch=-1, gap_open=-2, band=band)
+
+
+def test_banded_full_band_equals_lsw_golden(eng):
+    p = api.parse_input(os.path.join(GOLD, "shapes.in.txt"))
+    res = eng.align_batch(api.make_params(api.BSW, band=600, flags=ALL), p.sequences, p.pairs)
+    assert res.text() == open(os.path.join(GOLD, "shapes.LSW.out.txt"), "rb").read()
+
+
+def test_banded_python_prototype_scores(eng):
+    for c in json.load(open(os.path.join(GOLD, "bsw_python_scores.json"))):
+        blob, pairs = ol.parse_image(synth.pairs_to_file_bytes([(c["ref"].encode(), c["qry"].encode())]))
+        res = eng.align_batch(api.make_params(api.BSW, band=c["band"], flags=api.OUT_SCORE), blob, pairs)
+        assert int(res.scores[0]) == c["score"]
+
+
+def test_empty_batch_and_empty_sequences(eng):
+    res = eng.align_batch(api.make_params(api.LNW, flags=ALL), np.zeros(0, np.uint8), np.zeros(0, api.PAIR_DTYPE))
+    assert len(res.scores) == 0 and res.strings == []
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes([(b"", b""), (b"0123", b""), (b"", b"3210")]))
+    for algo in (api.LNW, api.LSW, api.ANW):
+        gpu_vs_oracle(eng, algo, blob, pairs, **KW[algo])
+
+
+def test_reference_style_classes_print_reference_bytes(eng, capsysbinary):
+    p = api.parse_input(os.path.join(GOLD, "adversarial.in.txt"))
+    want = open(os.path.join(GOLD, "adversarial.LNW.out.txt"), "rb").read()
+    for i in range(12):                          # c++/main.cpp:243-246
+        pr = p.pairs[i]
+        r = p.sequences[pr["referenceIdx"]: pr["referenceIdx"] + pr["referenceSize"]].tobytes()
+        q = p.sequences[pr["queryIdx"]: pr["queryIdx"] + pr["querySize"]].tobytes()
+        api.LinearNeedlemanWunsch(r, q, i, 3, -1, -2).align()
+    out = capsysbinary.readouterr().out
+    assert want.startswith(out) and out.count(b"\n") == 48
+
+
+# ---- DPX instruction semantics on hardware ----------------------------------------------------------
+OPS = ["__vimax3_s32", "__vimax3_s16x2", "__vimax3_u32", "__vimax3_u16x2", "__vimin3_s32", "__vimin3_s16x2", "__vimin3_u32",
+       "__vimin3_u16x2", "__vimax_s32_relu", "__vimax_s16x2_relu", "__vimin_s32_relu", "__vimin_s16x2_relu",
+       "__vimax3_s32_relu", "__vimax3_s16x2_relu", "__vimin3_s32_relu", "__vimin3_s16x2_relu",
+       "__vibmax_s32", "__vibmax_u32", "__vibmin_s32", "__vibmin_u32", "__vibmax_s16x2", "__vibmax_u16x2",
+       "__vibmin_s16x2", "__vibmin_u16x2", "__viaddmax_s32", "__viaddmax_u32", "__viaddmin_s32", "__viaddmin_u32",
+       "__viaddmax_s16x2", "__viaddmax_u16x2", "__viaddmin_s16x2", "__viaddmin_u16x2",
+       "__viaddmax_s32_relu", "__viaddmin_s32_relu", "__viaddmax_s16x2_relu", "__viaddmin_s16x2_relu"]
+
+
+def test_fakedpx_known_answers_on_hardware(eng):
+    vec = json.load(open(os.path.join(GOLD, "fakedpx_vectors.json")))
+    assert len(vec) >= 70
+    assert eng.selftest() == 0
+    for v in vec:
+        op = OPS.index(v["fn"])
+        args = [x & 0xFFFFFFFF for x in v["args"]] + [0] * (3 - len(v["args"]))
+        out, ph, pl = eng.dpx_eval(op, [args[0]], [args[1]], [args[2]])
+        assert int(out[0]) == v["want"] & 0xFFFFFFFF, v
+        if "pred_hi" in v["preds"]:
+            assert bool(ph[0]) == v["preds"]["pred_hi"], v
+        if "pred_low" in v["preds"]:
+            assert bool(pl[0]) == v["preds"]["pred_low"], v
+
+
+def _s16(x):
+    x = np.asarray(x, dtype=np.uint32)
+    lo = (x & 0xFFFF).astype(np.int64); hi = (x >> 16).astype(np.int64)
+    return np.where(lo >= 32768, lo - 65536, lo), np.where(hi >= 32768, hi - 65536, hi)
+
+
+def test_s16x2_ops_random_vs_numpy(eng):
+    """The reference's FakeDPX never tests the s16x2 add/relu variants (c++/testFakeDPX.cpp:108-113 stop at u32);
+    check the ones our kernels use against their definition (per-half, wrap-around add)."""
+    rng = np.random.default_rng(5)
+    n = 4096
+    a = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    c = rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    (al, ah), (bl, bh), (cl, ch) = _s16(a), _s16(b), _s16(c)
+
+    def wrap(x):
+        return ((x + 32768) % 65536) - 32768
+
+    def pack(lo, hi):
+        return ((hi.astype(np.int64) & 0xFFFF) << 16 | (lo.astype(np.int64) & 0xFFFF)).astype(np.uint32)
+
+    out, _, _ = eng.dpx_eval(OPS.index("__viaddmax_s16x2"), a, b, c)
+    assert (out == pack(np.maximum(wrap(al + bl), cl), np.maximum(wrap(ah + bh), ch))).all()
+    out, _, _ = eng.dpx_eval(OPS.index("__viaddmax_s16x2_relu"), a, b, c)
+    assert (out == pack(np.maximum(np.maximum(wrap(al + bl), cl), 0), np.maximum(np.maximum(wrap(ah + bh), ch), 0))).all()
+    out, _, _ = eng.dpx_eval(OPS.index("__vimax3_s16x2_relu"), a, b, c)
+    assert (out == pack(np.maximum(np.maximum(np.maximum(al, bl), cl), 0), np.maximum(np.maximum(np.maximum(ah, bh), ch), 0))).all()
+    out, ph, pl = eng.dpx_eval(OPS.index("__vibmax_s16x2"), a, b, c)
+    assert (out == pack(np.maximum(al, bl), np.maximum(ah, bh))).all()
+    assert (ph.astype(bool) == (ah >= bh)).all() and (pl.astype(bool) == (al >= bl)).all()

@@ -12,6 +12,8 @@
 #include "dpx_ops.cuh"
 #include "wavefront.cuh"
 #include "backtrack.cuh"
+#include "pack.cuh"
+#include "shortread.cuh"
 
 using namespace dpx;
 
@@ -37,6 +39,12 @@ struct dpx_batch {
     uint8_t* d_blob = nullptr;
     dpx_seq_pair* d_pairs = nullptr;
     int32_t* d_order = nullptr;
+    // 2-bit packed copy (pack.cuh); n_symbols = distinct sequence bytes in the batch
+    uint32_t* d_packed = nullptr;
+    unsigned long long* d_pk_off = nullptr;
+    int n_symbols = 0;
+    bool packed2 = false;
+    std::vector<int32_t> h_order; bool order_ready = false; bool uniform = true;
     // device outputs
     int32_t* d_scores = nullptr;
     int32_t* d_end_rc = nullptr;
@@ -231,7 +239,7 @@ void dpx_batch_free(dpx_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->ctx->stream);
-    cudaFree(b->d_blob); cudaFree(b->d_pairs); cudaFree(b->d_order); cudaFree(b->d_scores); cudaFree(b->d_end_rc);
+    cudaFree(b->d_blob); cudaFree(b->d_pairs); cudaFree(b->d_order); cudaFree(b->d_packed); cudaFree(b->d_pk_off); cudaFree(b->d_scores); cudaFree(b->d_end_rc);
     cudaFree(b->d_tb); cudaFree(b->d_tb_off); cudaFree(b->d_strings); cudaFree(b->d_str_off); cudaFree(b->d_str_start);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_begin) cudaEventDestroy(b->ev_begin);
@@ -267,6 +275,35 @@ int dpx_batch_upload(dpx_ctx* ctx, const char* sequences, size_t n_bytes, const 
     if (n_bytes) CUB(cudaMemcpyAsync(b->d_blob, sequences, n_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (n_pairs) CUB(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->stream));
     CUB(cudaEventCreate(&b->ev_begin)); CUB(cudaEventCreate(&b->ev_end));
+    b->uniform = (b->max_q == b->min_q && b->max_r == b->min_r);
+    if (n_pairs) {
+        // alphabet scan -> rank codes -> 2-bit pack when <= 4 symbols (pack.cuh)
+        uint32_t* d_present = nullptr;
+        CUB(cudaMalloc(&d_present, 8 * sizeof(uint32_t)));
+        CUB(cudaMemsetAsync(d_present, 0, 8 * sizeof(uint32_t), ctx->stream));
+        const int pblocks = (int)std::min<size_t>((n_pairs + 7) / 8, (size_t)ctx->sm_count * 8);
+        present_kernel<<<pblocks, 256, 0, ctx->stream>>>(b->d_blob, b->d_pairs, (int)n_pairs, d_present);
+        uint32_t present[8];
+        CUB(cudaMemcpyAsync(present, d_present, sizeof(present), cudaMemcpyDeviceToHost, ctx->stream));
+        // word offsets of the packed copy while the scan runs
+        std::vector<unsigned long long> pk_off(n_pairs + 1, 0);
+        for (size_t i = 0; i < n_pairs; ++i)
+            pk_off[i + 1] = pk_off[i] + (unsigned long long)((pairs[i].referenceSize + 15) >> 4) + (unsigned long long)((pairs[i].querySize + 15) >> 4);
+        CUB(cudaStreamSynchronize(ctx->stream));
+        cudaFree(d_present);
+        PackLut lut{}; int nsym = 0;
+        for (int c = 0; c < 256; ++c) if (present[c >> 5] >> (c & 31) & 1u) lut.code[c] = (uint8_t)(nsym++ & 0xff);
+        b->n_symbols = nsym;
+        if (nsym <= 4) {
+            CUB(cudaMalloc(&b->d_packed, std::max<size_t>(pk_off[n_pairs], 1) * sizeof(uint32_t)));
+            CUB(cudaMalloc(&b->d_pk_off, (n_pairs + 1) * sizeof(unsigned long long)));
+            CUB(cudaMemcpyAsync(b->d_pk_off, pk_off.data(), (n_pairs + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+            pack2_kernel<<<pblocks, 256, 0, ctx->stream>>>(b->d_blob, b->d_pairs, (int)n_pairs, b->d_pk_off, b->d_packed, lut);
+            CUB(cudaGetLastError());
+            CUB(cudaStreamSynchronize(ctx->stream));      // pk_off (host vector) must outlive the copy
+            b->packed2 = true;
+        }
+    }
 #undef CUB
     *out = b;
     return DPX_OK;
@@ -303,6 +340,46 @@ static int dispatch_wf(dpx_ctx* ctx, int algo, bool tb, int K, const WfArgs& a, 
         case DPX_ALGO_BSW: return tb ? dispatch_wf_k<DPX_ALGO_BSW, true>(ctx, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_BSW, false>(ctx, K, a, blocks, query_only, slots, blocks_out);
     }
     return DPX_ERR_INVALID;
+}
+
+template <int G, int K>
+static int run_short(dpx_ctx* ctx, dpx_batch* b, const dpx_params* p, SrArgs a, bool track, bool xormode) {
+    const int gpb = 128 / G;
+    a.bnd_stride = b->max_r + G + 2;
+    a.rsel_stride = (b->max_r + 2 * G + 2 + 1) & ~1;
+    const size_t smem = (size_t)gpb * ((size_t)a.bnd_stride * 4 + (size_t)a.rsel_stride * 2);
+    auto launch = [&](auto kern) -> int {
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+        if (per_sm < 1) { ctx->err = "short-read kernel does not fit on an SM"; return DPX_ERR_RANGE; }
+        const int warps_needed = (a.n_slots + (32 / G) - 1) / (32 / G);
+        int blocks = std::min(ctx->sm_count * per_sm, (warps_needed + 3) / 4);
+        if (blocks < 1) blocks = 1;
+        kern<<<blocks, 128, smem, ctx->stream>>>(a);
+        CU(cudaGetLastError());
+        return DPX_OK;
+    };
+    if (track) return xormode ? launch(sr_lsw_kernel<G, K, true, true>) : launch(sr_lsw_kernel<G, K, true, false>);
+    return xormode ? launch(sr_lsw_kernel<G, K, false, true>) : launch(sr_lsw_kernel<G, K, false, false>);
+}
+
+// Eligibility of the packed int16x2 short-read kernel (shortread.cuh).
+static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, bool* xormode, int* kbits_out) {
+    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || !b->packed2) return false;
+    const int m = p->match, x = p->mismatch, g = p->gap_open;
+    if (!(m > 0 && x < 0 && g < 0)) return false;                 // pads must stay strictly below real cells
+    if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
+    if (b->max_r > 4096 || b->max_q > 65535) return false;
+    const int B = std::max(2, -g);
+    // position bits: (Hmax + B) << k < 32768; blocks of 2^k steps, at most 256 blocks per pass
+    const long long top = (long long)m * std::min(b->max_r, b->max_q) + B;
+    int k = 0;
+    while (k < 8 && (top << (k + 1)) < 32768) ++k;
+    if (k < 4) return false;
+    if (((long long)b->max_r + 16) >> k >= 255) return false;
+    *B_out = B; *xormode = (x - g < 0); *kbits_out = k;
+    return true;
 }
 
 static uint64_t inband_cells(long long Q, long long R, long long W) {
@@ -347,19 +424,61 @@ int dpx_batch_run(dpx_batch* b, const dpx_params* p) {
     CU(cudaEventRecord(b->ev_begin, ctx->stream));
     if (n == 0) { CU(cudaEventRecord(b->ev_end, ctx->stream)); return DPX_OK; }
 
-    // ---- schedule: longest pairs first when lengths differ ------------------------------------
-    std::vector<int32_t> order;
-    const bool uniform = (b->max_q == b->min_q && b->max_r == b->min_r);
-    if (!uniform) {
-        order.resize(n);
-        std::iota(order.begin(), order.end(), 0);
+    // ---- schedule: longest pairs first when lengths differ (computed once per batch) ------------------
+    const bool uniform = b->uniform;
+    if (!uniform && !b->order_ready) {
+        b->h_order.resize(n);
+        std::iota(b->h_order.begin(), b->h_order.end(), 0);
         const auto& hp = b->h_pairs;
-        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) {
-            return (uint64_t)hp[x].querySize * hp[x].referenceSize > (uint64_t)hp[y].querySize * hp[y].referenceSize; });
+        // key: query length first (rows decide the short-read kernel's passes), then reference length
+        std::stable_sort(b->h_order.begin(), b->h_order.end(), [&](int32_t x, int32_t y) {
+            if (hp[x].querySize != hp[y].querySize) return hp[x].querySize > hp[y].querySize;
+            return hp[x].referenceSize > hp[y].referenceSize; });
         if (!b->d_order) CU(cudaMalloc(&b->d_order, n * sizeof(int32_t)));
-        CU(cudaMemcpyAsync(b->d_order, order.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(b->d_order, b->h_order.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        b->order_ready = true;
+        CU(cudaEventRecord(b->ev_begin, ctx->stream));
     }
+    const std::vector<int32_t>& order = b->h_order;
     auto pid_at = [&](size_t pos) -> size_t { return uniform ? pos : (size_t)order[pos]; };
+
+    // ---- short-read path: packed int16x2 DPX kernel (score / end cell only) -------------------------
+    {
+        int B = 0, kbits = 0; bool xormode = false;
+        if (short_eligible(b, p, &B, &xormode, &kbits)) {
+            const int g = p->gap_open;
+            SrArgs sa{};
+            sa.packed = b->d_packed; sa.pk_off = b->d_pk_off; sa.pairs = b->d_pairs; sa.order = uniform ? nullptr : b->d_order;
+            sa.n_pairs = (int)n; sa.n_slots = (int)((n + 1) / 2);
+            const int ms = p->match - g, xs = p->mismatch - g;
+            uint8_t tab[8];
+            for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)(int8_t)xs;
+            tab[xormode ? 0 : 3] = (uint8_t)(int8_t)ms;
+            sa.lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
+            sa.lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
+            auto pk = [](int v) { return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16); };
+            sa.one = 1u; sa.kbits = kbits; sa.kmul = 1u << kbits; sa.B = B; sa.B2 = pk(B); sa.Bg2 = pk(B + g);
+            sa.G2 = (uint32_t)(g & 0xffff) | ((uint32_t)((g - 1) & 0xffff) << 16);
+            sa.scores = b->d_scores; sa.end_rc = b->d_end_rc;
+            sa.counter = ctx->counters;
+            CU(cudaMemsetAsync(sa.counter, 0, sizeof(unsigned int), ctx->stream));
+            const bool track = (p->flags & DPX_OUT_END_COORDS) != 0;
+            cudaEvent_t s, e;
+            CU(cudaEventCreate(&s)); CU(cudaEventCreate(&e));
+            b->ev.push_back(s); b->ev.push_back(e); b->ev_kind.push_back(0);
+            CU(cudaEventRecord(s, ctx->stream));
+            int st;
+            if (b->max_q <= 64) st = run_short<8, 8>(ctx, b, p, sa, track, xormode);
+            else                st = run_short<8, 19>(ctx, b, p, sa, track, xormode);
+            if (st) return st;
+            CU(cudaEventRecord(e, ctx->stream));
+            b->stats.kernel_launches = 1;
+            b->stats.kernel_id = DPX_KERNEL_SHORT_S16X2;
+            CU(cudaEventRecord(b->ev_end, ctx->stream));
+            return DPX_OK;
+        }
+    }
 
     // ---- traceback + string slots; chunks of schedule positions under the traceback budget --------
     std::vector<unsigned long long> tb_off;

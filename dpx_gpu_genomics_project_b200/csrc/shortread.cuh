@@ -1,0 +1,236 @@
+// shortread.cuh — LinearSmithWaterman score (+ end cell) for batches of short pairs: packed int16x2 DPX.
+//
+// Reference semantics: c++/LinearSmithWaterman.cpp:70-114 (recurrence, ReLU) and :145-157 (end cell =
+// first strict maximum in row-major order).  No traceback here (the wavefront kernels do that).
+//
+// Mapping.  A group of G lanes aligns TWO pairs at once, pair A in the low and pair B in the high int16
+// half of every register (both padded to common dimensions with never-matching pad symbols).  Lane g of
+// the group keeps K consecutive query rows in registers and sweeps the reference columns one step behind
+// lane g-1 (anti-diagonal wavefront of K-row blocks); the bottom row of a lane reaches the next lane with
+// one __shfl_up per column step, i.e. one shuffle per K cell-pairs.  G*K rows are one pass; longer queries
+// take several passes with the last lane's row handed over through a per-group shared-memory row.
+//
+// Arithmetic (per cell-pair; measured pipe model in profiles/: ALU/DPX 64 lanes/clk/SM, FMA pipe another 64):
+//   x   = qsel + rsel                  nibble-wise q + (3 - r): equals 3 iff the bases match   (IADD, either pipe)
+//                                      [XORMODE: x = qsel ^ rsel, 0 iff match — LOP3, ALU only; used when
+//                                       mismatch - gap < 0 so the table needs the sign-replicating selector]
+//   s   = prmt(LUT, x)                 8-entry byte table -> packed (score - gap) per int16 half (ALU)
+//   e   = __viaddmax_s16x2(diag, s, left) max(diag + s, left)   — independent of the row above (VIADDMNMX.S16x2)
+//   h   = __vimax3_s16x2(e, up, B2)       ReLU against the bias B (= zero)                     (VIMNMX3.S16x2)
+//   hg  = h + G2                       plain 32-bit add: all values carry a bias B >= -gap, so the low half
+//                                      always carries into the high half and G2's high half is gap-1  (either pipe)
+//   key = h * 2^k + code(step)         one IMAD on the FMA pipe: the (positive, biased) score moves up k bits in
+//                                      both halves and the low k bits take 2^k-1 - (step mod 2^k)
+//   best= max.s16x2(best, key)         per row register: highest score, earliest step wins      (VIMNMX.S16x2)
+//   Every 2^k steps (warp-uniform) the K row registers are folded into one 32-bit key per pair and lane,
+//   (score | 31-row | 255-block | code): higher score, then smaller row, then earlier step — exactly the
+//   reference's first-strict-max-in-row-major rule; lanes / passes are merged with the same order.
+// => 4 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells).
+// Registers hold hg = H + gap + B ("already gapped"), which is what the right and lower neighbours need;
+// the diagonal neighbour wants H, so the table holds score - gap.
+#pragma once
+#include "common.cuh"
+
+namespace dpx {
+
+struct SrArgs {
+    const uint32_t* packed;              // 2-bit packed sequences (pack.cuh)
+    const unsigned long long* pk_off;    // [n_pairs+1]
+    const dpx_seq_pair* pairs;
+    const int32_t* order;                // schedule (nullable = identity); slot s = schedule positions 2s, 2s+1
+    int n_pairs, n_slots;
+    uint32_t lut_lo, lut_hi;             // prmt table: byte 3 (XORMODE: byte 0) = match - gap, others = mismatch - gap
+    uint32_t B2, Bg2, G2;                // packed bias, bias + gap, and the add constant ((gap-1)<<16 | gap&0xffff)
+    int B;
+    uint32_t one;                        // 1 (run-time constant for the FMA-pipe adds)
+    uint32_t kmul;                       // 1 << kbits, passed as data so the shift stays an FMA-pipe IMAD
+    int kbits;                           // position bits per int16 key: (Hmax + B) << kbits must stay < 32768
+    int32_t* scores;
+    int32_t* end_rc;                     // nullable
+    unsigned int* counter;
+    int bnd_stride, rsel_stride;         // per-group shared-memory strides (uint32 / uint16 entries)
+};
+
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));   // generic mode: nibble msb = replicate sign
+    return d;
+}
+
+// Integer ops pinned to the FMA pipe: mad.lo with a run-time multiplier of 1 (`one` comes from the kernel
+// arguments, so ptxas cannot fold it into an ALU-pipe add / select).  The ALU pipe (DPX, PRMT) is the
+// bottleneck of this kernel; the FMA pipe issues in the other half of the SMSP's cycles.
+__device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t get2(const uint32_t* __restrict__ w, int k) { return (w[k >> 4] >> (2 * (k & 15))) & 3u; }
+
+template <int G, int K, bool TRACK, bool XORMODE>
+__global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
+    extern __shared__ uint32_t sr_smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int GPW = 32 / G;                    // groups per warp
+    constexpr int GPB = 128 / G;                   // groups per block
+    const int lane = threadIdx.x & 31, gl = lane % G, gw = lane / G;
+    const int gib = threadIdx.x / G;
+    uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride;
+    uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(sr_smem + (size_t)GPB * a.bnd_stride) + (size_t)gib * a.rsel_stride;
+    const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, lut_lo = a.lut_lo, lut_hi = a.lut_hi, one = a.one;
+    const int kmask = (1 << a.kbits) - 1;
+    const uint32_t kmul = a.kmul;
+
+    for (;;) {
+        int base = 0;
+        if (lane == 0) base = (int)atomicAdd(a.counter, (unsigned)GPW);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= a.n_slots) break;
+        const int slot = base + gw;
+        int pa = -1, pb = -1, RA = 0, QA = 0, RB = 0, QB = 0;
+        const uint32_t *refA = a.packed, *qryA = a.packed, *refB = a.packed, *qryB = a.packed;
+        if (slot < a.n_slots) {
+            pa = a.order ? a.order[2 * slot] : 2 * slot;
+            const dpx_seq_pair p = a.pairs[pa];
+            RA = p.referenceSize; QA = p.querySize;
+            refA = a.packed + a.pk_off[pa]; qryA = refA + ((RA + 15) >> 4);
+            if (2 * slot + 1 < a.n_pairs) {
+                pb = a.order ? a.order[2 * slot + 1] : 2 * slot + 1;
+                const dpx_seq_pair q = a.pairs[pb];
+                RB = q.referenceSize; QB = q.querySize;
+                refB = a.packed + a.pk_off[pb]; qryB = refB + ((RB + 15) >> 4);
+            }
+        }
+        const int Rw = __reduce_max_sync(FULL, max(RA, RB));
+        const int Qw = __reduce_max_sync(FULL, max(QA, QB));
+        const int passes = (Qw + G * K - 1) / (G * K);
+        const int nsteps2 = (Rw + G - 1 + 1) & ~1;          // column steps incl. pipeline drain, rounded to even
+
+        // ---- per-group column table: entry e <-> column j = e - (G-1); pads never match ---------------
+        __syncwarp();
+        for (int e = gl; e < Rw + 2 * G + 2; e += G) {
+            const int j = e - (G - 1);
+            // ADD mode: c = 3 - r (pad 4); q + c == 3 iff match; sums stay <= 8 (8 -> sign-replicate of byte 0 = 0,
+            //   only where row AND column are pads); every table byte is >= 0 so the high byte is the constant
+            //   selector 8 (sign of byte 0) and no nibble can carry into the other pair's half.
+            // XOR mode: r (pad 5) with the sign-replicating copy r|8 in the odd nibbles; q ^ r == 0 iff match.
+            uint32_t cA, cB;
+            if (XORMODE) {
+                cA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 5u;
+                cB = (j >= 1 && j <= RB) ? get2(refB, j - 1) : 5u;
+                rsel[e] = (uint16_t)(cA | ((cA | 8u) << 4) | (cB << 8) | ((cB | 8u) << 12));
+            } else {
+                cA = (j >= 1 && j <= RA) ? 3u - get2(refA, j - 1) : 4u;
+                cB = (j >= 1 && j <= RB) ? 3u - get2(refB, j - 1) : 4u;
+                rsel[e] = (uint16_t)(cA | 0x80u | (cB << 8) | 0x8000u);
+            }
+        }
+        if (passes > 1)
+            for (int e = gl; e < Rw + G + 2; e += G) bnd[e] = Bg2;
+        __syncwarp();
+
+        int bestA = 0, rowA = 0, colA = 0, bestB = 0, rowB = 0, colB = 0;
+
+        for (int p = 0; p < passes; ++p) {
+            const int i0 = p * G * K + gl * K;                  // matrix row of register row r is i0 + r + 1
+            uint32_t qsel[K], hgA[K], hgB[K], best[K];
+            uint32_t laneKeyA = 0, laneKeyB = 0;                 // score<<(13+k) | (31-r)<<(8+k) | (255-blk)<<k | code
+            #pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int i = i0 + r;                            // 0-based query index
+                const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
+                const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
+                qsel[r] = XORMODE ? (qa * 0x11u + qb * 0x1100u) : (qa | (qb << 8));
+                hgA[r] = Bg2; hgB[r] = Bg2; best[r] = 0;
+            }
+            uint32_t best2 = B2;                                 // !TRACK: one running max for all rows
+            uint32_t bot = Bg2, topprev = Bg2;
+            const bool more = (p + 1 < passes);
+
+#define DPX_SR_STEP(S, OLD, NEW)                                                                         \
+            {                                                                                            \
+                const int j = (S) - gl + 1;                                                              \
+                uint32_t top = __shfl_up_sync(FULL, bot, 1, G);                                          \
+                if (gl == 0) top = (p == 0) ? Bg2 : bnd[j];                                              \
+                const uint32_t rs = rsel[(S) - gl + G];                                                  \
+                const uint32_t cs2 = (uint32_t)(kmask - ((S) & kmask)) * 0x00010001u;                    \
+                uint32_t upg = top, diag = topprev;                                                      \
+                topprev = top;                                                                           \
+                _Pragma("unroll")                                                                        \
+                for (int r = 0; r < K; ++r) {                                                            \
+                    const uint32_t x = XORMODE ? (qsel[r] ^ rs) : fma_add(qsel[r], one, rs);             \
+                    const uint32_t sc = prmt_b32(lut_lo, lut_hi, x);                                     \
+                    const uint32_t e = __viaddmax_s16x2(diag, sc, OLD[r]);   /* off the row chain */     \
+                    const uint32_t h = __vimax3_s16x2(e, upg, B2);           /* chain: h -> hg -> h */   \
+                    diag = OLD[r];                                                                       \
+                    NEW[r] = fma_add(h, one, G2);                                                        \
+                    upg = NEW[r];                                                                        \
+                    if (TRACK) {                                                                         \
+                        const uint32_t key = fma_add(h, kmul, cs2);        /* IMAD, FMA pipe */          \
+                        best[r] = __vmaxs2(best[r], key);                                                \
+                    } else {                                                                             \
+                        best2 = __vmaxs2(best2, h);                                                       \
+                    }                                                                                    \
+                }                                                                                        \
+                bot = NEW[K - 1];                                                                        \
+                if (gl == G - 1 && more && j >= 1) bnd[j] = bot;                                         \
+            }
+
+            const int bs = kmask + 1;                            // steps per position block (even)
+            for (int blk = 0; blk * bs < nsteps2; ++blk) {
+                const int s_end = min((blk + 1) * bs, nsteps2);
+                #pragma unroll 1
+                for (int s = blk * bs; s < s_end; s += 2) {
+                    DPX_SR_STEP(s, hgA, hgB)
+                    DPX_SR_STEP(s + 1, hgB, hgA)
+                }
+                if (TRACK) {
+                    // fold the row registers into the lane keys (warp-uniform point; ~12 ALU ops per row per 2^k steps)
+                    const uint32_t tagb = (uint32_t)(255 - blk) << a.kbits;
+                    #pragma unroll
+                    for (int r = 0; r < K; ++r) {
+                        const uint32_t tag = tagb | ((uint32_t)(31 - r) << (8 + a.kbits));
+                        const uint32_t lo = best[r] & 0xffffu, hi = best[r] >> 16;
+                        laneKeyA = max(laneKeyA, ((lo & ~(uint32_t)kmask) << 13) | tag | (lo & (uint32_t)kmask));
+                        laneKeyB = max(laneKeyB, ((hi & ~(uint32_t)kmask) << 13) | tag | (hi & (uint32_t)kmask));
+                    }
+                }
+            }
+#undef DPX_SR_STEP
+
+            if (TRACK) {
+                // decode: step of the maximum = block * 2^k + (2^k-1 - code); column = step - lane + 1
+                const int hA = (int)(laneKeyA >> (13 + a.kbits)) - a.B;
+                const int hB = (int)(laneKeyB >> (13 + a.kbits)) - a.B;
+                if (hA > bestA) {
+                    bestA = hA; rowA = i0 + (31 - (int)((laneKeyA >> (8 + a.kbits)) & 31u)) + 1;
+                    colA = (255 - (int)((laneKeyA >> a.kbits) & 255u)) * bs + (kmask - (int)(laneKeyA & (uint32_t)kmask)) - gl + 1;
+                }
+                if (hB > bestB) {
+                    bestB = hB; rowB = i0 + (31 - (int)((laneKeyB >> (8 + a.kbits)) & 31u)) + 1;
+                    colB = (255 - (int)((laneKeyB >> a.kbits) & 255u)) * bs + (kmask - (int)(laneKeyB & (uint32_t)kmask)) - gl + 1;
+                }
+            } else {
+                bestA = max(bestA, (int)(short)(best2 & 0xffffu) - a.B);
+                bestB = max(bestB, (int)(short)(best2 >> 16) - a.B);
+            }
+            __syncwarp();
+        }
+
+        // ---- reduce over the lanes of the group: higher score, then smaller row ---------------------------
+        #pragma unroll
+        for (int off = G / 2; off > 0; off >>= 1) {
+            const int sA = __shfl_xor_sync(FULL, bestA, off), rA_ = __shfl_xor_sync(FULL, rowA, off), cA_ = __shfl_xor_sync(FULL, colA, off);
+            const int sB = __shfl_xor_sync(FULL, bestB, off), rB_ = __shfl_xor_sync(FULL, rowB, off), cB_ = __shfl_xor_sync(FULL, colB, off);
+            if (sA > bestA || (sA == bestA && rA_ < rowA)) { bestA = sA; rowA = rA_; colA = cA_; }
+            if (sB > bestB || (sB == bestB && rB_ < rowB)) { bestB = sB; rowB = rB_; colB = cB_; }
+        }
+        if (gl == 0) {
+            if (pa >= 0) { a.scores[pa] = bestA; if (TRACK && a.end_rc) { a.end_rc[2 * pa] = rowA; a.end_rc[2 * pa + 1] = colA; } }
+            if (pb >= 0) { a.scores[pb] = bestB; if (TRACK && a.end_rc) { a.end_rc[2 * pb] = rowB; a.end_rc[2 * pb + 1] = colB; } }
+        }
+    }
+}
+
+}  // namespace dpx

@@ -137,3 +137,26 @@ def mutated_fixed_file_bytes(n_pairs: int, R: int, Q: int, seed: int, sub: float
         img[s:s + n, 2:2 + R] = ref
         img[s:s + n, 3 + R:3 + R + Q] = qry
     return img.reshape(-1)
+
+
+def uniform_blob_pairs(n_pairs: int, R: int, Q: int, seed: int, alphabet: bytes = b"0123"):
+    """Same records as uniform_file_bytes, already in parseInput's output form: (blob with '\\n' -> 0,
+    seqPair index) — what parseInput would return for that file (c++/parseInput.cpp:78-113)."""
+    img = uniform_file_bytes(n_pairs, R, Q, seed, alphabet)
+    rec = 2 + R + 1 + Q + 1
+    m = img.reshape(n_pairs, rec)
+    m[:, 1] = 0; m[:, 2 + R] = 0; m[:, rec - 1] = 0
+    pairs = np.zeros(n_pairs, dtype=[("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
+    base = np.arange(n_pairs, dtype=np.int64) * rec
+    pairs["referenceIdx"] = base + 2
+    pairs["referenceSize"] = R
+    pairs["queryIdx"] = base + 3 + R
+    pairs["querySize"] = Q
+    return img, pairs
+
+
+def blob_to_file_bytes(blob: np.ndarray) -> np.ndarray:
+    """Inverse of the parser's newline->NUL rewrite for generator-made blobs (no NUL inside sequences)."""
+    out = blob.copy()
+    out[out == 0] = 10
+    return out

@@ -180,3 +180,63 @@ def test_s16x2_ops_random_vs_numpy(eng):
     out, ph, pl = eng.dpx_eval(OPS.index("__vibmax_s16x2"), a, b, c)
     assert (out == pack(np.maximum(al, bl), np.maximum(ah, bh))).all()
     assert (ph.astype(bool) == (ah >= bh)).all() and (pl.astype(bool) == (al >= bl)).all()
+
+
+# ---- packed int16x2 short-read kernel (score + end cell) ------------------------------------------------
+def _staged(eng, blob, pairs, params):
+    b = eng.upload(blob, pairs)
+    b.run(params)
+    res = b.fetch()
+    st = b.stats()
+    b.free()
+    return res, st
+
+
+@pytest.mark.parametrize("shape", [(150, 150, 4096), (150, 150, 4097), (100, 100, 513), (64, 40, 300), (151, 152, 257),
+                                   (250, 250, 128), (300, 100, 64), (33, 400, 64), (1, 1, 70), (500, 160, 40)])
+@pytest.mark.parametrize("w", [dict(match=3, mismatch=-1, gap_open=-2), dict(match=2, mismatch=-2, gap_open=-1),
+                               dict(match=5, mismatch=-4, gap_open=-3)])
+def test_short_read_kernel_uniform(eng, shape, w):
+    R, Q, n = shape
+    img = synth.uniform_file_bytes(n, R, Q, 0x5EED0002 + R * 7 + Q)
+    blob, pairs = ol.parse_image(img)
+    # make a quarter of the pairs similar so that scores are large and ties / long diagonals occur
+    rng = np.random.default_rng(R + Q)
+    for k in range(0, n, 4):
+        r0, q0 = pairs[k]["referenceIdx"], pairs[k]["queryIdx"]
+        m = min(R, Q)
+        blob[q0:q0 + m] = blob[r0:r0 + m]
+        flips = rng.integers(0, m, max(1, m // 20))
+        blob[q0 + flips] = ord("0")
+    for flags in (api.OUT_SCORE | api.OUT_END_COORDS, api.OUT_SCORE):
+        res, st = _staged(eng, blob, pairs, api.make_params(api.LSW, flags=flags, **w))
+        assert st["kernel_id"] == 2, "short-read kernel was not selected"
+        s, e, _ = ol.align_batch(ol.params(ol.LSW, **w), blob, pairs, strings=False, threads=8)
+        assert (res.scores == s).all()
+        if flags & api.OUT_END_COORDS:
+            bad = np.flatnonzero((res.end_row_col != e).any(axis=1))
+            assert len(bad) == 0, f"{len(bad)} end cells differ, first {bad[:5]}: gpu {res.end_row_col[bad[:3]]} oracle {e[bad[:3]]}"
+
+
+def test_short_read_kernel_ragged_lengths(eng):
+    rng = synth.Rng(0x5EED0000 + 77)
+    pairs = []
+    for k in range(1501):
+        R = 1 + int(rng.below(1, 300)[0])
+        r = synth.random_seq(rng, R, b"0123" if k % 3 else b"01")
+        q = synth.mutate(rng, r, 0.05, 0.02, 0.02) if k % 2 else synth.random_seq(rng, 1 + int(rng.below(1, 300)[0]))
+        pairs.append((r, q))
+    pairs += [(b"", b"0123"), (b"0123", b""), (b"", b"")]
+    blob, idx = ol.parse_image(synth.pairs_to_file_bytes(pairs))
+    res, st = _staged(eng, blob, idx, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
+    assert st["kernel_id"] == 2
+    s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, idx, strings=False, threads=8)
+    assert (res.scores == s).all() and (res.end_row_col == e).all()
+
+
+def test_five_symbol_alphabet_escapes_to_byte_kernels(eng):
+    blob, idx = random_pairs(0x44, 200, 120, alphabets=(b"01234",))
+    res, st = _staged(eng, blob, idx, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
+    assert st["kernel_id"] == 1
+    s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, idx, strings=False)
+    assert (res.scores == s).all() and (res.end_row_col == e).all()

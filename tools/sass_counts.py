@@ -1,0 +1,79 @@
+"""Counts the instructions of each fill kernel's hot loop in the built libdpxalign.so and splits them by
+issue pipe (measured model, profiles/r01_dpx_microbench*.json: ALU pipe incl. DPX 64 lanes/clk/SM, FMA pipe
+64 lanes/clk/SM, issue 128 lanes/clk/SM).  Output: profiles/sass_counts.json, read by bench.py for the
+DPX-issue roofline (I_cell counted from the committed SASS inner loop).
+
+usage: python tools/sass_counts.py [libdpxalign.so] [out.json]"""
+import collections
+import json
+import os
+import re
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from sass_loops import kernels, loops, opcode  # noqa: E402
+
+FMA_PIPE = ("IMAD", "FFMA", "FMUL", "FADD", "HFMA2", "HADD2", "HMUL2")
+OTHER = ("LDS", "STS", "LDG", "STG", "LDC", "LDCU", "SHFL", "BRA", "ATOM", "RED", "BAR", "S2R", "S2UR", "CS2R", "NOP",
+         "BSSY", "BSYNC", "EXIT", "MEMBAR", "ERRBAR", "CCTL", "WARPSYNC", "YIELD", "VOTE", "VOTEU", "R2UR", "REDUX", "CREDUX",
+         "UIADD3", "UISETP", "UMOV", "ULEA", "ULOP3", "USHF", "UIMAD", "USEL", "UPRMT", "UFLO", "UPOPC", "LDSM", "MATCH", "CALL", "RET")
+
+
+def pipe(op):
+    base = op.split(".")[0]
+    if base in FMA_PIPE:
+        return "fma"
+    if base in OTHER:
+        return "other"
+    return "alu"
+
+
+# kernel-name regex -> (label, cells per inner-loop trip as a function of template ints)
+SPECS = [
+    (r"sr_lsw_kernelILi(\d+)ELi(\d+)ELb([01])ELb([01])E", "shortread_s16x2",
+     lambda g: dict(G=int(g[0]), K=int(g[1]), track=bool(int(g[2])), xormode=bool(int(g[3])), cells=2 * 2 * int(g[1]))),
+    (r"wf_fill_kernelILi(\d+)ELb([01])ELi(\d+)E", "wavefront_s32",
+     lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=int(g[2]))),
+]
+
+
+def main():
+    lib = sys.argv[1] if len(sys.argv) > 1 else "dpx_gpu_genomics_project_b200/libdpxalign.so"
+    out = sys.argv[2] if len(sys.argv) > 2 else "profiles/sass_counts.json"
+    res = {}
+    for name, ins in kernels(lib).items():
+        for pat, label, fn in SPECS:
+            m = re.search(pat, name)
+            if not m:
+                continue
+            info = fn(m.groups())
+            # hot loop = the innermost loop with the most DPX (VIMNMX*/VIADDMNMX*) or max instructions
+            best = None
+            for (s, e) in loops(ins):
+                body = [t for a, t in ins if s <= a <= e]
+                dpx = sum(1 for t in body if re.match(r"(@!?U?P\d+\s+)?VI(ADD)?MNMX", t))
+                if dpx == 0:
+                    continue
+                if best is None or len(body) < len(best[0]):
+                    best = (body, dpx)
+            if best is None:
+                continue
+            body, dpx = best
+            hist = collections.Counter(opcode(t) for t in body)
+            by_pipe = collections.Counter()
+            for op, c in hist.items():
+                by_pipe[pipe(op)] += c
+            cells = info.pop("cells")
+            key = label + ":" + ",".join(f"{k}={v}" for k, v in info.items())
+            res[key] = dict(mangled=name, loop_instructions=len(body), cells_per_trip=cells, dpx_instructions=dpx,
+                            alu_pipe=by_pipe["alu"], fma_pipe=by_pipe["fma"], other=by_pipe["other"],
+                            alu_per_cell=by_pipe["alu"] / cells, fma_per_cell=by_pipe["fma"] / cells,
+                            issue_per_cell=len(body) / cells, histogram=dict(hist.most_common()), **info)
+    with open(out, "w") as f:
+        json.dump(res, f, indent=1, sort_keys=True)
+    for k, v in sorted(res.items()):
+        print(f"{k:70s} instr/cell {v['issue_per_cell']:.2f}  alu/cell {v['alu_per_cell']:.2f}  fma/cell {v['fma_per_cell']:.2f}")
+
+
+if __name__ == "__main__":
+    main()

@@ -241,6 +241,7 @@ def main():
     sampler.stop_flag.set(); sampler.join(timeout=1.0)
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     ms_total = float(sum(ms_steps))
+    batch.sync()
     kernel_ms = float(batch.stats()["fill_ms"])          # library's own event pair around the last fill kernel
 
     # result check of the timed configuration on a sample (outside the timed region)
@@ -265,6 +266,15 @@ def main():
             raise RuntimeError(f"dpx_align_batch failed: {st} {L.dpx_last_error(eng.ctx)}")
 
     e2e_once()
+    # context for the e2e number: what a bare pinned H2D copy of the same input bytes costs on this box
+    dev_blob = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_blob.copy_(pin_blob, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record(stream); dev_blob.copy_(pin_blob, non_blocking=True); c1.record(stream)
+    torch.cuda.synchronize()
+    h2d_ms = c0.elapsed_time(c1)
+    del dev_blob
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -320,7 +330,8 @@ def main():
            "dtype": "int16x2", "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(nb + npairs_bytes),
                    "d2h_bytes_per_step": int(args.pairs * 12), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                   "api": "dpx_align_batch (C ABI), pinned host buffers"},
+                   "api": "dpx_align_batch (C ABI), pinned host buffers",
+                   "bare_h2d_copy_ms": h2d_ms, "bare_h2d_gbs": nb / (h2d_ms * 1e-3) / 1e9},
            "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
            "kernel_ms_last_step": kernel_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}
 

@@ -28,7 +28,7 @@ struct BtArgs {
     const int32_t* scores;
     const int32_t* end_rc;               // SW start cells
     const uint32_t* tb;
-    const unsigned long long* tb_off;
+    unsigned long long tb_stride;        // words per schedule position (as in WfArgs)
     char* strings;                       // output slab
     const unsigned long long* str_off;   // [n_pairs] byte offset of the pair's slot
     int32_t* str_start;                  // [n_pairs] out
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
     const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
     const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
     const WfGeom geo = WfGeom::make(a.K, CB, Q, R, ALGO == DPX_ALGO_BSW ? a.band : -1);
-    const uint32_t* __restrict__ tb = a.tb + a.tb_off[pid];
+    const uint32_t* __restrict__ tb = a.tb + (unsigned long long)pos * a.tb_stride;
 
     const size_t F = (size_t)Q + R + 1;
     char* __restrict__ o0 = a.strings + a.str_off[pid];
@@ -113,6 +113,40 @@ __global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
         }
     }
     a.str_start[pid] = (int32_t)p;
+}
+
+// string_offsets[3*i + k] = slot offset + k * F + first character  (the ABI's view of the slab)
+__global__ void __launch_bounds__(256) str_offsets_kernel(const dpx_seq_pair* __restrict__ pairs, int n, const unsigned long long* __restrict__ str_off,
+                                                          const int32_t* __restrict__ str_start, unsigned long long* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long F = (unsigned long long)pairs[i].querySize + (unsigned long long)pairs[i].referenceSize + 1ull;
+    const unsigned long long b = str_off[i] + (unsigned long long)str_start[i];
+    out[3 * i] = b; out[3 * i + 1] = b + F; out[3 * i + 2] = b + 2 * F;
+}
+
+// sort key of the schedule: longer queries first, then longer references (descending via bitwise not)
+__global__ void __launch_bounds__(256) sched_keys_kernel(const dpx_seq_pair* __restrict__ pairs, int n, unsigned long long* __restrict__ keys, int32_t* __restrict__ ids) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = ~(((unsigned long long)(uint32_t)pairs[i].querySize << 32) | (unsigned long long)(uint32_t)pairs[i].referenceSize);
+    ids[i] = i;
+}
+
+// in-band cell count of the banded algorithm: sum over rows of |{j in [1,R] : |i-j| <= W}|
+__global__ void __launch_bounds__(256) band_cells_kernel(const dpx_seq_pair* __restrict__ pairs, int n, int W, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    unsigned long long c = 0;
+    for (int p = warp; p < n; p += nwarps) {
+        const long long Q = pairs[p].querySize, R = pairs[p].referenceSize;
+        for (long long i = 1 + lane; i <= Q; i += 32) {
+            const long long lo = i - W < 1 ? 1 : i - W, hi = i + W > R ? R : i + W;
+            if (hi >= lo) c += (unsigned long long)(hi - lo + 1);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+    if (lane == 0 && c) atomicAdd(out, c);
 }
 
 }  // namespace dpx

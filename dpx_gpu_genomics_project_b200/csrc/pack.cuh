@@ -7,12 +7,78 @@
 // (the data sets use '0'..'4', reference correct-outputs/LNW/web-scraper-LNW.py:5-12) is the escape: the
 // batch then stays on the byte-compare kernels.
 //
-// Packed layout: pair p owns words [pk_off[p], pk_off[p+1]) : ceil(R/16) reference words followed by
+// Packed layout: pair p starts at word pk_off[p] (or p * pk_stride when all pairs have equal lengths): ceil(R/16) reference words followed by
 // ceil(Q/16) query words; base k of a sequence sits in word k/16 at bits 2*(k%16).
 #pragma once
 #include "common.cuh"
 
 namespace dpx {
+
+// Per-batch facts the host needs before it can choose kernels, gathered in ONE pass on the device so the host
+// never loops over the pairs: alphabet presence set, length extrema, cell count, packed size, string-slot
+// size, and a validity flag for the index (every range inside the blob).
+struct BatchInfo {
+    uint32_t present[8];
+    int max_r, max_q;
+    int min_r_inv, min_q_inv;              // INT_MAX - min (so that a zeroed struct works with atomicMax)
+    unsigned long long cells;              // sum Q*R
+    unsigned long long packed_words;       // sum ceil(R/16) + ceil(Q/16)
+    unsigned long long str_bytes;          // sum 3*(Q+R+1)
+    int invalid;
+    int pad;
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(const uint8_t* __restrict__ blob, long long byte_lo, long long byte_hi,
+                                                   const dpx_seq_pair* __restrict__ pairs, int n_pairs, BatchInfo* __restrict__ info,
+                                                   unsigned long long* __restrict__ pk_words, unsigned long long* __restrict__ str_len) {
+    __shared__ uint32_t sh[8];
+    __shared__ unsigned long long sh_cells, sh_words, sh_str;
+    __shared__ int sh_maxr, sh_maxq, sh_minr, sh_minq, sh_bad;
+    if (threadIdx.x < 8) sh[threadIdx.x] = 0;
+    if (threadIdx.x == 0) { sh_cells = 0; sh_words = 0; sh_str = 0; sh_maxr = 0; sh_maxq = 0; sh_minr = 0; sh_minq = 0; sh_bad = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long cells = 0, words = 0, strb = 0;
+    int maxr = 0, maxq = 0, minr = 0, minq = 0, bad = 0;
+    for (int p = warp; p < n_pairs; p += nwarps) {
+        const dpx_seq_pair pr = pairs[p];
+        const bool ok = pr.referenceSize >= 0 && pr.querySize >= 0 && pr.referenceIdx >= byte_lo && pr.queryIdx >= byte_lo &&
+                        (long long)pr.referenceIdx + pr.referenceSize <= byte_hi && (long long)pr.queryIdx + pr.querySize <= byte_hi;
+        if (!ok) { bad = 1; if (lane == 0) { if (pk_words) pk_words[p] = 0; if (str_len) str_len[p] = 0; } continue; }
+        for (int k = lane; k < pr.referenceSize; k += 32) { const uint8_t c = blob[pr.referenceIdx + k]; loc[c >> 5] |= 1u << (c & 31); }
+        for (int k = lane; k < pr.querySize; k += 32)     { const uint8_t c = blob[pr.queryIdx + k];     loc[c >> 5] |= 1u << (c & 31); }
+        if (lane == 0) {
+            const unsigned long long w = (unsigned long long)((pr.referenceSize + 15) >> 4) + (unsigned long long)((pr.querySize + 15) >> 4);
+            const unsigned long long sl = 3ull * ((unsigned long long)pr.referenceSize + pr.querySize + 1);
+            if (pk_words) pk_words[p] = w;
+            if (str_len) str_len[p] = sl;
+            cells += (unsigned long long)pr.referenceSize * (unsigned long long)pr.querySize; words += w; strb += sl;
+            maxr = max(maxr, pr.referenceSize); maxq = max(maxq, pr.querySize);
+            minr = max(minr, 0x7fffffff - pr.referenceSize); minq = max(minq, 0x7fffffff - pr.querySize);
+        }
+    }
+    #pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        const uint32_t v = __reduce_or_sync(0xffffffffu, loc[w]);
+        if (lane == 0 && v) atomicOr(&sh[w], v);
+    }
+    if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(&sh_bad, 1); }
+    if (lane == 0) {
+        atomicAdd(&sh_cells, cells); atomicAdd(&sh_words, words); atomicAdd(&sh_str, strb);
+        atomicMax(&sh_maxr, maxr); atomicMax(&sh_maxq, maxq); atomicMax(&sh_minr, minr); atomicMax(&sh_minq, minq);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8 && sh[threadIdx.x]) atomicOr(&info->present[threadIdx.x], sh[threadIdx.x]);
+    if (threadIdx.x == 0) {
+        atomicAdd(&info->cells, sh_cells); atomicAdd(&info->packed_words, sh_words); atomicAdd(&info->str_bytes, sh_str);
+        atomicMax(&info->max_r, sh_maxr); atomicMax(&info->max_q, sh_maxq);
+        atomicMax(&info->min_r_inv, sh_minr); atomicMax(&info->min_q_inv, sh_minq);
+        if (sh_bad) atomicOr(&info->invalid, 1);
+    }
+}
 
 __global__ void __launch_bounds__(256) present_kernel(const uint8_t* __restrict__ blob, const dpx_seq_pair* __restrict__ pairs,
                                                        int n_pairs, uint32_t* __restrict__ present /*[8]*/) {
@@ -41,6 +107,7 @@ struct PackLut { uint8_t code[256]; };
 
 __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ blob, const dpx_seq_pair* __restrict__ pairs,
                                                      int n_pairs, const unsigned long long* __restrict__ pk_off,
+                                                     unsigned long long pk_stride,      // used when pk_off == nullptr (uniform lengths)
                                                      uint32_t* __restrict__ packed, const PackLut lut) {
     __shared__ uint8_t code[256];
     code[threadIdx.x] = lut.code[threadIdx.x];
@@ -50,7 +117,7 @@ __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ 
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int p = warp; p < n_pairs; p += nwarps) {
         const dpx_seq_pair pr = pairs[p];
-        uint32_t* __restrict__ out = packed + pk_off[p];
+        uint32_t* __restrict__ out = packed + (pk_off ? pk_off[p] : (unsigned long long)p * pk_stride);
         const int rw = (pr.referenceSize + 15) >> 4, qw = (pr.querySize + 15) >> 4;
         for (int w = lane; w < rw + qw; w += 32) {
             const bool isq = w >= rw;

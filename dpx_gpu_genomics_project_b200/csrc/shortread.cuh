@@ -19,13 +19,15 @@
 //   h   = __vimax3_s16x2(e, up, B2)       ReLU against the bias B (= zero)                     (VIMNMX3.S16x2)
 //   hg  = h + G2                       plain 32-bit add: all values carry a bias B >= -gap, so the low half
 //                                      always carries into the high half and G2's high half is gap-1  (either pipe)
-//   key = h * 2^k + code(step)         one IMAD on the FMA pipe: the (positive, biased) score moves up k bits in
-//                                      both halves and the low k bits take 2^k-1 - (step mod 2^k)
-//   best= max.s16x2(best, key)         per row register: highest score, earliest step wins      (VIMNMX.S16x2)
-//   Every 2^k steps (warp-uniform) the K row registers are folded into one 32-bit key per pair and lane,
+//   key = h * 2^k + code               one IMAD on the FMA pipe: the (positive, biased) score moves up k bits in
+//                                      both halves; the low k bits are [upper row of the row pair : 1][2^(k-1)-1 -
+//                                      (step mod 2^(k-1)) : k-1]
+//   best= vimax3.s16x2(best, key_r, key_r+1)   one VIMNMX3 per TWO rows: highest score, then upper row, then
+//                                      earliest step
+//   Every 2^(k-1) steps (warp-uniform) the row-pair registers are folded into one 32-bit key per pair and lane,
 //   (score | 31-row | 255-block | code): higher score, then smaller row, then earlier step — exactly the
 //   reference's first-strict-max-in-row-major rule; lanes / passes are merged with the same order.
-// => 4 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells).
+// => 3.5 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells).
 // Registers hold hg = H + gap + B ("already gapped"), which is what the right and lower neighbours need;
 // the diagonal neighbour wants H, so the table holds score - gap.
 #pragma once
@@ -35,7 +37,8 @@ namespace dpx {
 
 struct SrArgs {
     const uint32_t* packed;              // 2-bit packed sequences (pack.cuh)
-    const unsigned long long* pk_off;    // [n_pairs+1]
+    const unsigned long long* pk_off;    // [n_pairs] word offsets, or null: pair p starts at p * pk_stride
+    unsigned long long pk_stride;
     const dpx_seq_pair* pairs;
     const int32_t* order;                // schedule (nullable = identity); slot s = schedule positions 2s, 2s+1
     int n_pairs, n_slots;
@@ -79,7 +82,8 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
     uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride;
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(sr_smem + (size_t)GPB * a.bnd_stride) + (size_t)gib * a.rsel_stride;
     const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, lut_lo = a.lut_lo, lut_hi = a.lut_hi, one = a.one;
-    const int kmask = (1 << a.kbits) - 1;
+    const int kmask = (1 << a.kbits) - 1;             // all position bits of an int16 key
+    const int smask = (1 << (a.kbits - 1)) - 1;       // step-code bits (the bit above them marks the upper row of a pair)
     const uint32_t kmul = a.kmul;
 
     for (;;) {
@@ -94,12 +98,12 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
             pa = a.order ? a.order[2 * slot] : 2 * slot;
             const dpx_seq_pair p = a.pairs[pa];
             RA = p.referenceSize; QA = p.querySize;
-            refA = a.packed + a.pk_off[pa]; qryA = refA + ((RA + 15) >> 4);
+            refA = a.packed + (a.pk_off ? a.pk_off[pa] : (unsigned long long)pa * a.pk_stride); qryA = refA + ((RA + 15) >> 4);
             if (2 * slot + 1 < a.n_pairs) {
                 pb = a.order ? a.order[2 * slot + 1] : 2 * slot + 1;
                 const dpx_seq_pair q = a.pairs[pb];
                 RB = q.referenceSize; QB = q.querySize;
-                refB = a.packed + a.pk_off[pb]; qryB = refB + ((RB + 15) >> 4);
+                refB = a.packed + (a.pk_off ? a.pk_off[pb] : (unsigned long long)pb * a.pk_stride); qryB = refB + ((RB + 15) >> 4);
             }
         }
         const int Rw = __reduce_max_sync(FULL, max(RA, RB));
@@ -134,16 +138,18 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
 
         for (int p = 0; p < passes; ++p) {
             const int i0 = p * G * K + gl * K;                  // matrix row of register row r is i0 + r + 1
-            uint32_t qsel[K], hgA[K], hgB[K], best[K];
-            uint32_t laneKeyA = 0, laneKeyB = 0;                 // score<<(13+k) | (31-r)<<(8+k) | (255-blk)<<k | code
+            uint32_t qsel[K], hgA[K], hgB[K], best[(K + 1) / 2];
+            uint32_t laneKeyA = 0, laneKeyB = 0;                 // score<<(k+12) | (31-row)<<(k+7) | (255-blk)<<(k-1) | code
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
                 const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
                 const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
                 qsel[r] = XORMODE ? (qa * 0x11u + qb * 0x1100u) : (qa | (qb << 8));
-                hgA[r] = Bg2; hgB[r] = Bg2; best[r] = 0;
+                hgA[r] = Bg2; hgB[r] = Bg2;
             }
+            #pragma unroll
+            for (int r = 0; r < (K + 1) / 2; ++r) best[r] = 0;
             uint32_t best2 = B2;                                 // !TRACK: one running max for all rows
             uint32_t bot = Bg2, topprev = Bg2;
             const bool more = (p + 1 < passes);
@@ -154,7 +160,9 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                 uint32_t top = __shfl_up_sync(FULL, bot, 1, G);                                          \
                 if (gl == 0) top = (p == 0) ? Bg2 : bnd[j];                                              \
                 const uint32_t rs = rsel[(S) - gl + G];                                                  \
-                const uint32_t cs2 = (uint32_t)(kmask - ((S) & kmask)) * 0x00010001u;                    \
+                const uint32_t csL = (uint32_t)(smask - ((S) & smask)) * 0x00010001u;                    \
+                const uint32_t csU = csL + (uint32_t)(smask + 1) * 0x00010001u;                          \
+                uint32_t keyprev = 0;                                                                    \
                 uint32_t upg = top, diag = topprev;                                                      \
                 topprev = top;                                                                           \
                 _Pragma("unroll")                                                                        \
@@ -167,17 +175,21 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                     NEW[r] = fma_add(h, one, G2);                                                        \
                     upg = NEW[r];                                                                        \
                     if (TRACK) {                                                                         \
-                        const uint32_t key = fma_add(h, kmul, cs2);        /* IMAD, FMA pipe */          \
-                        best[r] = __vmaxs2(best[r], key);                                                \
+                        const uint32_t key = fma_add(h, kmul, (r & 1) ? csL : csU);  /* IMAD, FMA pipe */\
+                        if (r & 1) best[r >> 1] = __vimax3_s16x2(best[r >> 1], keyprev, key);            \
+                        else if (r == K - 1) best[r >> 1] = __vmaxs2(best[r >> 1], key);                 \
+                        keyprev = key;                                                                   \
                     } else {                                                                             \
-                        best2 = __vmaxs2(best2, h);                                                       \
+                        if (r & 1) best2 = __vimax3_s16x2(best2, keyprev, h);                            \
+                        else if (r == K - 1) best2 = __vmaxs2(best2, h);                                 \
+                        keyprev = h;                                                                     \
                     }                                                                                    \
                 }                                                                                        \
                 bot = NEW[K - 1];                                                                        \
                 if (gl == G - 1 && more && j >= 1) bnd[j] = bot;                                         \
             }
 
-            const int bs = kmask + 1;                            // steps per position block (even)
+            const int bs = smask + 1;                            // steps per position block (even)
             for (int blk = 0; blk * bs < nsteps2; ++blk) {
                 const int s_end = min((blk + 1) * bs, nsteps2);
                 #pragma unroll 1
@@ -186,30 +198,32 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                     DPX_SR_STEP(s + 1, hgB, hgA)
                 }
                 if (TRACK) {
-                    // fold the row registers into the lane keys (warp-uniform point; ~12 ALU ops per row per 2^k steps)
-                    const uint32_t tagb = (uint32_t)(255 - blk) << a.kbits;
+                    // fold the row-pair registers into the lane keys (warp-uniform point).  lane key =
+                    // score << (k+12) | (31 - row) << (k+7) | (255 - blk) << (k-1) | step code
+                    const uint32_t tagb = (uint32_t)(255 - blk) << (a.kbits - 1);
+                    const uint32_t rbit = (uint32_t)(smask + 1);
                     #pragma unroll
-                    for (int r = 0; r < K; ++r) {
-                        const uint32_t tag = tagb | ((uint32_t)(31 - r) << (8 + a.kbits));
-                        const uint32_t lo = best[r] & 0xffffu, hi = best[r] >> 16;
-                        laneKeyA = max(laneKeyA, ((lo & ~(uint32_t)kmask) << 13) | tag | (lo & (uint32_t)kmask));
-                        laneKeyB = max(laneKeyB, ((hi & ~(uint32_t)kmask) << 13) | tag | (hi & (uint32_t)kmask));
+                    for (int q = 0; q < (K + 1) / 2; ++q) {
+                        const uint32_t tag = tagb | ((uint32_t)(30 - 2 * q) << (a.kbits + 7));   // lower row of the pair; the row bit adds 1
+                        const uint32_t lo = best[q] & 0xffffu, hi = best[q] >> 16;
+                        laneKeyA = max(laneKeyA, (((lo & ~(uint32_t)kmask) << 12) | ((lo & rbit) << 8) | (lo & (uint32_t)smask)) + tag);
+                        laneKeyB = max(laneKeyB, (((hi & ~(uint32_t)kmask) << 12) | ((hi & rbit) << 8) | (hi & (uint32_t)smask)) + tag);
                     }
                 }
             }
 #undef DPX_SR_STEP
 
             if (TRACK) {
-                // decode: step of the maximum = block * 2^k + (2^k-1 - code); column = step - lane + 1
-                const int hA = (int)(laneKeyA >> (13 + a.kbits)) - a.B;
-                const int hB = (int)(laneKeyB >> (13 + a.kbits)) - a.B;
+                // decode: step of the maximum = block * bs + (bs-1 - code); column = step - lane + 1
+                const int hA = (int)(laneKeyA >> (12 + a.kbits)) - a.B;
+                const int hB = (int)(laneKeyB >> (12 + a.kbits)) - a.B;
                 if (hA > bestA) {
-                    bestA = hA; rowA = i0 + (31 - (int)((laneKeyA >> (8 + a.kbits)) & 31u)) + 1;
-                    colA = (255 - (int)((laneKeyA >> a.kbits) & 255u)) * bs + (kmask - (int)(laneKeyA & (uint32_t)kmask)) - gl + 1;
+                    bestA = hA; rowA = i0 + (31 - (int)((laneKeyA >> (7 + a.kbits)) & 31u)) + 1;
+                    colA = (255 - (int)((laneKeyA >> (a.kbits - 1)) & 255u)) * bs + (smask - (int)(laneKeyA & (uint32_t)smask)) - gl + 1;
                 }
                 if (hB > bestB) {
-                    bestB = hB; rowB = i0 + (31 - (int)((laneKeyB >> (8 + a.kbits)) & 31u)) + 1;
-                    colB = (255 - (int)((laneKeyB >> a.kbits) & 255u)) * bs + (kmask - (int)(laneKeyB & (uint32_t)kmask)) - gl + 1;
+                    bestB = hB; rowB = i0 + (31 - (int)((laneKeyB >> (7 + a.kbits)) & 31u)) + 1;
+                    colB = (255 - (int)((laneKeyB >> (a.kbits - 1)) & 255u)) * bs + (smask - (int)(laneKeyB & (uint32_t)smask)) - gl + 1;
                 }
             } else {
                 bestA = max(bestA, (int)(short)(best2 & 0xffffu) - a.B);

@@ -29,7 +29,7 @@ struct WfArgs {
     int32_t* scores;                     // [n_pairs] by pair id
     int32_t* end_rc;                     // [2*n_pairs] by pair id (may be null)
     uint32_t* tb;                        // traceback words of this launch (null when !TB)
-    const unsigned long long* tb_off;    // [n_pairs] word offset of each pair inside tb
+    unsigned long long tb_stride;        // words per schedule position of this launch (geometry of (Qmax, Rmax))
     int32_t* boundary;                   // per-warp-slot boundary rows
     long long boundary_stride;           // int32 per warp slot (>= 2*(Rmax+1))
     int rmax_p1;                         // Rmax + 1 (offset of the D row inside a slot)
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
         const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
         const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
         const WfGeom geo = WfGeom::make(K, CB, Q, R, band);
-        uint32_t* __restrict__ tbp = TB ? (a.tb + a.tb_off[pid]) : nullptr;
+        uint32_t* __restrict__ tbp = TB ? (a.tb + (unsigned long long)pos * a.tb_stride) : nullptr;
 
         // ---- row 0 of the matrix into the boundary row (init_matrix of each aligner) -------------
         __syncwarp();

@@ -1,0 +1,11 @@
+// Drop-in for reference c++/LinearNeedlemanWunsch.h:42-47 (same constructor argument order).
+#pragma once
+#include "GpuAligner.h"
+
+class LinearNeedlemanWunsch : public dpxhost::GpuAligner {
+  public:
+    LinearNeedlemanWunsch(const std::string input_reference, const std::string input_query, const int pairNum,
+                          const int match_weight, const int mismatch_weight, const int gap_weight)
+        : GpuAligner(input_reference, input_query, pairNum,
+                     dpxhost::make_params(DPX_ALGO_LNW, match_weight, mismatch_weight, gap_weight, 0, 0)) {}
+};

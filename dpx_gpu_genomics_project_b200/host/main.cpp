@@ -1,0 +1,79 @@
+// main.cpp — drop-in driver: same command line and the same stdout bytes as the reference driver
+// (c++/main.cpp:118-262), but the whole file goes to the GPU as ONE batch instead of one aligner object per pair.
+//
+//   main -pairs <file> [-match m] [-mismatch x] [-open g] [-extend e]          (positional, as the reference :133-150)
+//   extra, after the reference's flags:  -algo LSW|LNW|ANW|BSW   (the reference picks it with a #define, :22-24;
+//                                                                default LSW = what the reference ships enabled)
+//                                        -band W                 (BSW only, default 64)
+//                                        -scores                 score (+ end cell) lines only, no alignment strings
+// Output: "Parsing input file: F", "Pair # | Score", then per pair "<i> | <score>" REF REL QRY, then
+// "Elapsed time (usec): N" and "Cleaning up" (:153,165,257,260).  Linear aligners take -open as their gap (:238,244).
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "GpuAligner.h"
+#include "parseInput.h"
+
+int main(int argc, char* argv[]) {
+    if (argc < 2) {
+        fprintf(stderr, "usage: main -pairs <InSeqFile> -match <matchWeight> -mismatch <mismatchWeight> -open <gapOpen> [-extend <gapExtend>] [-algo LSW|LNW|ANW|BSW] [-band W] [-scores]\n");
+        exit(EXIT_FAILURE);
+    }
+    const char* pairFileName = nullptr;
+    int matchWeight = 3, mismatchWeight = -1, gapOpenWeight = -4, gapExtendWeight = -1;   // defaults of main.cpp:128-132
+    int algo = DPX_ALGO_LSW, band = 64; bool scores_only = false;
+    for (int i = 1; i < argc; ++i) {
+        const bool has = i + 1 < argc;
+        if (!strcmp(argv[i], "-pairs") && has) pairFileName = argv[++i];
+        else if (!strcmp(argv[i], "-match") && has) matchWeight = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-mismatch") && has) mismatchWeight = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-open") && has) gapOpenWeight = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-extend") && has) gapExtendWeight = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-band") && has) band = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-scores")) scores_only = true;
+        else if (!strcmp(argv[i], "-algo") && has) {
+            const char* a = argv[++i];
+            if (!strcmp(a, "LNW")) algo = DPX_ALGO_LNW; else if (!strcmp(a, "ANW")) algo = DPX_ALGO_ANW;
+            else if (!strcmp(a, "LSW")) algo = DPX_ALGO_LSW; else if (!strcmp(a, "BSW")) algo = DPX_ALGO_BSW;
+            else { fprintf(stderr, "unknown -algo %s\n", a); exit(EXIT_FAILURE); }
+        }
+    }
+    if (!pairFileName) { fprintf(stderr, "missing -pairs <InSeqFile>\n"); exit(EXIT_FAILURE); }
+
+    printf("Parsing input file: %s\n", pairFileName);
+    seqPair* sequenceIdxs; char* sequences;
+    inputInfo fileInfo = parseInput(pairFileName, sequenceIdxs, sequences);
+
+    const auto t0 = std::chrono::steady_clock::now();
+    printf("Pair # | Score\n");
+
+    dpx_params p = dpxhost::make_params(algo, matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight, band);
+    if (scores_only) p.flags = DPX_OUT_SCORE | DPX_OUT_END_COORDS;
+    const size_t n = fileInfo.numPairs;
+    std::vector<int32_t> scores(n), rc(2 * n);
+    char* strings = nullptr; size_t* offs = nullptr;
+    dpx_ctx* ctx = dpxhost::engine();
+    const int st = dpx_align_batch(ctx, &p, sequences, fileInfo.numBytes, reinterpret_cast<const dpx_seq_pair*>(sequenceIdxs), n,
+                                   scores.data(), rc.data(), scores_only ? nullptr : &strings, scores_only ? nullptr : &offs);
+    if (st != DPX_OK) { fprintf(stderr, "dpxalign: %s (%s)\n", dpx_strerror(st), dpx_last_error(ctx)); exit(1); }
+
+    std::string out;
+    out.reserve(1 << 20);
+    for (size_t i = 0; i < n; ++i) {
+        out += std::to_string(i); out += " | "; out += std::to_string(scores[i]); out += '\n';
+        if (!scores_only) {
+            for (int k = 0; k < 3; ++k) { out += strings + offs[3 * i + k]; out += '\n'; }
+        }
+        if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
+    }
+    fwrite(out.data(), 1, out.size(), stdout);
+    dpx_free(strings); dpx_free(offs);
+
+    const long long usec = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+    printf("Elapsed time (usec): %lld\n", usec);
+    printf("Cleaning up\n");
+    cleanupParsedFile(sequenceIdxs, sequences);
+    return 0;
+}

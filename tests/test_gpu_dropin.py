@@ -1,0 +1,49 @@
+"""The C++ drop-in (host/main and the shim classes) prints exactly the reference driver's bytes."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "dpx_gpu_genomics_project_b200", "host")
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+
+
+@pytest.mark.parametrize("algo,flags", [("LNW", ["-open", "-2"]), ("LSW", ["-open", "-2"]), ("ANW", ["-open", "-3", "-extend", "-1"])])
+@pytest.mark.parametrize("name", ["adversarial", "cfg1_small", "mid"])
+def test_dropin_main_stdout_equals_reference_driver(algo, flags, name):
+    path = os.path.join(GOLD, f"{name}.in.txt")
+    out = subprocess.run([os.path.join(HOST, "main"), "-pairs", path, "-match", "3", "-mismatch", "-1"] + flags + ["-algo", algo],
+                         check=True, capture_output=True).stdout
+    lines = out.split(b"\n")
+    # reference c++/main.cpp:153,165 header and :257,260 footer around the blocks
+    assert lines[0] == b"Parsing input file: " + path.encode()
+    assert lines[1] == b"Pair # | Score"
+    assert lines[-3].startswith(b"Elapsed time (usec): ") and lines[-2] == b"Cleaning up" and lines[-1] == b""
+    body = b"\n".join(lines[2:-3]) + b"\n"
+    assert body == open(os.path.join(GOLD, f"{name}.{algo}.out.txt"), "rb").read()
+
+
+@pytest.mark.parametrize("algo", ["LNW", "LSW", "ANW", "BSW"])
+def test_reference_per_pair_loop_compiles_against_shims_and_matches(algo):
+    """c++/main.cpp:237-252's loop (construct aligner, align()) against the shim classes; BSW with a full band == LSW."""
+    path = os.path.join(GOLD, "adversarial.in.txt")
+    out = subprocess.run([os.path.join(HOST, "example_per_pair"), algo, path, "40"], check=True, capture_output=True).stdout
+    want = open(os.path.join(GOLD, f"adversarial.{'LSW' if algo == 'BSW' else algo}.out.txt"), "rb").read()
+    assert want.startswith(out) and out.count(b"\n") == 160
+
+
+def test_dropin_main_reports_parse_errors_like_the_reference(tmp_path):
+    bad = tmp_path / "bad.txt"
+    bad.write_bytes(b"0\n0123\n")
+    r = subprocess.run([os.path.join(HOST, "main"), "-pairs", str(bad)], capture_output=True)
+    assert r.returncode == 1 and b"Number of lines not a multiple of 3" in r.stderr
+    r = subprocess.run([os.path.join(HOST, "main"), "-pairs", str(tmp_path / "nope.txt")], capture_output=True)
+    assert r.returncode == 1 and b"Could not open file" in r.stderr

@@ -1,6 +1,7 @@
 // dpxalign.cu — C ABI (include/dpxalign.h) and host-side orchestration of libdpxalign.so.
 // sm_100a only; no CPU fallback: every alignment entry point needs a CUDA device.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -52,13 +53,14 @@ struct dpx_ctx {
     cudaStream_t own_stream = nullptr;             // lane 0 (unless the caller supplies a stream)
     cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // lanes 1..3 of the chunked one-call pipeline
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;            // every H2D input copy goes through this one stream: strict chunk order on the DMA engine
     std::string err;
     DevPool pool;
     BatchInfo* h_info[4] = {nullptr, nullptr, nullptr, nullptr};     // pinned read-back slots, one per lane
     int32_t* boundary[4] = {nullptr, nullptr, nullptr, nullptr}; size_t boundary_ints[4] = {0, 0, 0, 0};
     unsigned int* counters = nullptr;              // 64 dynamic-work counters per lane
     size_t tb_budget_bytes = (size_t)16 << 30;     // traceback chunk budget
-    int chunks = 8;                                // one-call pipeline depth (env DPX_CHUNKS)
+    int chunks = 12;                               // one-call pipeline: equal middle chunks (env DPX_CHUNKS)
 };
 
 struct dpx_batch {
@@ -72,6 +74,7 @@ struct dpx_batch {
     bool uniform = true;
     int n_symbols = 0;
     bool packed2 = false;
+    PackLut lut;
     // device inputs
     uint8_t* d_blob_alloc = nullptr;               // holds bytes [byte_lo, byte_hi)
     const uint8_t* d_blob = nullptr;               // d_blob_alloc - byte_lo: indexable with the seqPair offsets
@@ -93,7 +96,7 @@ struct dpx_batch {
     bool ran = false; dpx_params params{};
     std::vector<cudaEvent_t> ev;     // pairs of (start, end) per kernel; kind in ev_kind
     std::vector<int> ev_kind;        // 0 fill, 1 backtrack
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_h2d = nullptr;
     dpx_run_stats stats{};
 };
 
@@ -147,6 +150,7 @@ int dpx_create(dpx_ctx** out, int device) {
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->counters, 4 * 64 * sizeof(unsigned int)) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int l = 0; l < 3 && ok; ++l) ok = cudaStreamCreateWithFlags(&ctx->aux_stream[l], cudaStreamNonBlocking) == cudaSuccess;
     for (int l = 0; l < 4 && ok; ++l) ok = cudaHostAlloc(&ctx->h_info[l], sizeof(BatchInfo), cudaHostAllocDefault) == cudaSuccess;
     if (!ok) { cudaGetLastError(); dpx_destroy(ctx); return DPX_ERR_CUDA; }
@@ -166,6 +170,7 @@ void dpx_destroy(dpx_ctx* ctx) {
     for (int l = 0; l < 4; ++l) { if (ctx->boundary[l]) cudaFree(ctx->boundary[l]); if (ctx->h_info[l]) cudaFreeHost(ctx->h_info[l]); }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int l = 0; l < 3; ++l) if (ctx->aux_stream[l]) cudaStreamDestroy(ctx->aux_stream[l]);
     delete ctx;
 }
@@ -292,6 +297,7 @@ static void batch_release(dpx_batch* b) {
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_begin) cudaEventDestroy(b->ev_begin);
     if (b->ev_end) cudaEventDestroy(b->ev_end);
+    if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
     delete b;
 }
 
@@ -315,8 +321,12 @@ static int batch_begin(dpx_ctx* ctx, cudaStream_t st, int lane, const char* sequ
     b->d_blob = b->d_blob_alloc - byte_lo;
     CUB_(cudaEventCreate(&b->ev_begin)); CUB_(cudaEventCreate(&b->ev_end));
     if (n_pairs == 0) { *out = b; return DPX_OK; }
-    if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, st));
-    CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, st));
+    // inputs cross PCIe on the context's single copy stream (chunks arrive in issue order); the lane waits on the event
+    CUB_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUB_(cudaEventRecord(b->ev_h2d, ctx->copy_stream));
+    CUB_(cudaStreamWaitEvent(st, b->ev_h2d, 0));
     if (!pool_alloc(ctx, &b->d_info, 1) || !pool_alloc(ctx, &b->d_pk_off, n_pairs + 1) || !pool_alloc(ctx, &b->d_str_len, n_pairs + 1)) return fail(DPX_ERR_NOMEM);
     CUB_(cudaMemsetAsync(b->d_info, 0, sizeof(BatchInfo), st));
     const int pblocks = (int)std::min<size_t>((n_pairs + 7) / 8, (size_t)ctx->sm_count * 8);
@@ -342,9 +352,10 @@ static int batch_finish(dpx_batch* b) {
     b->max_r = b->info.max_r; b->max_q = b->info.max_q;
     b->min_r = 0x7fffffff - b->info.min_r_inv; b->min_q = 0x7fffffff - b->info.min_q_inv;
     b->uniform = (b->max_r == b->min_r && b->max_q == b->min_q);
-    PackLut lut{}; int nsym = 0;
-    for (int c = 0; c < 256; ++c) if (b->info.present[c >> 5] >> (c & 31) & 1u) lut.code[c] = (uint8_t)(nsym++ & 0xff);
-    b->n_symbols = nsym;
+    PackLut lut; int nsym = 0;
+    memset(lut.code, 0xFF, sizeof(lut.code));          // 0xFF = symbol not present in this batch
+    for (int c = 0; c < 256; ++c) if (b->info.present[c >> 5] >> (c & 31) & 1u) lut.code[c] = (uint8_t)(nsym++ & 0x7f);
+    b->n_symbols = nsym; b->lut = lut;
     const int pblocks = (int)std::min<size_t>((n_pairs + 7) / 8, (size_t)ctx->sm_count * 8);
     if (nsym <= 4) {
         if (!pool_alloc(ctx, &b->d_packed, (size_t)b->info.packed_words + 1)) return fail(DPX_ERR_NOMEM);
@@ -363,12 +374,50 @@ static int batch_finish(dpx_batch* b) {
             ctx->pool.release(tmp);
             off = b->d_pk_off;
         }
-        pack2_kernel<<<pblocks, 256, 0, st>>>(b->d_blob, b->d_pairs, (int)n_pairs, off, b->pk_stride, b->d_packed, lut);
+        pack2_kernel<<<pblocks, 256, 0, st>>>(b->d_blob, b->d_pairs, (int)n_pairs, off, b->pk_stride, b->d_packed, lut, nullptr);
         CUB_(cudaGetLastError());
         b->packed2 = true;
     } else {
         ctx->pool.release(b->d_pk_off); b->d_pk_off = nullptr;
     }
+    return DPX_OK;
+}
+
+// Upload without the device pass and without a host sync, for chunks whose facts are already known from the host's
+// scan of the index (uniform lengths).  Part 1 queues the copies; part 2 (once the alphabet map of the call is known)
+// queues the pack kernel, which raises *d_unknown when it meets a byte outside that map (the caller then redoes the
+// call the slow way).
+static int batch_known_copy(dpx_ctx* ctx, cudaStream_t st, int lane, const char* sequences, long long byte_lo, long long byte_hi,
+                            const dpx_seq_pair* pairs, size_t n_pairs, int R, int Q, dpx_batch** out) {
+    dpx_batch* b = new dpx_batch();
+    b->ctx = ctx; b->stream = st; b->lane = lane; b->n_pairs = n_pairs; b->byte_lo = byte_lo; b->byte_hi = byte_hi;
+    auto fail = [&](int s) { cudaStreamSynchronize(st); batch_release(b); return s; };
+    const size_t nb = (size_t)(byte_hi - byte_lo);
+    b->max_r = b->min_r = R; b->max_q = b->min_q = Q; b->uniform = true;
+    b->info.max_r = R; b->info.max_q = Q; b->info.cells = (unsigned long long)n_pairs * R * Q;
+    b->pk_stride = (unsigned long long)((R + 15) >> 4) + (unsigned long long)((Q + 15) >> 4);
+    b->info.packed_words = b->pk_stride * n_pairs;
+    if (!pool_alloc(ctx, &b->d_blob_alloc, nb + 16) || !pool_alloc(ctx, &b->d_pairs, n_pairs) ||
+        !pool_alloc(ctx, &b->d_scores, n_pairs) || !pool_alloc(ctx, &b->d_end_rc, 2 * n_pairs) ||
+        !pool_alloc(ctx, &b->d_packed, (size_t)b->info.packed_words + 1)) return fail(DPX_ERR_NOMEM);
+    b->d_blob = b->d_blob_alloc - byte_lo;
+    CUB_(cudaEventCreate(&b->ev_begin)); CUB_(cudaEventCreate(&b->ev_end));
+    CUB_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->copy_stream));
+    CUB_(cudaEventRecord(b->ev_h2d, ctx->copy_stream));
+    CUB_(cudaStreamWaitEvent(st, b->ev_h2d, 0));
+    *out = b;
+    return DPX_OK;
+}
+
+static int batch_known_pack(dpx_batch* b, const PackLut& lut, int nsym, int* d_unknown) {
+    dpx_ctx* ctx = b->ctx;
+    b->n_symbols = nsym; b->lut = lut;
+    const int pblocks = (int)std::min<size_t>((b->n_pairs + 7) / 8, (size_t)ctx->sm_count * 8);
+    pack2_kernel<<<pblocks, 256, 0, b->stream>>>(b->d_blob, b->d_pairs, (int)b->n_pairs, nullptr, b->pk_stride, b->d_packed, lut, d_unknown);
+    CU(cudaGetLastError());
+    b->packed2 = true;
     return DPX_OK;
 }
 
@@ -725,8 +774,8 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     CU(cudaSetDevice(ctx->device));
     const bool want_strings = (params->flags & DPX_OUT_STRINGS) != 0;
     const size_t min_chunk = 32768;
-    size_t nchunks = want_strings ? 1 : std::min<size_t>((size_t)ctx->chunks, n_pairs / min_chunk);
-    if (nchunks <= 1) {
+    size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)ctx->chunks, n_pairs / min_chunk);
+    if (nbase <= 1) {
         dpx_batch* b = nullptr;
         int st = dpx_batch_upload(ctx, sequences, n_bytes, pairs, n_pairs, &b);
         if (st) return st;
@@ -737,55 +786,121 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     }
     if (strings_blob) *strings_blob = nullptr;
     if (string_offsets) *string_offsets = nullptr;
-    // Software pipeline over chunks c = 0..nchunks-1 on 4 lanes (streams):
-    //   A(c): host scan of the chunk's byte range, H2D + prep kernel + info read-back   (asynchronous)
-    //   B(c): wait for A(c), pack, fill kernel, D2H of the results                        (asynchronous after the wait)
-    // issued as A(0) A(1) B(0) A(2) B(1) ... so the copy engine always has the next chunk queued while the
-    // SMs work on the previous one.
+    // Software pipeline over chunks on 4 lanes (streams); all input copies go through one copy stream in chunk order.
+    //   chunk 0 (small): H2D + device pass (prep_kernel) + one host sync -> alphabet map of the call.
+    //   later chunks whose index the host scan finds uniform: NO device pass and NO sync — H2D, pack (validating the
+    //     alphabet), fill kernel and the D2H of the results are queued at once, so the GPU free-runs behind PCIe.
+    //   other chunks: the two-stage form A (H2D + prep) / B (sync, pack, fill, D2H), queued two chunks ahead.
+    // If a later chunk contains a byte outside chunk 0's alphabet the pack kernel raises a flag and the call is redone
+    // through the single-batch route.
     constexpr int NL = 4;
     cudaStream_t lanes[NL] = {ctx->stream, ctx->aux_stream[0], ctx->aux_stream[1], ctx->aux_stream[2]};
     dpx_batch* inflight[NL] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<size_t> bound;
+    {
+        const size_t small = std::max<size_t>(n_pairs / 32, 8192);
+        const bool edge = n_pairs >= 16 * small;
+        const size_t lo = edge ? small : 0, hi = edge ? n_pairs - 2 * small : n_pairs;
+        bound.push_back(0);
+        for (size_t k = (edge ? 0 : 1); k < nbase; ++k) bound.push_back(lo + (hi - lo) * k / nbase);
+        if (edge) { bound.push_back(hi); bound.push_back(hi + small); }
+        bound.push_back(n_pairs);
+    }
+    const size_t nchunks = bound.size() - 1;
     std::vector<dpx_batch*> chunk_batch(nchunks, nullptr);
     int status = DPX_OK;
+    const bool trace = getenv("DPX_TRACE") != nullptr;
+    const auto t_call = std::chrono::steady_clock::now();
+    auto now_us = [&]() { return (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_call).count(); };
+    bool have_lut = false; PackLut lut; int nsym = 0;
+    int* d_unknown = nullptr;
+    if (!pool_alloc(ctx, &d_unknown, 1)) return DPX_ERR_NOMEM;
+    CU(cudaMemsetAsync(d_unknown, 0, sizeof(int), ctx->copy_stream));
+
+    std::vector<char> chunk_fast(nchunks, 0);
+    // A(c): host scan of the chunk's index, buffers, input copies (and the device pass when the chunk is not uniform)
     auto stage_a = [&](size_t c) -> int {
-        const size_t p0 = n_pairs * c / nchunks, p1 = n_pairs * (c + 1) / nchunks;
+        const size_t p0 = bound[c], p1 = bound[c + 1];
+        const long long ta = now_us();
         long long lo = (long long)n_bytes, hi = 0;
+        int minr = 0x7fffffff, maxr = -1, minq = 0x7fffffff, maxq = -1;
         for (size_t i = p0; i < p1; ++i) {
             const dpx_seq_pair& q = pairs[i];
             const long long a0 = std::min(q.referenceIdx, q.queryIdx);
             const long long a1 = std::max((long long)q.referenceIdx + q.referenceSize, (long long)q.queryIdx + q.querySize);
             lo = std::min(lo, a0); hi = std::max(hi, a1);
+            minr = std::min(minr, q.referenceSize); maxr = std::max(maxr, q.referenceSize);
+            minq = std::min(minq, q.querySize); maxq = std::max(maxq, q.querySize);
         }
-        if (lo < 0 || hi > (long long)n_bytes || hi < lo) { ctx->err = "a seqPair entry points outside the sequence blob"; return DPX_ERR_INVALID; }
+        if (lo < 0 || hi > (long long)n_bytes || hi < lo || minr < 0 || minq < 0) { ctx->err = "a seqPair entry points outside the sequence blob"; return DPX_ERR_INVALID; }
         const int lane = (int)(c % NL);
         if (inflight[lane]) {                       // the lane's previous chunk (c - NL): wait, then recycle its buffers
             cudaStreamSynchronize(lanes[lane]);
             batch_release(inflight[lane]); inflight[lane] = nullptr;
         }
         dpx_batch* b = nullptr;
-        int s = batch_begin(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, &b);
+        const bool fast = c > 0 && minr == maxr && minq == maxq;
+        int s = fast ? batch_known_copy(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, maxr, maxq, &b)
+                     : batch_begin(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, &b);
         if (s) return s;
-        inflight[lane] = b; chunk_batch[c] = b;
+        inflight[lane] = b; chunk_batch[c] = b; chunk_fast[c] = fast;
+        if (trace) fprintf(stderr, "[dpx] A(%zu)%s pairs %zu bytes %lld  issue %lld..%lld us\n", c, fast ? " fast" : "", p1 - p0, hi - lo, ta, now_us());
         return DPX_OK;
     };
+    // B(c): everything after the copies.  Fast chunks: pack (validating the alphabet) + fill + D2H, no sync.
     auto stage_b = [&](size_t c) -> int {
-        const size_t p0 = n_pairs * c / nchunks;
+        const size_t p0 = bound[c];
         dpx_batch* b = chunk_batch[c];
-        int s = batch_finish(b);
-        if (s) { inflight[c % NL] = nullptr; return s; }          // batch_finish released it
-        s = batch_run(b, params);
+        const long long tb0 = now_us();
+        int s;
+        if (chunk_fast[c] && have_lut && nsym <= 4) {
+            s = batch_known_pack(b, lut, nsym, d_unknown);
+        } else {
+            if (chunk_fast[c]) {
+                // alphabet too wide for the packed path: this chunk still needs its own facts -> device pass now
+                const size_t n = b->n_pairs;
+                if (!pool_alloc(ctx, &b->d_info, 1) || !pool_alloc(ctx, &b->d_pk_off, n + 1) || !pool_alloc(ctx, &b->d_str_len, n + 1)) return DPX_ERR_NOMEM;
+                ctx->pool.release(b->d_packed); b->d_packed = nullptr;
+                CU(cudaMemsetAsync(b->d_info, 0, sizeof(BatchInfo), b->stream));
+                const int pblocks = (int)std::min<size_t>((n + 7) / 8, (size_t)ctx->sm_count * 8);
+                prep_kernel<<<pblocks, 256, 0, b->stream>>>(b->d_blob, b->byte_lo, b->byte_hi, b->d_pairs, (int)n, b->d_info, b->d_pk_off, b->d_str_len);
+                CU(cudaMemcpyAsync(ctx->h_info[b->lane], b->d_info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, b->stream));
+            }
+            s = batch_finish(b);
+            if (s) { inflight[c % NL] = nullptr; return s; }          // batch_finish released it
+            if (!have_lut) { have_lut = true; lut = b->lut; nsym = b->n_symbols; }
+        }
+        const long long tb1 = now_us();
+        if (!s) s = batch_run(b, params);
         if (!s) s = batch_fetch_async(b, scores + p0, end_row_col ? end_row_col + 2 * p0 : nullptr);
+        if (trace) fprintf(stderr, "[dpx] B(%zu) wait %lld..%lld us, issued by %lld us\n", c, tb0, tb1, now_us());
         return s;
     };
+    // copies stay queued two chunks ahead of the chunk being processed; chunk 0 defines the alphabet map
     status = stage_a(0);
+    if (status == DPX_OK && nchunks > 1) status = stage_a(1);
     for (size_t c = 0; c < nchunks && status == DPX_OK; ++c) {
-        if (c + 1 < nchunks) status = stage_a(c + 1);
+        if (c + 2 < nchunks) status = stage_a(c + 2);
         if (status == DPX_OK) status = stage_b(c);
     }
     for (int lane = 0; lane < NL; ++lane) {
         cudaError_t e = cudaStreamSynchronize(lanes[lane]);
         if (e != cudaSuccess && status == DPX_OK) { ctx->err = std::string("stream sync: ") + cudaGetErrorString(e); status = DPX_ERR_CUDA; }
         if (inflight[lane]) batch_release(inflight[lane]);
+    }
+    int unknown = 0;
+    if (status == DPX_OK && cudaMemcpy(&unknown, d_unknown, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) status = DPX_ERR_CUDA;
+    ctx->pool.release(d_unknown);
+    if (trace) fprintf(stderr, "[dpx] done %lld us%s\n", now_us(), unknown ? " (alphabet grew: redo)" : "");
+    if (status == DPX_OK && unknown) {
+        // a chunk used a symbol chunk 0 did not have: redo as one batch (device pass over everything)
+        dpx_batch* b = nullptr;
+        int st = dpx_batch_upload(ctx, sequences, n_bytes, pairs, n_pairs, &b);
+        if (st) return st;
+        st = dpx_batch_run(b, params);
+        if (!st) st = dpx_batch_fetch(b, scores, end_row_col, nullptr, nullptr);
+        dpx_batch_free(b);
+        return st;
     }
     return status;
 }

@@ -108,7 +108,8 @@ struct PackLut { uint8_t code[256]; };
 __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ blob, const dpx_seq_pair* __restrict__ pairs,
                                                      int n_pairs, const unsigned long long* __restrict__ pk_off,
                                                      unsigned long long pk_stride,      // used when pk_off == nullptr (uniform lengths)
-                                                     uint32_t* __restrict__ packed, const PackLut lut) {
+                                                     uint32_t* __restrict__ packed, const PackLut lut,
+                                                     int* __restrict__ unknown_symbol /* nullable: set to 1 when a byte has code 0xFF */) {
     __shared__ uint8_t code[256];
     code[threadIdx.x] = lut.code[threadIdx.x];
     __syncthreads();
@@ -124,11 +125,12 @@ __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ 
             const uint8_t* __restrict__ src = blob + (isq ? pr.queryIdx : pr.referenceIdx);
             const int len = isq ? pr.querySize : pr.referenceSize;
             const int k0 = (isq ? w - rw : w) << 4;
-            uint32_t v = 0;
+            uint32_t v = 0; bool bad = false;
             #pragma unroll
             for (int k = 0; k < 16; ++k)
-                if (k0 + k < len) v |= (uint32_t)(code[src[k0 + k]] & 3u) << (2 * k);
+                if (k0 + k < len) { const uint8_t c = code[src[k0 + k]]; bad |= (c == 0xFF); v |= (uint32_t)(c & 3u) << (2 * k); }
             out[w] = v;
+            if (bad && unknown_symbol) *unknown_symbol = 1;
         }
     }
 }

@@ -279,3 +279,22 @@ def test_invalid_index_is_rejected(eng):
     with pytest.raises(api.DpxError) as e:
         eng.align_batch(api.make_params(api.LSW), blob, bad)
     assert e.value.status == -1
+
+
+@pytest.mark.parametrize("late_symbol", [ord("3"), ord("4")])
+def test_one_call_pipeline_redoes_when_alphabet_grows(eng, late_symbol):
+    """Chunk 0 fixes the alphabet map of the pipelined call; a symbol that first appears in a later chunk must not
+    change any result (the pack kernel flags it and the call is redone through the single-batch route)."""
+    n = 300_000
+    blob, pairs = synth.uniform_blob_pairs(n, 40, 36, 0x5EED0000 + 21, alphabet=b"012")
+    blob = blob.copy()
+    tail = pairs[-5000:]
+    rng = np.random.default_rng(4)
+    for k in range(0, 5000, 7):
+        blob[tail["referenceIdx"][k] + int(rng.integers(0, 40))] = late_symbol
+        blob[tail["queryIdx"][k] + int(rng.integers(0, 36))] = late_symbol
+    p = api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS)
+    one = eng.align_batch(p, blob, pairs)
+    for sl in (slice(0, 3000), slice(n - 6000, n)):
+        s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs[sl], strings=False, threads=8)
+        assert (one.scores[sl] == s).all() and (one.end_row_col[sl] == e).all()

@@ -93,6 +93,15 @@ def lib() -> C.CDLL:
     L.dpx_align_long_pair.restype = C.c_int
     L.dpx_align_long_pair.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                       i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dpx_stripe_create.restype = C.c_int
+    L.dpx_stripe_create.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
+    L.dpx_stripe_export.restype = C.c_int; L.dpx_stripe_export.argtypes = [vp, vp]
+    L.dpx_stripe_connect.restype = C.c_int; L.dpx_stripe_connect.argtypes = [vp, vp, vp]
+    L.dpx_stripe_reset.restype = C.c_int; L.dpx_stripe_reset.argtypes = [vp]
+    L.dpx_stripe_run.restype = C.c_int; L.dpx_stripe_run.argtypes = [vp]
+    L.dpx_stripe_result.restype = C.c_int
+    L.dpx_stripe_result.argtypes = [vp, i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    L.dpx_stripe_free.restype = None; L.dpx_stripe_free.argtypes = [vp]
     L.dpx_selftest_dpx.restype = C.c_int; L.dpx_selftest_dpx.argtypes = [vp]
     L.dpx_dpx_eval.restype = C.c_int
     L.dpx_dpx_eval.argtypes = [vp, C.c_int, vp, vp, vp, C.c_int, vp, vp, vp]

@@ -20,6 +20,7 @@
 #include "pack.cuh"
 #include "backtrack.cuh"
 #include "shortread.cuh"
+#include "longpair.cuh"
 
 using namespace dpx;
 
@@ -677,6 +678,163 @@ static int batch_fetch_async(dpx_batch* b, int32_t* scores, int32_t* end_rc) {
     return DPX_OK;
 }
 
+// ---- one long pair on one GPU: systolic array of warps over column blocks (longpair.cuh) ------------------------
+struct LongPlan { int K; int capacity_warps; };
+
+template <int K, bool PACK>
+static int long_capacity(dpx_ctx* ctx, int* warps) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK>, 128, 0));
+    *warps = per_sm * ctx->sm_count * 4;
+    return DPX_OK;
+}
+
+template <int K, bool PACK>
+static int long_launch(dpx_ctx* ctx, const LongArgs& a, cudaStream_t st) {
+    const int blocks = (a.nwarps + 3) / 4;
+    void* kargs[] = {(void*)&a};
+    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK>, dim3(blocks), dim3(128), kargs, 0, st));
+    return DPX_OK;
+}
+
+// pack = the travelling H and the query base share one 32-bit shuffle word (needs H < 2^23)
+static int long_launch_k(dpx_ctx* ctx, int K, bool pack, const LongArgs& a, cudaStream_t st) {
+    switch (K) {
+        case 2: return pack ? long_launch<2, true>(ctx, a, st) : long_launch<2, false>(ctx, a, st);
+        case 4: return pack ? long_launch<4, true>(ctx, a, st) : long_launch<4, false>(ctx, a, st);
+        case 8: return pack ? long_launch<8, true>(ctx, a, st) : long_launch<8, false>(ctx, a, st);
+        default: return pack ? long_launch<16, true>(ctx, a, st) : long_launch<16, false>(ctx, a, st);
+    }
+}
+
+static int long_capacity_k(dpx_ctx* ctx, int K, bool pack, int* warps) {
+    switch (K) {
+        case 2: return pack ? long_capacity<2, true>(ctx, warps) : long_capacity<2, false>(ctx, warps);
+        case 4: return pack ? long_capacity<4, true>(ctx, warps) : long_capacity<4, false>(ctx, warps);
+        case 8: return pack ? long_capacity<8, true>(ctx, warps) : long_capacity<8, false>(ctx, warps);
+        default: return pack ? long_capacity<16, true>(ctx, warps) : long_capacity<16, false>(ctx, warps);
+    }
+}
+
+static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
+    return (long double)p->match * (long double)std::min(R, Q) < 8.0e6L && p->match > 0;
+}
+
+static long long pow2_at_least(long long v) { long long p = 64; while (p < v) p <<= 1; return p; }
+
+// K: columns per lane.  Fewer columns per lane = more warps = more of the GPU busy, but more shuffles per cell; take the
+// largest K in {16,8,4,2} that still gives at least ~8 warps per SM, never more warps than can be co-resident per pass.
+static int long_pick_k(dpx_ctx* ctx, long long R_local) {
+    for (int K : {16, 8, 4, 2}) {
+        const long long nw = (R_local + 32LL * K - 1) / (32LL * K);
+        if (nw >= 8LL * ctx->sm_count || K == 2) return K;
+    }
+    return 2;
+}
+
+static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
+                            int32_t* score, int64_t* end_row, int64_t* end_col) {
+    cudaStream_t st = ctx->stream;
+    int K = long_pick_k(ctx, (long long)R);
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }   // tests
+    int capacity = 0;
+    const bool pack = long_can_pack(p, R, Q);
+    { int s = long_capacity_k(ctx, K, pack, &capacity); if (s) return s; }
+    if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
+    if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
+    const long long CW = 32LL * K;
+    const long long nw_total = ((long long)R + CW - 1) / CW;
+    const long long passes = (nw_total + capacity - 1) / capacity;
+    const long long nw_pass = (nw_total + passes - 1) / passes;
+    const long long RING = 2048;
+
+    uint8_t *d_ref = nullptr, *d_qry = nullptr;
+    unsigned long long *d_rings = nullptr, *d_full[2] = {nullptr, nullptr}; int32_t* d_bs = nullptr;
+    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
+    LongChan* d_chans = nullptr; int* d_err = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        DevPool& P = ctx->pool;
+        P.release(d_ref); P.release(d_qry); P.release(d_rings); P.release(d_full[0]); P.release(d_full[1]); P.release(d_bs);
+        P.release(d_cnt); P.release(d_br); P.release(d_bc); P.release(d_chans); P.release(d_err);
+    };
+#define LCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
+    bool ok = pool_alloc(ctx, &d_ref, R + 16) && pool_alloc(ctx, &d_qry, Q + 16) && pool_alloc(ctx, &d_rings, (size_t)(nw_pass * RING)) &&
+              pool_alloc(ctx, &d_cnt, (size_t)(2 * (nw_pass + 2))) && pool_alloc(ctx, &d_bs, (size_t)nw_pass) &&
+              pool_alloc(ctx, &d_br, (size_t)nw_pass) && pool_alloc(ctx, &d_bc, (size_t)nw_pass) &&
+              pool_alloc(ctx, &d_chans, (size_t)(nw_pass + 1)) && pool_alloc(ctx, &d_err, 1);
+    const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
+    if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
+    if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
+    LCU(cudaMemcpyAsync(d_ref, ref, R, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemcpyAsync(d_qry, qry, Q, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+
+    int32_t best = 0; long long brow = 0, bcol = 0;
+    std::vector<LongChan> chans((size_t)nw_pass + 1);
+    std::vector<int32_t> h_bs((size_t)nw_pass); std::vector<long long> h_br((size_t)nw_pass), h_bc((size_t)nw_pass);
+    for (long long ps = 0; ps < passes; ++ps) {
+        const long long w0 = ps * nw_pass, nw = std::min(nw_pass, nw_total - w0);
+        if (nw <= 0) break;
+        // credit counters and ring tags start from zero (a tag of 0 never equals a row >= 1)
+        LCU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)(2 * (nw_pass + 2)), st));
+        LCU(cudaMemsetAsync(d_rings, 0, sizeof(unsigned long long) * (size_t)(nw_pass * RING), st));
+        if (ps + 1 < passes) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
+        long long* cred = d_cnt;
+        for (long long c = 0; c <= nw; ++c) {
+            LongChan ch{};
+            if (c == 0) {
+                if (ps > 0) { ch.ring = d_full[(ps - 1) & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
+            } else if (c == nw) {
+                if (ps + 1 < passes) { ch.ring = d_full[ps & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
+            } else {
+                ch.ring = d_rings + (c - 1) * RING; ch.size = RING; ch.credit = cred + c;
+            }
+            chans[(size_t)c] = ch;
+        }
+        LCU(cudaMemcpyAsync(d_chans, chans.data(), sizeof(LongChan) * (size_t)(nw + 1), cudaMemcpyHostToDevice, st));
+        LongArgs a{};
+        a.ref = d_ref; a.qry = d_qry; a.Q = (long long)Q; a.R_local = (long long)R; a.col0 = w0 * CW; a.col_offset = 0;
+        a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open; a.nwarps = (int)nw; a.chans = d_chans;
+        a.best_score = d_bs; a.best_row = d_br; a.best_col = d_bc; a.error_flag = d_err; a.system_scope = 0;
+        { int s = long_launch_k(ctx, K, pack, a, st); if (s) { cleanup(); return s; } }
+        LCU(cudaMemcpyAsync(h_bs.data(), d_bs, sizeof(int32_t) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(h_br.data(), d_br, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(h_bc.data(), d_bc, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        int err = 0;
+        LCU(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        if (err) { ctx->err = "long-pair pipeline watchdog fired"; cleanup(); return DPX_ERR_CUDA; }
+        for (long long w = 0; w < nw; ++w) {
+            const int32_t s = h_bs[(size_t)w]; const long long r = h_br[(size_t)w], c = h_bc[(size_t)w];
+            if (s > best || (s == best && s > 0 && (r < brow || (r == brow && c < bcol)))) { best = s; brow = r; bcol = c; }
+        }
+    }
+#undef LCU
+    cleanup();
+    *score = best; if (end_row) *end_row = brow; if (end_col) *end_col = bcol;
+    return DPX_OK;
+}
+
+// ---- multi-GPU mode B: one column stripe of a long pair per GPU -------------------------------------------------
+struct dpx_stripe {
+    dpx_ctx* ctx = nullptr;
+    dpx_params params{};
+    size_t R_local = 0, col_offset = 0, Q = 0;
+    int index = 0, n = 1, K = 8, nw = 0; bool pack = false;
+    static constexpr long long XRING = 65536, RING = 2048;
+    // exchange buffer (own memory, exported over CUDA IPC): [1] out credit (written by the next stripe), inbox ring of
+    // tagged 8-byte entries at byte 128 (written by the previous stripe)
+    char* xbuf = nullptr;
+    char* prev_x = nullptr; char* next_x = nullptr;          // neighbours' exchange buffers (peer mappings)
+    uint8_t *d_ref = nullptr, *d_qry = nullptr;
+    unsigned long long* d_rings = nullptr; int32_t* d_bs = nullptr;
+    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
+    LongChan* d_chans = nullptr; int* d_err = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool launched = false;
+};
+
 extern "C" {
 
 void dpx_batch_free(dpx_batch* b) {
@@ -905,22 +1063,153 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     return status;
 }
 
+int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_stripe, size_t R_local, size_t col_offset,
+                      const char* qry, size_t Q, int stripe_index, int n_stripes, dpx_stripe** out) {
+    if (!ctx || !params || !out || !ref_stripe || !qry || R_local == 0 || Q == 0 || n_stripes < 1 || stripe_index < 0 || stripe_index >= n_stripes) return DPX_ERR_INVALID;
+    if (params->algo != DPX_ALGO_LSW) return DPX_ERR_UNSUPPORTED;
+    if (Q > 0x7ffffff0u || (long double)params->match * (long double)Q > 2.0e9L) return DPX_ERR_RANGE;
+    CU(cudaSetDevice(ctx->device));
+    dpx_stripe* s = new dpx_stripe();
+    s->ctx = ctx; s->params = *params; s->R_local = R_local; s->col_offset = col_offset; s->Q = Q; s->index = stripe_index; s->n = n_stripes;
+    auto fail = [&](int st) { dpx_stripe_free(s); return st; };
+    // lane width: the whole stripe must be one co-resident pass
+    int K = long_pick_k(ctx, (long long)R_local), cap = 0;
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }
+    s->pack = (long double)params->match * (long double)Q < 8.0e6L && params->match > 0;
+    for (;;) {
+        if (long_capacity_k(ctx, K, s->pack, &cap)) return fail(DPX_ERR_CUDA);
+        if ((long long)((R_local + 32ull * K - 1) / (32ull * K)) <= cap || K == 16) break;
+        K *= 2;
+    }
+    s->K = K; s->nw = (int)((R_local + 32ull * K - 1) / (32ull * K));
+    if (s->nw > cap) { ctx->err = "stripe too wide for one co-resident pass"; return fail(DPX_ERR_RANGE); }
+    const size_t nw = (size_t)s->nw;
+    bool ok = cudaMalloc(&s->xbuf, 128 + sizeof(unsigned long long) * (size_t)dpx_stripe::XRING) == cudaSuccess &&
+              cudaMalloc(&s->d_ref, R_local + 16) == cudaSuccess && cudaMalloc(&s->d_qry, Q + 16) == cudaSuccess &&
+              cudaMalloc(&s->d_rings, sizeof(unsigned long long) * nw * (size_t)dpx_stripe::RING) == cudaSuccess &&
+              cudaMalloc(&s->d_cnt, sizeof(long long) * 2 * (nw + 2)) == cudaSuccess &&
+              cudaMalloc(&s->d_bs, sizeof(int32_t) * nw) == cudaSuccess && cudaMalloc(&s->d_br, sizeof(long long) * nw) == cudaSuccess &&
+              cudaMalloc(&s->d_bc, sizeof(long long) * nw) == cudaSuccess && cudaMalloc(&s->d_chans, sizeof(LongChan) * (nw + 1)) == cudaSuccess &&
+              cudaMalloc(&s->d_err, sizeof(int)) == cudaSuccess &&
+              cudaEventCreate(&s->e0) == cudaSuccess && cudaEventCreate(&s->e1) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); return fail(DPX_ERR_NOMEM); }
+    if (cudaMemcpy(s->d_ref, ref_stripe, R_local, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->d_qry, qry, Q, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(s->xbuf, 0, 128) != cudaSuccess) return fail(DPX_ERR_CUDA);
+    *out = s;
+    return DPX_OK;
+}
+
+int dpx_stripe_export(dpx_stripe* s, void* handle) {
+    if (!s || !handle) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = s->ctx;
+    static_assert(sizeof(cudaIpcMemHandle_t) == DPX_IPC_HANDLE_BYTES, "IPC handle size");
+    CU(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, s->xbuf));
+    memcpy(handle, &h, sizeof(h));
+    return DPX_OK;
+}
+
+int dpx_stripe_connect(dpx_stripe* s, const void* prev_handle, const void* next_handle) {
+    if (!s) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    if (prev_handle && s->index > 0) {
+        cudaIpcMemHandle_t h; memcpy(&h, prev_handle, sizeof(h));
+        CU(cudaIpcOpenMemHandle((void**)&s->prev_x, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    if (next_handle && s->index + 1 < s->n) {
+        cudaIpcMemHandle_t h; memcpy(&h, next_handle, sizeof(h));
+        CU(cudaIpcOpenMemHandle((void**)&s->next_x, h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    if ((s->index > 0 && !s->prev_x) || (s->index + 1 < s->n && !s->next_x)) return DPX_ERR_INVALID;
+    // channels: [0] = inbox (own memory; credit goes back to prev), [1..nw-1] local rings, [nw] = next stripe's inbox (peer)
+    const long long nw = s->nw;
+    std::vector<LongChan> ch((size_t)nw + 1);
+    long long* cred = s->d_cnt;
+    for (long long c = 0; c <= nw; ++c) {
+        LongChan x{};
+        if (c == 0) {
+            if (s->index > 0) { x.ring = (unsigned long long*)(s->xbuf + 128); x.size = dpx_stripe::XRING; x.credit = (long long*)(s->prev_x + 8); }
+        } else if (c == nw) {
+            if (s->index + 1 < s->n) { x.ring = (unsigned long long*)(s->next_x + 128); x.size = dpx_stripe::XRING; x.credit = (long long*)(s->xbuf + 8); }
+        } else { x.ring = s->d_rings + (c - 1) * dpx_stripe::RING; x.size = dpx_stripe::RING; x.credit = cred + c; }
+        ch[(size_t)c] = x;
+    }
+    CU(cudaMemcpy(s->d_chans, ch.data(), sizeof(LongChan) * (size_t)(nw + 1), cudaMemcpyHostToDevice));
+    return DPX_OK;
+}
+
+int dpx_stripe_reset(dpx_stripe* s) {
+    if (!s) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemset(s->xbuf, 0, 128 + sizeof(unsigned long long) * (size_t)dpx_stripe::XRING));     // credit + inbox tags
+    CU(cudaMemset(s->d_cnt, 0, sizeof(long long) * 2 * ((size_t)s->nw + 2)));
+    CU(cudaMemset(s->d_rings, 0, sizeof(unsigned long long) * (size_t)s->nw * (size_t)dpx_stripe::RING));
+    CU(cudaMemset(s->d_err, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    return DPX_OK;
+}
+
+int dpx_stripe_run(dpx_stripe* s) {
+    if (!s) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    LongArgs a{};
+    a.ref = s->d_ref; a.qry = s->d_qry; a.Q = (long long)s->Q; a.R_local = (long long)s->R_local; a.col0 = 0; a.col_offset = (long long)s->col_offset;
+    a.match = s->params.match; a.mismatch = s->params.mismatch; a.gap = s->params.gap_open; a.nwarps = s->nw; a.chans = s->d_chans;
+    a.best_score = s->d_bs; a.best_row = s->d_br; a.best_col = s->d_bc; a.error_flag = s->d_err; a.system_scope = s->n > 1;
+    CU(cudaEventRecord(s->e0, ctx->stream));
+    { int st = long_launch_k(ctx, s->K, s->pack, a, ctx->stream); if (st) return st; }
+    CU(cudaEventRecord(s->e1, ctx->stream));
+    s->launched = true;
+    return DPX_OK;
+}
+
+int dpx_stripe_result(dpx_stripe* s, int32_t* score, int64_t* end_row, int64_t* end_col, double* kernel_ms) {
+    if (!s || !s->launched || !score) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = s->ctx;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t nw = (size_t)s->nw;
+    std::vector<int32_t> bs(nw); std::vector<long long> br(nw), bc(nw); int err = 0;
+    CU(cudaMemcpy(bs.data(), s->d_bs, sizeof(int32_t) * nw, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(br.data(), s->d_br, sizeof(long long) * nw, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(bc.data(), s->d_bc, sizeof(long long) * nw, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(&err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { ctx->err = "stripe pipeline watchdog fired (a neighbour never produced / consumed)"; return DPX_ERR_CUDA; }
+    int32_t best = 0; long long r0 = 0, c0 = 0;
+    for (size_t w = 0; w < nw; ++w)
+        if (bs[w] > best || (bs[w] == best && best > 0 && (br[w] < r0 || (br[w] == r0 && bc[w] < c0)))) { best = bs[w]; r0 = br[w]; c0 = bc[w]; }
+    *score = best; if (end_row) *end_row = r0; if (end_col) *end_col = c0;
+    if (kernel_ms) { float ms = 0; CU(cudaEventElapsedTime(&ms, s->e0, s->e1)); *kernel_ms = ms; }
+    return DPX_OK;
+}
+
+void dpx_stripe_free(dpx_stripe* s) {
+    if (!s) return;
+    cudaSetDevice(s->ctx->device);
+    cudaDeviceSynchronize();
+    if (s->prev_x) cudaIpcCloseMemHandle(s->prev_x);
+    if (s->next_x) cudaIpcCloseMemHandle(s->next_x);
+    cudaFree(s->xbuf); cudaFree(s->d_ref); cudaFree(s->d_qry); cudaFree(s->d_rings); cudaFree(s->d_cnt); cudaFree(s->d_bs);
+    cudaFree(s->d_br); cudaFree(s->d_bc); cudaFree(s->d_chans); cudaFree(s->d_err);
+    if (s->e0) cudaEventDestroy(s->e0);
+    if (s->e1) cudaEventDestroy(s->e1);
+    delete s;
+}
+
 int dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params, const char* ref, size_t R, const char* qry, size_t Q,
                         int32_t* score, int64_t* end_row, int64_t* end_col) {
     if (!ctx || !params || !score || (!ref && R) || (!qry && Q)) return DPX_ERR_INVALID;
-    if (R + Q + 2 > 0x7fffffffu) return DPX_ERR_RANGE;
-    // Single-warp path for now: one pair through the batch engine (score + end cell only).
-    std::vector<char> blob(R + Q + 2);
-    if (R) memcpy(blob.data(), ref, R);
-    blob[R] = 0;
-    if (Q) memcpy(blob.data() + R + 1, qry, Q);
-    blob[R + 1 + Q] = 0;
-    dpx_seq_pair pr{0, (int32_t)R, (int32_t)(R + 1), (int32_t)Q};
-    dpx_params p = *params; p.flags = DPX_OUT_SCORE | DPX_OUT_END_COORDS;
-    int32_t rc[2] = {0, 0};
-    int st = dpx_align_batch(ctx, &p, blob.data(), blob.size(), &pr, 1, score, rc, nullptr, nullptr);
-    if (!st) { if (end_row) *end_row = rc[0]; if (end_col) *end_col = rc[1]; }
-    return st;
+    if (params->algo != DPX_ALGO_LSW) return DPX_ERR_UNSUPPORTED;
+    CU(cudaSetDevice(ctx->device));
+    *score = 0; if (end_row) *end_row = 0; if (end_col) *end_col = 0;
+    if (R == 0 || Q == 0) return DPX_OK;
+    if ((long double)params->match * (long double)std::min(R, Q) > 2.0e9L || Q > 0x7ffffff0u || R > 0x7ffffff0u) return DPX_ERR_RANGE;     // int32 scores / rows
+    return long_pair_single(ctx, params, ref, R, qry, Q, score, end_row, end_col);
 }
 
 }  // extern "C"

@@ -163,6 +163,24 @@ int         dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params,
                                 const char* ref, size_t R, const char* qry, size_t Q,
                                 int32_t* score, int64_t* end_row, int64_t* end_col);
 
+/* ---- one very long pair across SEVERAL GPUs (multi-GPU mode B): column stripes, one per GPU,
+ * pipelined along the anti-diagonal; the right edge of stripe g streams into stripe g+1's inbox by NVLink P2P
+ * stores.  One process per GPU: each rank creates its stripe, the ranks exchange the 64-byte IPC handles
+ * (e.g. torch.distributed.all_gather_object), connect to their neighbours, reset, barrier, run, and reduce the
+ * per-stripe (score, row, col) with the first-row-major tie rule.  The reference has no multi-GPU code at all.
+ *   ref_stripe  : the R_local reference bases of this stripe = global columns col_offset+1 .. col_offset+R_local
+ *   handle      : DPX_IPC_HANDLE_BYTES bytes */
+#define DPX_IPC_HANDLE_BYTES 64
+typedef struct dpx_stripe dpx_stripe;
+int         dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_stripe, size_t R_local, size_t col_offset,
+                              const char* qry, size_t Q, int stripe_index, int n_stripes, dpx_stripe** out);
+int         dpx_stripe_export(dpx_stripe* s, void* handle);
+int         dpx_stripe_connect(dpx_stripe* s, const void* prev_handle, const void* next_handle);
+int         dpx_stripe_reset(dpx_stripe* s);      /* zero the exchange counters; all ranks must barrier before dpx_stripe_run */
+int         dpx_stripe_run(dpx_stripe* s);        /* asynchronous */
+int         dpx_stripe_result(dpx_stripe* s, int32_t* score, int64_t* end_row, int64_t* end_col, double* kernel_ms);
+void        dpx_stripe_free(dpx_stripe* s);
+
 /* ---- device self-test: the FakeDPX known-answer vectors (c++/testFakeDPX.cpp:10-113) run
  * against the real sm_100a DPX instructions.  Returns the number of failing vectors (0 = pass)
  * or a negative dpx_status. */

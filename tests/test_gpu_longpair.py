@@ -1,0 +1,57 @@
+"""One long pair through the systolic warp chain (csrc/longpair.cuh) against the rolling-row CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from dpx_gpu_genomics_project_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(R, Q, seed, sub=0.02, indel=0.005):
+    rng = synth.Rng(seed)
+    r = synth.random_seq(rng, R)
+    if sub is None:
+        return r, synth.random_seq(rng, Q)
+    q = synth.mutate(rng, r[: int(Q * 1.05)], sub, indel, indel)
+    q = (q + synth.random_seq(rng, Q))[:Q]
+    return r, q
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = api.Engine(0)
+    yield e
+    e.close()
+
+
+@pytest.mark.parametrize("R,Q", [(1, 1), (5, 3), (31, 33), (64, 64), (257, 100), (1000, 1200), (4097, 3000), (20000, 9000), (7000, 30000)])
+def test_long_pair_matches_oracle(eng, R, Q):
+    for seed, sub in ((1, 0.02), (2, None)):
+        r, q = _pair(R, Q, seed * 1000 + R + Q, sub)
+        p = api.make_params(api.LSW)
+        assert eng.align_long_pair(p, r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
+
+
+@pytest.mark.parametrize("k,cap", [("2", "8"), ("4", "16"), ("8", "4"), ("16", "4"), ("2", "0"), ("8", "0")])
+def test_long_pair_forced_geometry_and_passes(eng, k, cap, monkeypatch):
+    """Every lane width, several passes over column super-blocks (full-length boundary arrays between passes), ring wrap-around."""
+    monkeypatch.setenv("DPX_LONG_K", k)
+    if cap != "0":
+        monkeypatch.setenv("DPX_LONG_CAP", cap)
+    r, q = _pair(5000, 6000, 77)
+    p = api.make_params(api.LSW, match=2, mismatch=-3, gap_open=-2)
+    assert eng.align_long_pair(p, r, q) == ol.lsw_score_only(ol.params(ol.LSW, match=2, mismatch=-3, gap_open=-2), r, q)
+    # tie-heavy input: the end cell must be the first maximum in row-major order
+    r2, q2 = b"01" * 1500, b"10" * 1700
+    assert eng.align_long_pair(api.make_params(api.LSW), r2, q2) == ol.lsw_score_only(ol.params(ol.LSW), r2, q2)
+
+
+def test_long_pair_equals_batch_engine(eng):
+    r, q = _pair(3000, 2500, 5)
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes([(r, q)]))
+    res = eng.align_batch(api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS), blob, pairs)
+    s, row, col = eng.align_long_pair(api.make_params(api.LSW), r, q)
+    assert (s, row, col) == (int(res.scores[0]), int(res.end_row_col[0][0]), int(res.end_row_col[0][1]))

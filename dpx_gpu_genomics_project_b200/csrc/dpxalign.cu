@@ -681,39 +681,77 @@ static int batch_fetch_async(dpx_batch* b, int32_t* scores, int32_t* end_rc) {
 // ---- one long pair on one GPU: systolic array of warps over column blocks (longpair.cuh) ------------------------
 struct LongPlan { int K; int capacity_warps; };
 
-template <int K, bool PACK>
+// mode bits: 1 = PACK (the travelling H and the query base share one 32-bit shuffle word; needs H < 2^23),
+//            2 = TABLE (2-bit coded sequences, per-column score table; needs <= 4 symbols and int8 scores)
+template <int K, bool PACK, bool TABLE>
 static int long_capacity(dpx_ctx* ctx, int* warps) {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK>, 128, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK, TABLE>, 128, 0));
     *warps = per_sm * ctx->sm_count * 4;
     return DPX_OK;
 }
 
-template <int K, bool PACK>
+template <int K, bool PACK, bool TABLE>
 static int long_launch(dpx_ctx* ctx, const LongArgs& a, cudaStream_t st) {
     const int blocks = (a.nwarps + 3) / 4;
     void* kargs[] = {(void*)&a};
-    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK>, dim3(blocks), dim3(128), kargs, 0, st));
+    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK, TABLE>, dim3(blocks), dim3(128), kargs, 0, st));
     return DPX_OK;
 }
 
-// pack = the travelling H and the query base share one 32-bit shuffle word (needs H < 2^23)
-static int long_launch_k(dpx_ctx* ctx, int K, bool pack, const LongArgs& a, cudaStream_t st) {
-    switch (K) {
-        case 2: return pack ? long_launch<2, true>(ctx, a, st) : long_launch<2, false>(ctx, a, st);
-        case 4: return pack ? long_launch<4, true>(ctx, a, st) : long_launch<4, false>(ctx, a, st);
-        case 8: return pack ? long_launch<8, true>(ctx, a, st) : long_launch<8, false>(ctx, a, st);
-        default: return pack ? long_launch<16, true>(ctx, a, st) : long_launch<16, false>(ctx, a, st);
+template <int K>
+static int long_launch_m(dpx_ctx* ctx, int mode, const LongArgs& a, cudaStream_t st) {
+    switch (mode & 3) {
+        case 0: return long_launch<K, false, false>(ctx, a, st);
+        case 1: return long_launch<K, true, false>(ctx, a, st);
+        case 2: return long_launch<K, false, true>(ctx, a, st);
+        default: return long_launch<K, true, true>(ctx, a, st);
+    }
+}
+template <int K>
+static int long_capacity_m(dpx_ctx* ctx, int mode, int* warps) {
+    switch (mode & 3) {
+        case 0: return long_capacity<K, false, false>(ctx, warps);
+        case 1: return long_capacity<K, true, false>(ctx, warps);
+        case 2: return long_capacity<K, false, true>(ctx, warps);
+        default: return long_capacity<K, true, true>(ctx, warps);
     }
 }
 
-static int long_capacity_k(dpx_ctx* ctx, int K, bool pack, int* warps) {
+static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaStream_t st) {
     switch (K) {
-        case 2: return pack ? long_capacity<2, true>(ctx, warps) : long_capacity<2, false>(ctx, warps);
-        case 4: return pack ? long_capacity<4, true>(ctx, warps) : long_capacity<4, false>(ctx, warps);
-        case 8: return pack ? long_capacity<8, true>(ctx, warps) : long_capacity<8, false>(ctx, warps);
-        default: return pack ? long_capacity<16, true>(ctx, warps) : long_capacity<16, false>(ctx, warps);
+        case 2: return long_launch_m<2>(ctx, mode, a, st);
+        case 4: return long_launch_m<4>(ctx, mode, a, st);
+        case 8: return long_launch_m<8>(ctx, mode, a, st);
+        default: return long_launch_m<16>(ctx, mode, a, st);
     }
+}
+
+static int long_capacity_k(dpx_ctx* ctx, int K, int mode, int* warps) {
+    switch (K) {
+        case 2: return long_capacity_m<2>(ctx, mode, warps);
+        case 4: return long_capacity_m<4>(ctx, mode, warps);
+        case 8: return long_capacity_m<8>(ctx, mode, warps);
+        default: return long_capacity_m<16>(ctx, mode, warps);
+    }
+}
+
+// Byte -> 2-bit code map over both sequences of a long pair; returns the number of distinct symbols (codes are only
+// meaningful when it is <= 4).  Host pass over a few MB, off the kernel's path.
+static int long_alphabet(const char* ref, size_t R, const char* qry, size_t Q, uint8_t code[256]) {
+    bool present[256] = {false};
+    for (size_t i = 0; i < R; ++i) present[(uint8_t)ref[i]] = true;
+    for (size_t i = 0; i < Q; ++i) present[(uint8_t)qry[i]] = true;
+    int n = 0;
+    for (int c = 0; c < 256; ++c) { code[c] = 0; if (present[c]) code[c] = (uint8_t)(n++ & 3); }
+    return n;
+}
+
+static bool long_table_ok(const dpx_params* p, size_t R, size_t Q) {
+    const int ms = p->match - p->gap_open, xs = p->mismatch - p->gap_open;
+    // int8 table entries; the row-maximum keys are h*16 + column, so h must stay below 2^27
+    return ms >= -128 && ms <= 127 && xs >= -128 && xs <= 127 && p->match > 0 &&
+           (long double)p->match * (long double)std::min(R, Q) < 1.3e8L;
 }
 
 static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
@@ -738,8 +776,10 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
     int K = long_pick_k(ctx, (long long)R);
     if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }   // tests
     int capacity = 0;
-    const bool pack = long_can_pack(p, R, Q);
-    { int s = long_capacity_k(ctx, K, pack, &capacity); if (s) return s; }
+    uint8_t code[256];
+    const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
+    const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
+    { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
     if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
     if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
     const long long CW = 32LL * K;
@@ -766,9 +806,16 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
     const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
     if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
     if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
-    LCU(cudaMemcpyAsync(d_ref, ref, R, cudaMemcpyHostToDevice, st));
-    LCU(cudaMemcpyAsync(d_qry, qry, Q, cudaMemcpyHostToDevice, st));
+    std::vector<uint8_t> cref, cqry;
+    if (table) {
+        cref.resize(R); cqry.resize(Q);
+        for (size_t i = 0; i < R; ++i) cref[i] = code[(uint8_t)ref[i]];
+        for (size_t i = 0; i < Q; ++i) cqry[i] = code[(uint8_t)qry[i]];
+    }
+    LCU(cudaMemcpyAsync(d_ref, table ? (const char*)cref.data() : ref, R, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemcpyAsync(d_qry, table ? (const char*)cqry.data() : qry, Q, cudaMemcpyHostToDevice, st));
     LCU(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    LCU(cudaStreamSynchronize(st));
 
     int32_t best = 0; long long brow = 0, bcol = 0;
     std::vector<LongChan> chans((size_t)nw_pass + 1);
@@ -797,7 +844,8 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
         a.ref = d_ref; a.qry = d_qry; a.Q = (long long)Q; a.R_local = (long long)R; a.col0 = w0 * CW; a.col_offset = 0;
         a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open; a.nwarps = (int)nw; a.chans = d_chans;
         a.best_score = d_bs; a.best_row = d_br; a.best_col = d_bc; a.error_flag = d_err; a.system_scope = 0;
-        { int s = long_launch_k(ctx, K, pack, a, st); if (s) { cleanup(); return s; } }
+        a.tab_match = p->match - p->gap_open; a.tab_mismatch = p->mismatch - p->gap_open; a.sixteen = 16u;
+        { int s = long_launch_k(ctx, K, mode, a, st); if (s) { cleanup(); return s; } }
         LCU(cudaMemcpyAsync(h_bs.data(), d_bs, sizeof(int32_t) * (size_t)nw, cudaMemcpyDeviceToHost, st));
         LCU(cudaMemcpyAsync(h_br.data(), d_br, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
         LCU(cudaMemcpyAsync(h_bc.data(), d_bc, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
@@ -821,7 +869,7 @@ struct dpx_stripe {
     dpx_ctx* ctx = nullptr;
     dpx_params params{};
     size_t R_local = 0, col_offset = 0, Q = 0;
-    int index = 0, n = 1, K = 8, nw = 0; bool pack = false;
+    int index = 0, n = 1, K = 8, nw = 0; int mode = 0;
     static constexpr long long XRING = 65536, RING = 2048;
     // exchange buffer (own memory, exported over CUDA IPC): [1] out credit (written by the next stripe), inbox ring of
     // tagged 8-byte entries at byte 128 (written by the previous stripe)
@@ -1075,9 +1123,22 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
     // lane width: the whole stripe must be one co-resident pass
     int K = long_pick_k(ctx, (long long)R_local), cap = 0;
     if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }
-    s->pack = (long double)params->match * (long double)Q < 8.0e6L && params->match > 0;
+    // The code map must be identical on every rank, so it is fixed instead of data-derived: digits '0'..'3' and A/C/G/T
+    // (either case) map to 0..3; any other byte in this rank's data switches this stripe to the byte-compare kernel, which
+    // is still exact because all ranks then compare (query byte, reference byte) pairs -- but the QUERY must be coded the
+    // same way everywhere, so TABLE is only used when the whole query and this stripe's reference are inside the map.
+    static const auto fixed_code = [](uint8_t c) -> int {
+        switch (c) { case '0': case 'A': case 'a': return 0; case '1': case 'C': case 'c': return 1;
+                     case '2': case 'G': case 'g': return 2; case '3': case 'T': case 't': return 3; default: return -1; }
+    };
+    bool table = long_table_ok(params, Q, Q) && !getenv("DPX_LONG_NOTABLE");
+    bool digits = false, letters = false;
+    for (size_t i = 0; i < Q && table; ++i) { const uint8_t c = (uint8_t)qry[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
+    for (size_t i = 0; i < R_local && table; ++i) { const uint8_t c = (uint8_t)ref_stripe[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
+    if (digits && letters) table = false;         // '0' and 'A' would collide
+    s->mode = ((long double)params->match * (long double)Q < 8.0e6L && params->match > 0 ? 1 : 0) | (table ? 2 : 0);
     for (;;) {
-        if (long_capacity_k(ctx, K, s->pack, &cap)) return fail(DPX_ERR_CUDA);
+        if (long_capacity_k(ctx, K, s->mode, &cap)) return fail(DPX_ERR_CUDA);
         if ((long long)((R_local + 32ull * K - 1) / (32ull * K)) <= cap || K == 16) break;
         K *= 2;
     }
@@ -1093,8 +1154,14 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
               cudaMalloc(&s->d_err, sizeof(int)) == cudaSuccess &&
               cudaEventCreate(&s->e0) == cudaSuccess && cudaEventCreate(&s->e1) == cudaSuccess;
     if (!ok) { cudaGetLastError(); return fail(DPX_ERR_NOMEM); }
-    if (cudaMemcpy(s->d_ref, ref_stripe, R_local, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(s->d_qry, qry, Q, cudaMemcpyHostToDevice) != cudaSuccess ||
+    std::vector<uint8_t> cref, cqry;
+    if (table) {
+        cref.resize(R_local); cqry.resize(Q);
+        for (size_t i = 0; i < R_local; ++i) cref[i] = (uint8_t)fixed_code((uint8_t)ref_stripe[i]);
+        for (size_t i = 0; i < Q; ++i) cqry[i] = (uint8_t)fixed_code((uint8_t)qry[i]);
+    }
+    if (cudaMemcpy(s->d_ref, table ? (const char*)cref.data() : ref_stripe, R_local, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(s->d_qry, table ? (const char*)cqry.data() : qry, Q, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemset(s->xbuf, 0, 128) != cudaSuccess) return fail(DPX_ERR_CUDA);
     *out = s;
     return DPX_OK;
@@ -1161,8 +1228,9 @@ int dpx_stripe_run(dpx_stripe* s) {
     a.ref = s->d_ref; a.qry = s->d_qry; a.Q = (long long)s->Q; a.R_local = (long long)s->R_local; a.col0 = 0; a.col_offset = (long long)s->col_offset;
     a.match = s->params.match; a.mismatch = s->params.mismatch; a.gap = s->params.gap_open; a.nwarps = s->nw; a.chans = s->d_chans;
     a.best_score = s->d_bs; a.best_row = s->d_br; a.best_col = s->d_bc; a.error_flag = s->d_err; a.system_scope = s->n > 1;
+    a.tab_match = s->params.match - s->params.gap_open; a.tab_mismatch = s->params.mismatch - s->params.gap_open; a.sixteen = 16u;
     CU(cudaEventRecord(s->e0, ctx->stream));
-    { int st = long_launch_k(ctx, s->K, s->pack, a, ctx->stream); if (st) return st; }
+    { int st = long_launch_k(ctx, s->K, s->mode, a, ctx->stream); if (st) return st; }
     CU(cudaEventRecord(s->e1, ctx->stream));
     s->launched = true;
     return DPX_OK;

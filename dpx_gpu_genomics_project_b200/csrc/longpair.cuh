@@ -45,8 +45,21 @@ struct LongArgs {
     long long* best_col;      // [nwarps]  (global, 1-based)
     int* error_flag;
     int system_scope;         // 1: a channel crosses GPUs
+    // TABLE kernels: ref / qry hold 2-bit codes (one per byte) and scores come from a per-column byte table
+    int tab_match, tab_mismatch;   // match - gap, mismatch - gap (both fit int8)
+    uint32_t sixteen;              // 16, passed as data so that h*16 + (15-k) stays one IMAD on the FMA pipe
 };
 
+__device__ __forceinline__ uint32_t prmt_b32l(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));   // generic mode: nibble msb = replicate sign
+    return d;
+}
+__device__ __forceinline__ uint32_t fma_u32(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));    // b is run-time data: stays an IMAD (FMA pipe)
+    return d;
+}
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -70,7 +83,13 @@ constexpr int LONG_WATCHDOG = 1 << 22;   // polls before a stuck channel raises 
 // rows at a time with coalesced loads (issued one block ahead) and reach the lane that needs them by warp shuffle; lane 31
 // stores its finished row straight into the outgoing ring.  With PACK the travelling H and the query base share one
 // 32-bit word (H < 2^23), so a row step costs two shuffles.  Ring sizes are powers of two (index = row & (size-1)).
-template <int K, bool PACK>
+// TABLE: sequences are 2-bit codes; column k keeps a 4-byte table T[k] = (score - gap) for query codes 0..3 and the
+// registers hold hg = H + gap of the previous row, so a cell is PRMT + 2 x VIADDMNMX on the ALU pipe + one FMA-pipe add:
+//     s' = prmt(T[k], sel(q))                      t = max(hg_diag + s', hg_up)                 (VIADDMNMX)
+//     h  = max(left + gap, t, 0)  (VIADDMNMX.RELU)  hg = h + gap                                 (IMAD)
+// and the end cell is tracked per LANE (a max3 tree per row step, a rare branch when the lane's maximum grows).
+// !TABLE: byte compare + per-column tracking, for alphabets with more than four symbols.
+template <int K, bool PACK, bool TABLE>
 __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -80,18 +99,31 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
     const int Q = (int)a.Q;
     const long long cfirst = a.col0 + (long long)w * (32 * K) + (long long)lane * K;    // local 0-based
     const int g = a.gap, ma = a.match, mi = a.mismatch;
+    const uint32_t sixteen = a.sixteen;
     const unsigned imask = cin.ring ? (unsigned)(cin.size - 1) : 0u, omask = cout.ring ? (unsigned)(cout.size - 1) : 0u;
     const bool has_in = cin.ring != nullptr, has_out = cout.ring != nullptr;
 
     uint32_t rc[K]; bool cv[K];
-    int Hc[K], bestS[K], bestR[K];                 // rows fit in int32 (Q < 2^31 is checked by the host)
+    int Hc[K], bestS[TABLE ? 1 : K], bestR[TABLE ? 1 : K];   // rows fit in int32 (Q < 2^31 is checked by the host)
     #pragma unroll
     for (int k = 0; k < K; ++k) {
         cv[k] = (cfirst + k) < a.R_local;
-        rc[k] = cv[k] ? (uint32_t)a.ref[cfirst + k] : 0x100u;       // 0x100 never equals a query byte
-        Hc[k] = 0; bestS[k] = 0; bestR[k] = 0;
+        if (TABLE) {
+            // table word: byte c = (c == ref code ? match : mismatch) - gap; columns beyond the stripe never match
+            const uint32_t xs = (uint32_t)(a.tab_mismatch & 0xff), ms = (uint32_t)(a.tab_match & 0xff);
+            uint32_t t = xs * 0x01010101u;
+            if (cv[k]) { const uint32_t c = a.ref[cfirst + k] & 3u; t = (t & ~(0xffu << (8 * c))) | (ms << (8 * c)); }
+            rc[k] = t;
+            Hc[k] = g;                                                 // hg of matrix row 0: 0 + gap
+        } else {
+            rc[k] = cv[k] ? (uint32_t)a.ref[cfirst + k] : 0x100u;       // 0x100 never equals a query byte
+            Hc[k] = 0;
+        }
     }
-    int lastH = 0, leftprev = 0;
+    #pragma unroll
+    for (int k = 0; k < (TABLE ? 1 : K); ++k) { bestS[k] = 0; bestR[k] = 0; }
+    int bestC = 0;                                                  // TABLE: column index (0..K-1) of the lane's best cell
+    int lastH = 0, leftprev = TABLE ? g : 0;
     uint32_t qc = 0;
     long long credit = 0;
     bool dead = false;
@@ -157,13 +189,31 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
             }                                                                                                    \
             if (!(CHECKED) || (i >= 1 && i <= Q)) {                                                              \
                 int diag = leftprev, left = leftH;                                                               \
-                leftprev = leftH;                                                                                \
-                _Pragma("unroll")                                                                                \
-                for (int k = 0; k < K; ++k) {                                                                    \
-                    const int up = Hc[k];                                                                        \
-                    const int h = __vimax3_s32_relu(diag + (qc == rc[k] ? ma : mi), up + g, left + g);           \
-                    diag = up; Hc[k] = h; left = h;                                                              \
-                    if (h > bestS[k]) { bestS[k] = h; bestR[k] = i; }   /* first row of the column's maximum */  \
+                if (TABLE) {                                                                                     \
+                    leftprev = leftH + g;                                                                        \
+                    const uint32_t sel = qc * 0x1111u + 0x8880u;        /* byte q, sign-replicated upwards */    \
+                    /* keys h*16 + (15-k): the row maximum with its FIRST column falls out of a max3 tree */     \
+                    int m0 = 0, m1 = 0;                                                                          \
+                    _Pragma("unroll")                                                                            \
+                    for (int k = 0; k < K; ++k) {                                                                \
+                        const int sc = (int)prmt_b32l(rc[k], 0u, sel);                                           \
+                        const int t2 = __viaddmax_s32(diag, sc, Hc[k]);                                          \
+                        const int h = __viaddmax_s32_relu(left, g, t2);                                          \
+                        diag = Hc[k]; Hc[k] = h + g; left = h;                                                   \
+                        const int key = (int)fma_u32((uint32_t)h, sixteen, (uint32_t)(15 - k));   /* FMA pipe */ \
+                        if (k & 1) m1 = __vimax3_s32(m1, m0, key); else m0 = key;                                \
+                    }                                                                                            \
+                    if (K & 1) m1 = max(m1, m0);                                                                 \
+                    if ((m1 >> 4) > bestS[0]) { bestS[0] = m1 >> 4; bestR[0] = i; bestC = 15 - (m1 & 15); }      \
+                } else {                                                                                         \
+                    leftprev = leftH;                                                                            \
+                    _Pragma("unroll")                                                                            \
+                    for (int k = 0; k < K; ++k) {                                                                \
+                        const int up = Hc[k];                                                                    \
+                        const int h = __vimax3_s32_relu(diag + (qc == rc[k] ? ma : mi), up + g, left + g);       \
+                        diag = up; Hc[k] = h; left = h;                                                          \
+                        if (h > bestS[k]) { bestS[k] = h; bestR[k] = i; } /* first row of the column's max */    \
+                    }                                                                                            \
                 }                                                                                                \
                 lastH = left;                                                                                    \
                 if (has_out && lane == 31)                                                                       \
@@ -184,9 +234,14 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
 
     // ---- best cell of this warp: higher score, then smaller row, then smaller column --------------------------
     int bs = 0; long long br = 0, bc = 0;
-    #pragma unroll
-    for (int k = 0; k < K; ++k)
-        if (cv[k] && (bestS[k] > bs || (bestS[k] == bs && bs > 0 && bestR[k] < br))) { bs = bestS[k]; br = bestR[k]; bc = a.col_offset + cfirst + k + 1; }
+    if (TABLE) {
+        // invalid columns never match, so they stay below the valid cell to their left and cannot be the lane's first maximum
+        if (bestS[0] > 0) { bs = bestS[0]; br = bestR[0]; bc = a.col_offset + cfirst + bestC + 1; }
+    } else {
+        #pragma unroll
+        for (int k = 0; k < K; ++k)
+            if (cv[k] && (bestS[k] > bs || (bestS[k] == bs && bs > 0 && bestR[k] < br))) { bs = bestS[k]; br = bestR[k]; bc = a.col_offset + cfirst + k + 1; }
+    }
     #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const int os = __shfl_xor_sync(FULL, bs, off);

@@ -55,3 +55,20 @@ def test_long_pair_equals_batch_engine(eng):
     res = eng.align_batch(api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS), blob, pairs)
     s, row, col = eng.align_long_pair(api.make_params(api.LSW), r, q)
     assert (s, row, col) == (int(res.scores[0]), int(res.end_row_col[0][0]), int(res.end_row_col[0][1]))
+
+
+def test_long_pair_byte_kernel_for_wide_alphabets(eng, monkeypatch):
+    """More than four symbols (or DPX_LONG_NOTABLE) use the byte-compare kernel instead of the score-table kernel."""
+    rng = synth.Rng(9)
+    r = synth.random_seq(rng, 3000, b"01234"); q = synth.mutate(rng, r, 0.05, 0.01, 0.01, b"01234")[:2800]
+    assert eng.align_long_pair(api.make_params(api.LSW), r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
+    monkeypatch.setenv("DPX_LONG_NOTABLE", "1")
+    r, q = _pair(4000, 5000, 31)
+    assert eng.align_long_pair(api.make_params(api.LSW), r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
+
+
+def test_long_pair_letters_and_odd_weights(eng):
+    rng = synth.Rng(10)
+    r = synth.random_seq(rng, 5000, b"ACGT"); q = synth.mutate(rng, r, 0.03, 0.01, 0.01, b"ACGT")
+    for w in (dict(match=1, mismatch=-1, gap_open=-1), dict(match=5, mismatch=-4, gap_open=-7), dict(match=100, mismatch=-100, gap_open=-120)):
+        assert eng.align_long_pair(api.make_params(api.LSW, **w), r, q) == ol.lsw_score_only(ol.params(ol.LSW, **w), r, q)

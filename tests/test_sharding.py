@@ -65,3 +65,23 @@ def test_two_rank_gloo_run_reassembles_pair_order(tmp_path):
     blob, pairs = _pairs()
     s, e = _oracle_compute(blob, pairs)
     assert (got["s"] == s).all() and (got["e"] == e).all()
+
+
+# ---- mode B host logic (column stripes of one long pair) ---------------------------------------------------------
+def test_stripe_bounds_cover_the_reference_in_whole_warp_blocks():
+    from dpx_gpu_genomics_project_b200.longpair import stripe_bounds
+    for R in (1, 511, 512, 513, 40000, 1_000_000, 999_999):
+        for n in (1, 2, 3, 4, 8):
+            b = stripe_bounds(R, n)
+            assert b[0] == 0 and b[-1] == R and len(b) == n + 1
+            assert all(b[i] <= b[i + 1] for i in range(n))
+            # every stripe that is followed by a non-empty stripe ends on a multiple of 512 columns (whole warps at K <= 16)
+            assert all(b[i + 1] % 512 == 0 for i in range(n - 1) if b[i + 2] > b[i + 1])
+
+
+def test_stripe_result_reduction_follows_the_reference_end_cell_rule():
+    from dpx_gpu_genomics_project_b200.longpair import reduce_results
+    # higher score wins; ties: smaller row, then smaller column (c++/LinearSmithWaterman.cpp:145-157); score 0 never wins
+    assert reduce_results([(5, 10, 3), (7, 50, 900), None, (7, 40, 1200)]) == (7, 40, 1200)
+    assert reduce_results([(7, 40, 1200), (7, 40, 900)]) == (7, 40, 900)
+    assert reduce_results([(0, 0, 0), None]) == (0, 0, 0)

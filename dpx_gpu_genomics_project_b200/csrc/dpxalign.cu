@@ -21,6 +21,7 @@
 #include "backtrack.cuh"
 #include "shortread.cuh"
 #include "longpair.cuh"
+#include "pairwf.cuh"
 
 using namespace dpx;
 
@@ -535,6 +536,58 @@ static int ensure_str_off(dpx_batch* b) {
     return DPX_OK;
 }
 
+
+// ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
+struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc; int b0, b1, bstep, dec_sub, dec_add; };
+
+static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
+    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW) || !b->packed2 || getenv("DPX_NO_PAIRWF")) return false;
+    const bool aff = p->algo == DPX_ALGO_ANW;
+    const long long m = p->match, x = p->mismatch, go = p->gap_open, ge = aff ? p->gap_extend : 0;
+    const long long open = aff ? go + ge : go;                   // cost of the first gap column: "goe" (Gotoh) or g (linear)
+    if (open >= 0 || ge > 0 || go > 0) return false;             // the add constant must be negative (always-carry rule)
+    const long long code = aff ? 3 : 1;
+    const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
+    if (tm < 0 || tm > 255 || tx < 0 || tx > 255) return false;
+    const int K = 8;
+    const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
+    // lowest value any stored quantity can take (gaps-only path bounds H from below) and the highest score
+    const long long lo = aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
+                             : (Qp + Rp + 1) * go + std::min<long long>(x, 0) - 2;
+    const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
+    const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
+    const long long B = -4 * lo + margin;
+    if (4 * hi + B + 16 > 32767) return false;
+    uint8_t tab[8];
+    for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)tx;
+    tab[3] = (uint8_t)tm;
+    pl->K = K;
+    pl->lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
+    pl->lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
+    auto pk = [](long long v) { return (uint32_t)(v & 0xffff) * 0x00010001u; };
+    pl->ext2 = aff ? pk(4 * ge) : pk(1);
+    const long long c = aff ? 4 * open : 4 * open - 2;           // (h' | 3) + c -> code 3 (Gotoh) / code 1 (linear)
+    pl->addc = (uint32_t)(c & 0xffff) | ((uint32_t)((c - 1) & 0xffff) << 16);
+    pl->b0 = (int)(4 * open + B + code);
+    pl->b1 = aff ? (int)(4 * (go + open) + B + code) : pl->b0;
+    pl->bstep = (int)(4 * (aff ? ge : go));
+    pl->dec_sub = (int)(B + code); pl->dec_add = (int)(-open);
+    return true;
+}
+
+template <int ALGO, bool TB>
+static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
+    auto kern = pw_nw_kernel<ALGO, TB, 8>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    if (per_sm < 1) { ctx->err = "pair-wavefront kernel does not fit on an SM"; return DPX_ERR_RANGE; }
+    const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, (n_slots + 3) / 4));
+    kern<<<blocks, 128, smem, st>>>(a);
+    CU(cudaGetLastError());
+    return DPX_OK;
+}
+
 static int batch_run(dpx_batch* b, const dpx_params* p) {
     dpx_ctx* ctx = b->ctx;
     cudaStream_t st = b->stream;
@@ -604,6 +657,63 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             CU(cudaEventRecord(e, st));
             b->stats.kernel_launches = 1;
             b->stats.kernel_id = DPX_KERNEL_SHORT_S16X2;
+            CU(cudaEventRecord(b->ev_end, st));
+            return DPX_OK;
+        }
+    }
+
+    // ---- NW / Gotoh: packed two-pair wavefront with directions in the low score bits (pairwf.cuh) ------------
+    {
+        PwPlan pl;
+        if (pairwf_eligible(b, p, &pl)) {
+            const bool aff = algo == DPX_ALGO_ANW;
+            const PwGeom geo = PwGeom::make(pl.K, aff ? 4 : 2);
+            const unsigned long long tbs = want_strings ? geo.words(b->max_q, b->max_r) : 0;
+            size_t per_chunk = n;
+            if (want_strings) {
+                size_t slots = std::max<size_t>(1, std::min<size_t>((n + 1) / 2, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tbs, 1)));
+                per_chunk = 2 * slots;
+                if (!b->d_tb && !pool_alloc(ctx, &b->d_tb, slots * (size_t)tbs)) return DPX_ERR_NOMEM;
+                b->stats.traceback_bytes = (uint64_t)((n + 1) / 2) * tbs * 4;
+            }
+            PwArgs a{};
+            a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
+            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc;
+            a.one = 1u; a.two = 2u; a.four = 4u; a.eight = 8u; a.sixteen = 16u;
+            a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
+            a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
+            a.bnd_stride = b->max_r + 36; a.rsel_stride = (b->max_r + 68) & ~1;
+            const size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
+            b->stats.kernel_id = DPX_KERNEL_PAIR_S16X2;
+            int c = 0;
+            for (size_t first = 0; first < n; first += per_chunk, ++c) {
+                a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
+                a.counter = counters + (c % 64);
+                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+                cudaEvent_t s, e;
+                { int r = add_event_pair(0, &s, &e); if (r) return r; }
+                CU(cudaEventRecord(s, st));
+                const int n_slots = (a.count + 1) / 2;
+                int r;
+                if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, st, a, smem, n_slots);
+                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, st, a, smem, n_slots);
+                if (r) return r;
+                CU(cudaEventRecord(e, st));
+                b->stats.kernel_launches++;
+                if (want_strings) {
+                    PwBtArgs t{};
+                    t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.K = pl.K;
+                    t.tb = b->d_tb; t.tb_stride = tbs; t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
+                    { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
+                    CU(cudaEventRecord(s, st));
+                    const int bt_blocks = (a.count + 127) / 128;
+                    if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    CU(cudaGetLastError());
+                    CU(cudaEventRecord(e, st));
+                    b->stats.kernel_launches++;
+                }
+            }
             CU(cudaEventRecord(b->ev_end, st));
             return DPX_OK;
         }

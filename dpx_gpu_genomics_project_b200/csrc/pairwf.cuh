@@ -1,0 +1,334 @@
+// pairwf.cuh — Needleman-Wunsch fills WITH traceback in packed int16x2: LinearNeedlemanWunsch and
+// AffineNeedlemanWunsch (Gotoh), two pairs per warp, directions carried in the low bits of the scores.
+//
+// Reference semantics restated bit for bit:
+//   LNW  c++/LinearNeedlemanWunsch.cpp:89-135   two __vibmax_s32: UP if up >= diag, then LEFT if left >= max(up, diag)
+//   ANW  c++/AffineNeedlemanWunsch.cpp:167-240  D/I: tie -> GAP_OPEN (:185-213); H: UP if D >= diag, LEFT if I >= max (:229-233)
+//        borders c++/AffineNeedlemanWunsch.cpp:43-53, c++/LinearNeedlemanWunsch.cpp:31-41
+//
+// Mapping.  One warp aligns TWO pairs at once: pair A in the low, pair B in the high int16 half of every register.
+// Lane t keeps K consecutive query rows in registers and sweeps the reference columns one step behind lane t-1
+// (anti-diagonal wavefront of K-row blocks); the bottom row of a lane reaches the next lane by __shfl_up (H, and D for
+// Gotoh).  32*K rows are one pass; longer queries take several passes, the last lane's row handed over through a
+// per-warp shared-memory row.
+//
+// Arithmetic: every value X is stored as 4*X + BIAS + code.  The two low bits are a tie-break code, so a plain
+// max picks the winner AND records who won:
+//   Gotoh   ds = Ho[diag] + tab              4*(Hdiag + s)        code 0   (IMAD, FMA pipe; tab = 4*(s - goe) - 3 from PRMT)
+//           D' = viaddmax(Dc[up], 4ge, Ho[up])   extend code 1 / open code 3: tie -> OPEN; bit 1 = "D opened here"
+//           I' = viaddmax(Ic[left], 4ge, Ho[left]) extend code 2 / open code 3: tie -> OPEN; bit 0 = "I opened here"
+//           Dc = D' & ~2 (code 1), Ic = I' & ~1 (code 2)
+//           h' = vimax3(ds, Dc, Ic)          code 0 DIAG < 1 UP < 2 LEFT: exactly the reference's LEFT > UP > DIAG ties
+//           Ho = (h' | 3) + 4*goe            "H + open + extend", code 3: what the right / lower / diagonal neighbours need
+//   => per cell-pair 10 ALU-pipe (PRMT, 3 DPX, 3 LOP3 clean, 3 LOP3 to bank the 4-bit code) + 6 FMA-pipe instructions.
+//   Linear  m  = viaddmax(Hg[diag], tab, Hg[up])   diag code 0 / up code 1;  h' = viaddmax(Hg[left], 1, m)  left code 2
+//           Hg = (h' | 3) + 4g - 2           "H + gap", code 1
+//   => per cell-pair 5 ALU-pipe + 3 FMA-pipe instructions.
+// All adds that are not fused into a DPX instruction are plain 32-bit IMADs on the FMA pipe: every stored value is
+// biased positive (>= the largest |constant|), so adding a negative constant ALWAYS carries out of the low half (the
+// constant's high half is pre-decremented) and adding a table entry (>= 0) NEVER does.
+//
+// Traceback: CB = 4 bits per cell (Gotoh: dir | D-open << 2 | I-open << 3) or 2 (linear: dir); each lane-step banks K
+// cells per pair into W = K*CB/16 words whose low / high halves belong to pair A / B (row r of the block sits in
+// word r / (16/CB), nibble or bit pair (16/CB - 1 - r % (16/CB))), stored [pass][step][w][lane]: one warp store = one
+// 128-byte line.  Algorithmic traceback bytes per cell: 0.5 (Gotoh), 0.25 (linear).
+#pragma once
+#include "common.cuh"
+#include "shortread.cuh"
+
+namespace dpx {
+
+constexpr uint32_t PW_DIAG = 0, PW_UP = 1, PW_LEFT = 2;     // direction codes of this kernel family
+constexpr uint32_t PW_DOPEN = 4, PW_IOPEN = 8;
+
+struct PwGeom {
+    int K, CB, W;                // rows per lane, code bits, words per lane-step
+    DPX_HD static PwGeom make(int K, int CB) { PwGeom g; g.K = K; g.CB = CB; g.W = K * CB / 16; return g; }
+    DPX_HD int passes(int Qw) const { return (Qw + 32 * K - 1) / (32 * K); }
+    DPX_HD int nsteps(int Rw) const { return (Rw + 31 + 1) & ~1; }          // column steps incl. pipeline drain, even
+    DPX_HD unsigned long long words(int Qw, int Rw) const { return (unsigned long long)passes(Qw) * nsteps(Rw) * W * 32ull; }
+};
+
+struct PwArgs {
+    const uint32_t* packed;              // 2-bit packed sequences (pack.cuh)
+    const unsigned long long* pk_off;    // [n_pairs] word offsets, or null: pair p starts at p * pk_stride
+    unsigned long long pk_stride;
+    const dpx_seq_pair* pairs;
+    const int32_t* order;                // schedule (nullable = identity)
+    int first, count;                    // schedule positions [first, first + count) of this launch; slot s = positions first+2s, first+2s+1
+    uint32_t lut_lo, lut_hi;             // prmt table: byte 3 = match entry, every other byte = mismatch entry
+    uint32_t ext2;                       // Gotoh: packed 4*ge; linear: packed 1
+    uint32_t addc;                       // carry-compensated add constant: Gotoh 4*goe, linear 4*g - 2
+    uint32_t one, two, four, eight, sixteen;   // run-time multipliers: keep shifts / adds on the FMA pipe as IMAD
+    int b0, b1, bstep;                   // border(idx) = idx == 0 ? b0 : b1 + bstep * idx   (stored form, one half)
+    int dec_sub, dec_add;                // score = ((half - dec_sub) >> 2) + dec_add
+    int32_t* scores;
+    int32_t* end_rc;                     // nullable; NW: (Q, R)
+    uint32_t* tb;                        // traceback words of this launch (slot-major); unused when !TB
+    unsigned long long tb_stride;        // words per slot
+    unsigned int* counter;
+    int bnd_stride, rsel_stride;         // per-warp shared-memory strides (uint32 / uint16 entries)
+};
+
+__device__ __forceinline__ uint32_t fma_mul(uint32_t a, uint32_t m) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(d) : "r"(a), "r"(m));
+    return d;
+}
+__device__ __forceinline__ uint32_t pw_pack(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
+
+template <int ALGO, bool TB, int K>
+__global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
+    extern __shared__ uint32_t pw_smem[];
+    constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
+    constexpr int CB = AFF ? 4 : 2;
+    constexpr int CPH = 16 / CB;                   // cells per half-word
+    constexpr int W = K / CPH;
+    static_assert(K % CPH == 0, "K must fill whole traceback words");
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    uint32_t* __restrict__ bndH = pw_smem + (size_t)wib * a.bnd_stride * (AFF ? 2 : 1);
+    uint32_t* __restrict__ bndD = bndH + a.bnd_stride;
+    uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (size_t)4 * a.bnd_stride * (AFF ? 2 : 1)) + (size_t)wib * a.rsel_stride;
+    const uint32_t lut_lo = a.lut_lo, lut_hi = a.lut_hi, one = a.one, ext2 = a.ext2, addc = a.addc;
+    const uint32_t two = a.two, four = a.four, eight = a.eight, sixteen = a.sixteen;
+    const int n_slots = (a.count + 1) >> 1;
+    const PwGeom geo = PwGeom::make(K, CB);
+
+    for (;;) {
+        int slot = 0;
+        if (lane == 0) slot = (int)atomicAdd(a.counter, 1u);
+        slot = __shfl_sync(FULL, slot, 0);
+        if (slot >= n_slots) break;
+        const int posA = a.first + 2 * slot;
+        const int pa = a.order ? a.order[posA] : posA;
+        int pb = -1, RB = 0, QB = 0;
+        const dpx_seq_pair prA = a.pairs[pa];
+        const int RA = prA.referenceSize, QA = prA.querySize;
+        const uint32_t* refA = a.packed + (a.pk_off ? a.pk_off[pa] : (unsigned long long)pa * a.pk_stride);
+        const uint32_t* qryA = refA + ((RA + 15) >> 4);
+        const uint32_t *refB = refA, *qryB = qryA;
+        if (2 * slot + 1 < a.count) {
+            pb = a.order ? a.order[posA + 1] : posA + 1;
+            const dpx_seq_pair prB = a.pairs[pb];
+            RB = prB.referenceSize; QB = prB.querySize;
+            refB = a.packed + (a.pk_off ? a.pk_off[pb] : (unsigned long long)pb * a.pk_stride); qryB = refB + ((RB + 15) >> 4);
+        }
+        const int Rw = max(RA, RB), Qw = max(QA, QB);
+        const int passes = geo.passes(Qw);
+        const int nsteps2 = geo.nsteps(Rw);
+        uint32_t* __restrict__ tbp = TB ? (a.tb + (unsigned long long)slot * a.tb_stride) : nullptr;
+
+        // ---- per-warp column table: entry e <-> column j = e - 31; pads never match -----------------------------
+        __syncwarp();
+        for (int e = lane; e < nsteps2 + 32; e += 32) {
+            const int j = e - 31;
+            const uint32_t cA = (j >= 1 && j <= RA) ? 3u - get2(refA, j - 1) : 4u;
+            const uint32_t cB = (j >= 1 && j <= RB) ? 3u - get2(refB, j - 1) : 4u;
+            rsel[e] = (uint16_t)(cA | 0x80u | (cB << 8) | 0x8000u);
+        }
+        __syncwarp();
+
+        // where H[Q][R] of each pair appears: pass, lane, register row
+        const int ppA = (QA > 0) ? (QA - 1) / (32 * K) : -1, glA = (QA > 0) ? ((QA - 1) / K) & 31 : -1, rrA = (QA > 0) ? (QA - 1) % K : 0;
+        const int ppB = (QB > 0) ? (QB - 1) / (32 * K) : -1, glB = (QB > 0) ? ((QB - 1) / K) & 31 : -1, rrB = (QB > 0) ? (QB - 1) % K : 0;
+
+        for (int p = 0; p < passes; ++p) {
+            const int i0 = p * 32 * K + lane * K;                // rows above this lane's block; its rows are i0+1 .. i0+K
+            uint32_t qsel[K], hA[K], hB[K], Ic[AFF ? K : 1];
+            #pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int i = i0 + r;                            // 0-based query index
+                const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
+                const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
+                qsel[r] = qa | (qb << 8);
+                hA[r] = pw_pack(a.b1 + a.bstep * (i + 1));       // column 0 border of matrix row i+1
+                hB[r] = hA[r];
+                if constexpr (AFF) Ic[r] = 0x00020002u;                    // I[i][0] never wins: column 1 always opens (:201-205)
+            }
+            uint32_t botH = hA[K - 1], botD = 0x00010001u;
+            uint32_t topprev = pw_pack(i0 == 0 ? a.b0 : a.b1 + a.bstep * i0);   // H[i0][0]: diagonal of (i0+1, 1)
+            const bool more = (p + 1 < passes);
+            uint32_t* __restrict__ tbpp = TB ? (tbp + (size_t)p * nsteps2 * W * 32 + lane) : nullptr;
+
+#define DPX_PW_STEP(S, OLD, NEW)                                                                                     \
+            {                                                                                                        \
+                const int j = (S) - lane + 1;                                                                        \
+                uint32_t topH = __shfl_up_sync(FULL, botH, 1);                                                       \
+                uint32_t topD = AFF ? __shfl_up_sync(FULL, botD, 1) : 0u;                                            \
+                uint32_t acc[W > 0 ? W : 1];                                                                         \
+                _Pragma("unroll")                                                                                    \
+                for (int w = 0; w < W; ++w) acc[w] = 0;                                                              \
+                if (j >= 1) {                                                                                        \
+                    if (lane == 0) {                                                                                 \
+                        if (p == 0) { topH = pw_pack(a.b1 + a.bstep * j); topD = 0x00010001u; }  /* row 0 border; D[0][j] never wins (:185-189) */ \
+                        else { topH = bndH[j]; if (AFF) topD = bndD[j]; }                                            \
+                    }                                                                                                \
+                    const uint32_t rs = rsel[(S) - lane + 32];                                                       \
+                    uint32_t up = topH, upD = topD, diag = topprev;                                                  \
+                    topprev = topH;                                                                                  \
+                    _Pragma("unroll")                                                                                \
+                    for (int r = 0; r < K; ++r) {                                                                    \
+                        const uint32_t x = fma_add(qsel[r], one, rs);                                                \
+                        const uint32_t sc = prmt_b32(lut_lo, lut_hi, x);                                             \
+                        uint32_t h;                                                                                  \
+                        if constexpr (AFF) {                                                                             \
+                            const uint32_t ds = fma_add(diag, one, sc);                                              \
+                            const uint32_t Dn = __viaddmax_s16x2(upD, ext2, up);                                     \
+                            const uint32_t In = __viaddmax_s16x2(Ic[r], ext2, OLD[r]);                               \
+                            const uint32_t Dc = Dn & 0xFFFDFFFDu, Icn = In & 0xFFFEFFFEu;                            \
+                            h = __vimax3_s16x2(ds, Dc, Icn);                                                         \
+                            upD = Dc; Ic[r] = Icn;                                                                   \
+                            if (TB) {                                                                                \
+                                const uint32_t x2 = fma_mul(Dn, two), y8 = fma_mul(In, eight);                       \
+                                const uint32_t u = (x2 & 0x00040004u) | (h & ~0x00040004u);                          \
+                                const uint32_t v = (y8 & 0x00080008u) | (u & ~0x00080008u);                          \
+                                acc[r / CPH] = (v & 0x000F000Fu) | (fma_mul(acc[r / CPH], sixteen) & ~0x000F000Fu);  \
+                            }                                                                                        \
+                        } else {                                                                                     \
+                            const uint32_t m = __viaddmax_s16x2(diag, sc, up);                                       \
+                            h = __viaddmax_s16x2(OLD[r], ext2, m);                                                   \
+                            if (TB) acc[r / CPH] = (h & 0x00030003u) | (fma_mul(acc[r / CPH], four) & ~0x00030003u); \
+                        }                                                                                            \
+                        diag = OLD[r];                                                                               \
+                        NEW[r] = fma_add(h | 0x00030003u, one, addc);                                                \
+                        up = NEW[r];                                                                                 \
+                    }                                                                                                \
+                    botH = up; botD = upD;                                                                           \
+                    if (lane == 31 && more) { bndH[j] = botH; if (AFF) bndD[j] = botD; }                             \
+                }                                                                                                    \
+                if (TB) {                                                                                            \
+                    _Pragma("unroll")                                                                                \
+                    for (int w = 0; w < W; ++w) __stcs(tbpp + ((size_t)(S) * W + w) * 32, acc[w]);                   \
+                }                                                                                                    \
+            }
+
+            // H[Q][R] of a pair appears in lane glX at step RX + glX - 1 of pass ppX.  The step loop is cut after the step
+            // pair that contains it, so the capture stays out of the hot loop: after a pair (s, s+1) hB holds step s, hA step s+1.
+            const int sA = (p == ppA && RA > 0) ? RA + glA - 1 : -1, sB = (p == ppB && RB > 0) ? RB + glB - 1 : -1;
+            const int eA = sA >= 0 ? (sA | 1) + 1 : nsteps2, eB = sB >= 0 ? (sB | 1) + 1 : nsteps2;
+            int s = 0;
+            #pragma unroll 1
+            for (int seg = 0; seg < 3; ++seg) {
+                const int s_end = seg == 0 ? min(eA, eB) : seg == 1 ? max(eA, eB) : nsteps2;
+                #pragma unroll 1
+                for (; s < s_end; s += 2) {
+                    DPX_PW_STEP(s, hA, hB)
+                    DPX_PW_STEP(s + 1, hB, hA)
+                }
+                if (sA >= 0 && s == eA && lane == glA) {
+                    uint32_t v = 0;
+                    #pragma unroll
+                    for (int r = 0; r < K; ++r) if (r == rrA) v = (sA & 1) ? hA[r] : hB[r];
+                    a.scores[pa] = (((int)(v & 0xffffu) - a.dec_sub) >> 2) + a.dec_add;
+                }
+                if (sB >= 0 && s == eB && lane == glB) {
+                    uint32_t v = 0;
+                    #pragma unroll
+                    for (int r = 0; r < K; ++r) if (r == rrB) v = (sB & 1) ? hA[r] : hB[r];
+                    a.scores[pb] = (((int)(v >> 16) - a.dec_sub) >> 2) + a.dec_add;
+                }
+            }
+#undef DPX_PW_STEP
+            __syncwarp();
+        }
+
+        // pairs with an empty sequence: the score is a pure border cell, nothing was captured above
+        if (lane == 0) {
+            if (QA == 0 || RA == 0) { const int n = QA + RA; a.scores[pa] = (((n == 0 ? a.b0 : a.b1 + a.bstep * n) - a.dec_sub) >> 2) + a.dec_add; }
+            if (pb >= 0 && (QB == 0 || RB == 0)) { const int n = QB + RB; a.scores[pb] = (((n == 0 ? a.b0 : a.b1 + a.bstep * n) - a.dec_sub) >> 2) + a.dec_add; }
+            if (a.end_rc) {
+                a.end_rc[2 * pa] = QA; a.end_rc[2 * pa + 1] = RA;
+                if (pb >= 0) { a.end_rc[2 * pb] = QB; a.end_rc[2 * pb + 1] = RB; }
+            }
+        }
+    }
+}
+
+// ---- backtrack over the slab written above ---------------------------------------------------------------------
+// Walk rules: LNW c++/LinearNeedlemanWunsch.cpp:137-223, ANW c++/AffineNeedlemanWunsch.cpp:242-403 (3-state walk, then
+// pad rows as deletions, then columns as insertions :366-378).  One thread walks one pair.
+struct PwBtArgs {
+    const uint8_t* blob;
+    const dpx_seq_pair* pairs;
+    const int32_t* order;
+    int first, count;
+    int K;
+    const uint32_t* tb;
+    unsigned long long tb_stride;        // words per slot
+    char* strings;
+    const unsigned long long* str_off;
+    int32_t* str_start;
+};
+
+template <int ALGO, int K>
+__global__ void __launch_bounds__(128) pw_bt_kernel(const PwBtArgs a) {
+    constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
+    constexpr int CB = AFF ? 4 : 2;
+    constexpr int CPH = 16 / CB;
+    constexpr int W = K / CPH;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.count) return;
+    const int pos = a.first + t;
+    const int pid = a.order ? a.order[pos] : pos;
+    const dpx_seq_pair pr = a.pairs[pid];
+    const int R = pr.referenceSize, Q = pr.querySize;
+    int Rw = R;
+    if ((t ^ 1) < a.count) { const int po = a.order ? a.order[a.first + (t ^ 1)] : a.first + (t ^ 1); Rw = max(Rw, a.pairs[po].referenceSize); }
+    const PwGeom geo = PwGeom::make(K, CB);
+    const int nsteps2 = geo.nsteps(Rw);
+    const int half = (t & 1) * 16;
+    const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
+    const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
+    const uint32_t* __restrict__ tb = a.tb + (unsigned long long)(t >> 1) * a.tb_stride;
+
+    const size_t F = (size_t)Q + R + 1;
+    char* __restrict__ o0 = a.strings + a.str_off[pid];
+    char* __restrict__ o1 = o0 + F;
+    char* __restrict__ o2 = o1 + F;
+    long long p = (long long)F - 1;
+    o0[p] = 0; o1[p] = 0; o2[p] = 0;
+
+    auto code = [&](int i, int j) -> uint32_t {
+        const int ii = i - 1;
+        const int ps = ii / (32 * K), ln = (ii / K) & 31, r = ii % K;
+        const int s = j - 1 + ln;
+        const uint32_t w = __ldg(tb + (((size_t)ps * nsteps2 + s) * W + r / CPH) * 32 + ln);
+        return (w >> (half + (CPH - 1 - r % CPH) * CB)) & ((1u << CB) - 1u);
+    };
+    auto emit_diag = [&](int i, int j) { const char rc = ref[j - 1], qc = qry[i - 1]; --p; o0[p] = rc; o1[p] = (rc == qc) ? '*' : '|'; o2[p] = qc; };
+    auto emit_up   = [&](int i)        { --p; o0[p] = '_'; o1[p] = ' '; o2[p] = qry[i - 1]; };
+    auto emit_left = [&](int j)        { --p; o0[p] = ref[j - 1]; o1[p] = ' '; o2[p] = '_'; };
+
+    int i = Q, j = R;
+    if (!AFF) {
+        while (i != 0 || j != 0) {
+            const uint32_t c = (i == 0) ? PW_LEFT : (j == 0) ? PW_UP : code(i, j);
+            if (c == PW_DIAG) { emit_diag(i, j); --i; --j; }
+            else if (c == PW_UP) { emit_up(i); --i; }
+            else { emit_left(j); --j; }
+        }
+    } else {
+        int state = 0;                   // 0 SCORING, 1 INSERTION, 2 DELETION
+        while (i != 0 && j != 0) {
+            const uint32_t c = code(i, j);
+            if (state == 0) {
+                const uint32_t d = c & 3u;
+                if (d == PW_DIAG) { emit_diag(i, j); --i; --j; }
+                else if (d == PW_UP) state = 2;
+                else state = 1;
+            } else if (state == 1) {
+                state = (c & PW_IOPEN) ? 0 : 1;
+                emit_left(j); --j;
+            } else {
+                state = (c & PW_DOPEN) ? 0 : 2;
+                emit_up(i); --i;
+            }
+        }
+        while (i > 0) { emit_up(i); --i; }
+        while (j > 0) { emit_left(j); --j; }
+    }
+    a.str_start[pid] = (int32_t)p;
+}
+
+}  // namespace dpx

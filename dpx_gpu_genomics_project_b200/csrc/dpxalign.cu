@@ -22,6 +22,7 @@
 #include "shortread.cuh"
 #include "longpair.cuh"
 #include "pairwf.cuh"
+#include "band.cuh"
 
 using namespace dpx;
 
@@ -93,6 +94,7 @@ struct dpx_batch {
     unsigned long long* d_str_off = nullptr;
     int32_t* d_str_start = nullptr;
     unsigned long long* d_band_cells = nullptr;
+    uint8_t* d_band_qs = nullptr; uint8_t* d_band_rs = nullptr; int band_prep_w = -1;   // padded streams of the band kernel (band.cuh)
     BatchInfo* d_info = nullptr;
     // run state
     bool ran = false; dpx_params params{};
@@ -295,7 +297,7 @@ static void batch_release(dpx_batch* b) {
     DevPool& P = b->ctx->pool;
     P.release(b->d_blob_alloc); P.release(b->d_pairs); P.release(b->d_packed); P.release(b->d_pk_off); P.release(b->d_str_len);
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
-    P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info);
+    P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
     for (auto e : b->ev) cudaEventDestroy(e);
     if (b->ev_begin) cudaEventDestroy(b->ev_begin);
     if (b->ev_end) cudaEventDestroy(b->ev_end);
@@ -588,6 +590,54 @@ static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t 
     return DPX_OK;
 }
 
+
+// ---- banded Smith-Waterman with the band mapped onto one warp (band.cuh) ---------------------------------------------
+struct BandPlan { uint32_t lut_lo, lut_hi; int gadd, zerog, kb; };
+
+static bool band_eligible(const dpx_batch* b, const dpx_params* p, int band, BandPlan* pl) {
+    if (p->algo != DPX_ALGO_BSW || !b->packed2 || getenv("DPX_NO_BANDKERNEL")) return false;
+    const long long m = p->match, x = p->mismatch, g = p->gap_open;
+    if (!(m > 0 && x < 0 && g < 0) || band < 0 || band > 96) return false;
+    const long long tm = 4 * (m - g) - 1, tx = 4 * (x - g) - 1;
+    if (tm < -128 || tm > 127 || tx < -128 || tx > 127 || g < -(1 << 20)) return false;   // int8 table entries
+    const long long hcmax = 4 * m * (long long)std::min(b->max_q, b->max_r) + 3;
+    int nb = 0; while ((hcmax >> nb) != 0) ++nb;
+    const int kb = std::min(16, 32 - nb);
+    if (kb < 4) return false;
+    uint8_t tab[8];
+    for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)tx;
+    tab[3] = (uint8_t)tm;
+    pl->lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
+    pl->lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
+    pl->gadd = (int)(4 * g - 2); pl->zerog = (int)(4 * g + 1); pl->kb = kb;
+    return true;
+}
+
+template <int M, bool EXTRA>
+static int launch_band(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, bool tb) {
+    auto go = [&](auto kern) -> int {
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+        const int blocks = std::max(1, std::min(ctx->sm_count * std::max(per_sm, 1), (a.count + 3) / 4));
+        kern<<<blocks, 128, 0, st>>>(a);
+        CU(cudaGetLastError());
+        return DPX_OK;
+    };
+    return tb ? go(band_sw_kernel<M, EXTRA, true>) : go(band_sw_kernel<M, EXTRA, false>);
+}
+
+static int launch_band_any(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, bool tb) {
+    const BandGeom g = BandGeom::make(a.W);
+    switch (g.M * 2 + g.extra) {
+        case 2: return launch_band<1, false>(ctx, st, a, tb);
+        case 3: return launch_band<1, true>(ctx, st, a, tb);
+        case 4: return launch_band<2, false>(ctx, st, a, tb);
+        case 5: return launch_band<2, true>(ctx, st, a, tb);
+        case 6: return launch_band<3, false>(ctx, st, a, tb);
+        default: return launch_band<3, true>(ctx, st, a, tb);
+    }
+}
+
 static int batch_run(dpx_batch* b, const dpx_params* p) {
     dpx_ctx* ctx = b->ctx;
     cudaStream_t st = b->stream;
@@ -709,6 +759,62 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     const int bt_blocks = (a.count + 127) / 128;
                     if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, st>>>(t);
                     else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    CU(cudaGetLastError());
+                    CU(cudaEventRecord(e, st));
+                    b->stats.kernel_launches++;
+                }
+            }
+            CU(cudaEventRecord(b->ev_end, st));
+            return DPX_OK;
+        }
+    }
+
+    // ---- banded SW: the band mapped onto one warp (band.cuh) ----------------------------------------------------
+    {
+        BandPlan pl;
+        if (band_eligible(b, p, band, &pl)) {
+            const BandGeom geo = BandGeom::make(band);
+            const int qs_len = geo.qs_len(b->max_q, b->max_r), rs_len = geo.rs_len(b->max_q, b->max_r);
+            if (b->band_prep_w != band) {
+                if (b->d_band_qs) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_band_qs); ctx->pool.release(b->d_band_rs); b->d_band_qs = b->d_band_rs = nullptr; }
+                if (!pool_alloc(ctx, &b->d_band_qs, n * (size_t)qs_len) || !pool_alloc(ctx, &b->d_band_rs, n * (size_t)rs_len)) return DPX_ERR_NOMEM;
+                band_prep_kernel<<<std::min<int>((int)((n + 7) / 8), ctx->sm_count * 8), 256, 0, st>>>(
+                    b->d_packed, b->d_pk_off, b->pk_stride, b->d_pairs, (int)n, geo.offq(), geo.offr(), qs_len, rs_len, b->d_band_qs, b->d_band_rs);
+                CU(cudaGetLastError());
+                b->band_prep_w = band;
+                CU(cudaEventRecord(b->ev_begin, st));       // stream layout is per-batch preparation, like the 2-bit pack
+            }
+            const unsigned long long tbs = want_strings ? geo.words(b->max_q, b->max_r) : 0;
+            size_t per_chunk = n;
+            if (want_strings) {
+                per_chunk = std::max<size_t>(1, std::min<size_t>(n, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tbs, 1)));
+                if (!b->d_tb && !pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tbs)) return DPX_ERR_NOMEM;
+                b->stats.traceback_bytes = (uint64_t)n * tbs * 4;
+            }
+            BandArgs a{};
+            a.pairs = b->d_pairs; a.order = b->d_order; a.qs = b->d_band_qs; a.rs = b->d_band_rs; a.qs_len = qs_len; a.rs_len = rs_len;
+            a.W = band; a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.gadd = pl.gadd; a.zerog = pl.zerog; a.kb = pl.kb; a.kmul = 1u << pl.kb;
+            a.one = 1u; a.four = 4u; a.sixteen = 16u; a.minus1 = 0xffffffffu; a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
+            b->stats.kernel_id = DPX_KERNEL_BAND_S32;
+            int c = 0;
+            for (size_t first = 0; first < n; first += per_chunk, ++c) {
+                a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
+                a.counter = counters + (c % 64);
+                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+                cudaEvent_t s, e;
+                { int r = add_event_pair(0, &s, &e); if (r) return r; }
+                CU(cudaEventRecord(s, st));
+                { int r = launch_band_any(ctx, st, a, want_strings); if (r) return r; }
+                CU(cudaEventRecord(e, st));
+                b->stats.kernel_launches++;
+                if (want_strings) {
+                    BandBtArgs t{};
+                    t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.W = band;
+                    t.scores = b->d_scores; t.end_rc = b->d_end_rc; t.tb = b->d_tb; t.tb_stride = tbs;
+                    t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
+                    { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
+                    CU(cudaEventRecord(s, st));
+                    band_bt_kernel<<<(a.count + 3) / 4, 128, 0, st>>>(t);
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, st));
                     b->stats.kernel_launches++;

@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                                 const uint32_t x2 = fma_mul(Dn, two), y8 = fma_mul(In, eight);                       \
                                 const uint32_t u = (x2 & 0x00040004u) | (h & ~0x00040004u);                          \
                                 const uint32_t v = (y8 & 0x00080008u) | (u & ~0x00080008u);                          \
-                                acc[r / CPH] = (v & 0x000F000Fu) | (fma_mul(acc[r / CPH], sixteen) & ~0x000F000Fu);  \
+                                acc[r / CPH] = fma_add(acc[r / CPH], sixteen, v & 0x000F000Fu);                       \
                             }                                                                                        \
                         } else {                                                                                     \
                             const uint32_t m = __viaddmax_s16x2(diag, sc, up);                                       \
                             h = __viaddmax_s16x2(OLD[r], ext2, m);                                                   \
-                            if (TB) acc[r / CPH] = (h & 0x00030003u) | (fma_mul(acc[r / CPH], four) & ~0x00030003u); \
+                            if (TB) acc[r / CPH] = fma_add(acc[r / CPH], four, h & 0x00030003u);                     \
                         }                                                                                            \
                         diag = OLD[r];                                                                               \
                         NEW[r] = fma_add(h | 0x00030003u, one, addc);                                                \

@@ -26,8 +26,7 @@
 //
 // Traceback: one 16-bit field per lane and super-step (2 bits per slot, order E[0..M-1], extra, O[0..M-1], first slot
 // in the highest bits), two steps per 32-bit word, stored [step/2][lane]: one warp store = one 128-byte line.
-// Backtrack: one warp per pair; the warp pulls 64 super-steps of traceback (4 KB, coalesced) and the matching sequence
-// bytes into shared memory, lane 0 walks inside that window, the warp flushes the emitted characters coalesced.
+// Backtrack: one thread per pair, private shared-memory windows of the traceback refilled warp-synchronously (below).
 #pragma once
 #include "common.cuh"
 #include "shortread.cuh"
@@ -228,6 +227,7 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
 // ---- backtrack: one warp per pair --------------------------------------------------------------------------------
 struct BandBtArgs {
     const uint8_t* blob;
+    const uint8_t* blob_lo;              // first byte of the blob allocation (4-byte aligned): lower clamp of the word loads
     const dpx_seq_pair* pairs;
     const int32_t* order;
     int first, count;
@@ -237,81 +237,142 @@ struct BandBtArgs {
     char* strings; const unsigned long long* str_off; int32_t* str_start;
 };
 
-constexpr int BAND_BT_ROWS = 32;          // traceback rows (2 super-steps each) per window
-constexpr int BAND_BT_MOVES = 64;         // moves per window (a move lowers the super-step by at most one)
+constexpr int BAND_BT_MOVES = 32;                         // moves per round (a move lowers the super-step by <= 1)
+constexpr int BAND_BT_NEED = BAND_BT_MOVES / 2 + 2;       // traceback rows (2 super-steps each) one round can touch
+constexpr int BAND_BT_AHEAD = 2 * BAND_BT_NEED;           // rows requested per round: this round's and the next one's
+constexpr int BAND_BT_RING = 64;                          // rows of the per-walker ring (power of two > BAND_BT_AHEAD)
+constexpr int BAND_BT_LANES = 4;                          // words per row: the aligned group of four owner lanes around the walk (one 16-byte copy)
+constexpr int BAND_BT_CRING = 32;                         // words of the per-walker sequence-byte rings (128 bytes each, filled 16 bytes at a time)
+constexpr int BAND_BT_OUT_STRIDE = 3 * BAND_BT_MOVES + 4; // bytes per walker of the output staging (odd word stride: no bank conflicts)
+constexpr int BAND_BT_WIN_WORDS = BAND_BT_RING * BAND_BT_LANES * 32;
+constexpr int BAND_BT_SMEM_WORDS = BAND_BT_WIN_WORDS + 2 * BAND_BT_CRING * 32 + 32 * BAND_BT_OUT_STRIDE / 4;
+static_assert(BAND_BT_MOVES == 32, "the flush writes one character per lane");
 
-__global__ void __launch_bounds__(128) band_bt_kernel(const BandBtArgs a) {
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// One THREAD walks one pair, one warp per block.  Every walker keeps private shared-memory rings of the traceback rows
+// around its position (the aligned group of four owner lanes = 16 diagonals) and of the sequence bytes it is about to emit, filled by 16-byte cp.async one
+// round AHEAD: a round requests the rows the next round can reach and waits only for what the previous round requested, so
+// the HBM latency of the scattered 4-byte reads is off the walk's critical path.  Then every walker takes up to
+// BAND_BT_MOVES branch-free steps out of shared memory, and the warp flushes all walkers' characters with coalesced stores.
+// A walk that drifts out of its four-lane window re-centres it (one exposed round trip) or reads the word from global memory.
+__global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ uint32_t s_win[4][BAND_BT_ROWS * 32];
-    __shared__ uint8_t s_q[4][BAND_BT_MOVES], s_r[4][BAND_BT_MOVES];
-    __shared__ char s_out[4][3][BAND_BT_MOVES];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= a.count) return;
-    const int pid = a.order ? a.order[a.first + t] : (a.first + t);
-    const dpx_seq_pair pr = a.pairs[pid];
-    const int R = pr.referenceSize, Q = pr.querySize, W = a.W;
+    extern __shared__ uint32_t bt_smem[];
+    __shared__ uint16_t s_lut[2 * 96 + 2];                       // diagonal c -> owner lane | bit position << 8
+    const int lane = threadIdx.x;
+    const int t = blockIdx.x * 32 + lane;
+    const bool live = t < a.count;
+    const int W = a.W;
     const BandGeom geo = BandGeom::make(W);
     const int M = geo.M, S = geo.slots();
-    const int kinv = M == 1 ? 256 : M == 2 ? 128 : 86;
-    const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
-    const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
-    const uint32_t* __restrict__ tb = a.tb + (unsigned long long)t * a.tb_stride;
-    uint32_t* win = s_win[wib];
+    for (int c = lane; c <= 2 * W; c += 32) {
+        const int k = c >> 1, isO = c & 1;
+        const int owner = min(k / M, 31);
+        const int slot = isO ? (M + geo.extra + (k - owner * M)) : (k - owner * M);      // processing order E.., extra, O..
+        s_lut[c] = (uint16_t)(owner | ((2 * (S - 1 - slot)) << 8));
+    }
+    __syncwarp();
+    uint32_t* win = bt_smem + lane * 4;                          // [row & 63][lane][4 words]: one 16-byte cp.async per row
+    uint32_t* rring = bt_smem + BAND_BT_WIN_WORDS + lane * 4;    // [(16-byte block address) & 7][lane][4 words]
+    uint32_t* qring = rring + BAND_BT_CRING * 32;
+    char* outw = reinterpret_cast<char*>(bt_smem + BAND_BT_WIN_WORDS + 2 * BAND_BT_CRING * 32);
+    char* out = outw + lane * BAND_BT_OUT_STRIDE;                // this walker's 3 x MOVES characters, filled from the back
+    const uintptr_t blob_lo = (uintptr_t)a.blob_lo;
 
-    const size_t F = (size_t)Q + R + 1;
-    char* __restrict__ o0 = a.strings + a.str_off[pid];
-    char* __restrict__ o1 = o0 + F;
-    char* __restrict__ o2 = o1 + F;
-    long long p = (long long)F - 1;
-    if (lane == 0) { o0[p] = 0; o1[p] = 0; o2[p] = 0; }
-    int i = 0, j = 0, done = 1;
-    if (a.scores[pid] > 0) { i = a.end_rc[2 * pid]; j = a.end_rc[2 * pid + 1]; done = 0; }
+    int pid = 0, i = 0, j = 0, done = 1;
+    const uint8_t *ref = nullptr, *qry = nullptr;
+    const uint32_t* tb = nullptr;
+    char *o0 = nullptr, *o1 = nullptr, *o2 = nullptr;
+    long long p = 0;
+    if (live) {
+        pid = a.order ? a.order[a.first + t] : (a.first + t);
+        const dpx_seq_pair pr = a.pairs[pid];
+        ref = a.blob + pr.referenceIdx; qry = a.blob + pr.queryIdx;
+        tb = a.tb + (unsigned long long)t * a.tb_stride;
+        const size_t F = (size_t)pr.querySize + pr.referenceSize + 1;
+        o0 = a.strings + a.str_off[pid]; o1 = o0 + F; o2 = o1 + F;
+        p = (long long)F - 1;
+        o0[p] = 0; o1[p] = 0; o2[p] = 0;
+        if (a.scores[pid] > 0) { i = a.end_rc[2 * pid]; j = a.end_rc[2 * pid + 1]; done = 0; }
+    }
+    // walk state: diagonal c = j - i + W and super-step u = i + (c >> 1) - 1 move incrementally:
+    //   DIAG: u-1;   UP: c+1, u-1 if c is even;   LEFT: c-1, u-1 if c is even
+    int c = j - i + W, u = i + (c >> 1) - 1;
+    int lane_lo = -100, row_loaded = 0;                          // rows [row_loaded, ...) of lanes lane_lo..lane_lo+2 are requested
+    uintptr_t r_loaded = 0, q_loaded = 0;                        // word addresses [x_loaded, ...) are requested
 
-    while (!done) {
-        // window: traceback rows [row_lo, row_hi] and the sequence bytes the next BAND_BT_MOVES moves can touch
-        const int c0 = j - i + W, k0 = c0 >> 1;
-        const int row_hi = (i + k0 - 1) >> 1, row_lo = max(0, row_hi - (BAND_BT_ROWS - 1));
-        __syncwarp();
-        for (int rr = 0; rr <= row_hi - row_lo; ++rr) win[rr * 32 + lane] = __ldcs(tb + (size_t)(row_lo + rr) * 32 + lane);
-        for (int x = lane; x < BAND_BT_MOVES; x += 32) {
-            s_q[wib][x] = (i - 1 - x >= 0) ? qry[i - 1 - x] : 0;
-            s_r[wib][x] = (j - 1 - x >= 0) ? ref[j - 1 - x] : 0;
+    while (__any_sync(FULL, !done)) {
+        if (!done) {
+            bool fresh = false;
+            const int row_hi = u >> 1;
+            const int owner = (int)(s_lut[c] & 0xff);
+            if ((unsigned)(owner - lane_lo) >= (unsigned)BAND_BT_LANES) {        // first round, or the walk left the window
+                lane_lo = owner & ~3;
+                row_loaded = row_hi + 1; fresh = true;
+            }
+            const int row_to = max(row_hi - (BAND_BT_AHEAD - 1), 0);
+            for (int row = row_loaded - 1; row >= row_to; --row) cp_async16(win + (row & (BAND_BT_RING - 1)) * 128, tb + (size_t)row * 32 + lane_lo);
+            row_loaded = min(row_loaded, row_to);
+            // sequence bytes [j - 2*MOVES, j) and [i - 2*MOVES, i) as aligned words, never below the start of the blob allocation
+            const uintptr_t r_hi = ((uintptr_t)(ref + j - 1)) & ~(uintptr_t)15, q_hi = ((uintptr_t)(qry + i - 1)) & ~(uintptr_t)15;
+            const uintptr_t r_to = max(((uintptr_t)(ref + j) - 2 * BAND_BT_MOVES) & ~(uintptr_t)15, blob_lo);
+            const uintptr_t q_to = max(((uintptr_t)(qry + i) - 2 * BAND_BT_MOVES) & ~(uintptr_t)15, blob_lo);
+            if (r_loaded == 0) { r_loaded = r_hi + 16; q_loaded = q_hi + 16; fresh = true; }
+            for (uintptr_t x = r_loaded; x > r_to; ) { x -= 16; cp_async16(rring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * 128, (const void*)x); }
+            for (uintptr_t x = q_loaded; x > q_to; ) { x -= 16; cp_async16(qring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * 128, (const void*)x); }
+            r_loaded = min(r_loaded, r_to); q_loaded = min(q_loaded, q_to);
+            cp_async_commit();
+            if (fresh) cp_async_wait<0>(); else cp_async_wait<1>();
         }
         __syncwarp();
         int cnt = 0;
-        if (lane == 0) {
-            const int i_start = i, j_start = j;
-            while (cnt < BAND_BT_MOVES) {
-                const int c = j - i + W;
-                uint32_t code = BD_STOP;
-                if (i >= 1 && j >= 1 && c >= 0 && c <= 2 * W) {
-                    const int k = c >> 1, isO = c & 1;
-                    const int u = i + k - 1;
-                    if ((u >> 1) < row_lo) break;                         // next window
-                    const int owner = min((k * kinv) >> 8, 31);                 // k / M for M <= 3
-                    const int slot = isO ? (M + geo.extra + (k - owner * M)) : (k - owner * M);    // processing order E.., extra, O..
-                    const uint32_t w = win[((u >> 1) - row_lo) * 32 + owner];
-                    code = (w >> ((u & 1) * 16 + 2 * (S - 1 - slot))) & 3u;
-                }
-                if (code == BD_STOP) { done = 1; break; }
-                const char rc = (char)s_r[wib][j_start - j], qc = (char)s_q[wib][i_start - i];
-                if (code == BD_DIAG) { s_out[wib][0][cnt] = rc; s_out[wib][1][cnt] = (rc == qc) ? '*' : '|'; s_out[wib][2][cnt] = qc; --i; --j; }
-                else if (code == BD_UP) { s_out[wib][0][cnt] = '_'; s_out[wib][1][cnt] = ' '; s_out[wib][2][cnt] = qc; --i; }
-                else { s_out[wib][0][cnt] = rc; s_out[wib][1][cnt] = ' '; s_out[wib][2][cnt] = '_'; --j; }
-                ++cnt;
-                if (i == 0 || j == 0) { done = 1; break; }                // the next cell is a border cell: H == 0
-            }
+        #pragma unroll 1
+        for (int mv = 0; mv < BAND_BT_MOVES; ++mv) {
+            if (__all_sync(FULL, done)) break;
+            if (done) continue;
+            const uint32_t e = s_lut[c];
+            const int wl = (int)(e & 0xffu) - lane_lo;
+            const uint32_t w = ((unsigned)wl < (unsigned)BAND_BT_LANES) ? win[((u >> 1) & (BAND_BT_RING - 1)) * 128 + wl]
+                                                                        : __ldg(tb + (size_t)(u >> 1) * 32 + (e & 0xffu));
+            const uint32_t code = (w >> ((u & 1) * 16 + (e >> 8))) & 3u;
+            if (code == BD_STOP) { done = 1; continue; }
+            const uintptr_t ar = (uintptr_t)(ref + j - 1), aq = (uintptr_t)(qry + i - 1);
+            const char rc = (char)((rring[((ar >> 4) & (BAND_BT_CRING / 4 - 1)) * 128 + ((ar >> 2) & 3)] >> (8 * (ar & 3))) & 0xffu);
+            const char qc = (char)((qring[((aq >> 4) & (BAND_BT_CRING / 4 - 1)) * 128 + ((aq >> 2) & 3)] >> (8 * (aq & 3))) & 0xffu);
+            ++cnt;
+            out[BAND_BT_MOVES - cnt] = (code == BD_UP) ? '_' : rc;
+            out[2 * BAND_BT_MOVES - cnt] = (code == BD_DIAG) ? ((rc == qc) ? '*' : '|') : ' ';
+            out[3 * BAND_BT_MOVES - cnt] = (code == BD_LEFT) ? '_' : qc;
+            u -= ((code == BD_DIAG) | ((c & 1) ^ 1));
+            c += (code == BD_UP) - (code == BD_LEFT);
+            i -= (code != BD_LEFT); j -= (code != BD_UP);
+            if (i == 0 || j == 0 || c < 0 || c > 2 * W) done = 1;   // the next cell is a border or out-of-band cell: H == 0
         }
-        cnt = __shfl_sync(FULL, cnt, 0); done = __shfl_sync(FULL, done, 0);
-        i = __shfl_sync(FULL, i, 0); j = __shfl_sync(FULL, j, 0);
         __syncwarp();
-        for (int x = lane; x < cnt; x += 32) {               // x-th emitted character sits at position p - 1 - x
-            o0[p - 1 - x] = s_out[wib][0][x]; o1[p - 1 - x] = s_out[wib][1][x]; o2[p - 1 - x] = s_out[wib][2][x];
-        }
+        // flush: the warp writes every walker's new characters with coalesced byte stores (positions [p - cnt, p) of each field)
         p -= cnt;
+        #pragma unroll 4
+        for (int w = 0; w < 32; ++w) {
+            const int n = __shfl_sync(FULL, cnt, w);
+            if (n == 0) continue;
+            const char* src = outw + w * BAND_BT_OUT_STRIDE + (BAND_BT_MOVES - n);
+            char* d0 = (char*)__shfl_sync(FULL, (unsigned long long)(o0 + p), w);
+            const long long Fw = __shfl_sync(FULL, (long long)(o1 - o0), w);
+            if (lane < n) { d0[lane] = src[lane]; d0[Fw + lane] = src[BAND_BT_MOVES + lane]; d0[2 * Fw + lane] = src[2 * BAND_BT_MOVES + lane]; }
+        }
+        __syncwarp();
     }
-    if (lane == 0) a.str_start[pid] = (int32_t)p;
+    if (live) a.str_start[pid] = (int32_t)p;
 }
 
 }  // namespace dpx

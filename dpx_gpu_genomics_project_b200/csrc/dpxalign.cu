@@ -809,12 +809,14 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 b->stats.kernel_launches++;
                 if (want_strings) {
                     BandBtArgs t{};
-                    t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.W = band;
+                    t.blob = b->d_blob; t.blob_lo = b->d_blob_alloc; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.W = band;
                     t.scores = b->d_scores; t.end_rc = b->d_end_rc; t.tb = b->d_tb; t.tb_stride = tbs;
                     t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, st));
-                    band_bt_kernel<<<(a.count + 3) / 4, 128, 0, st>>>(t);
+                    const size_t bt_smem = (size_t)BAND_BT_SMEM_WORDS * sizeof(uint32_t);
+                    CU(cudaFuncSetAttribute(band_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+                    band_bt_kernel<<<(a.count + 31) / 32, 32, bt_smem, st>>>(t);
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, st));
                     b->stats.kernel_launches++;

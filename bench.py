@@ -1,19 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the alignment hot path (BASELINE.json metric: GCUPS).
+"""bench.py — benchmark of the alignment hot path (BASELINE.json metric: GCUPS).
 
-Workload at N=1 (BASELINE.json configs[1]): batched LinearSmithWaterman, 1 000 000 synthetic DNA pairs of
-150 x 150 bp, score + end coordinates, match 3 / mismatch -1 / gap -2.  A "step" is one pass of the hot path
-over that batch.  With N>1 (torchrun, one rank per GPU) every rank aligns its own 1M-pair shard (independent
-pairs: no data-path collective, weak scaling); value = cells of all ranks / max-over-ranks device time.
+Default workload (N=1, BASELINE.json configs[1]): batched LinearSmithWaterman, 1 000 000 synthetic DNA pairs of
+150 x 150 bp, score + end coordinates, match 3 / mismatch -1 / gap -2.  `--config 3` / `--config 4` run BASELINE configs
+[2] / [3] (AffineNeedlemanWunsch 1000 x 1000 with full traceback + alignment strings; BandedSmithWaterman band 64 on
+10 kbp x 10 kbp with traceback + strings) through the same code.  A "step" is one pass of the hot path over the batch.
+With N>1 (torchrun, one rank per GPU) every rank aligns its own shard of that size (independent pairs: no data-path
+collective, weak scaling); value = cells of all ranks / max-over-ranks device time.
 
-  value     GCUPS with the batch already resident (packed) in HBM: CUDA events around dpx_batch_run.
-  e2e       GCUPS through the one-call C ABI (dpx_align_batch) with pinned HOST buffers in and out:
-            H2D of the parseInput blob + index, alphabet scan + 2-bit pack, kernel, D2H of scores/end cells.
-  roofline  DPX-issue roofline of the dominant kernel (north_star / SURVEY.md §8d):
-            cells/clk/SM = min(64 / ALU-pipe instr per cell, 128 / issued instr per cell) from the committed SASS
-            counts (profiles/sass_counts.json) x SMs x SM clock sampled during the timed region; the HBM view of
-            the same launch (algorithmic bytes / time vs MEASURED_PEAKS.json) is reported beside it.
-  cpu_baseline  the reference's own C++ classes (oracle/_ref/ref_align) on the host cores, bounded sample.
+  value     GCUPS with the batch already resident (packed) in HBM: CUDA events around dpx_batch_run (fill kernel, and for
+            traceback configs the GPU backtrack that leaves the alignment strings in HBM).
+  e2e       GCUPS through the one-call C ABI (dpx_align_batch) with HOST buffers in and out: H2D of the parseInput blob +
+            index, alphabet scan + 2-bit pack, kernels, D2H of scores / end cells (and of the strings for configs 3, 4).
+  roofline  DPX-issue roofline of the dominant kernel (north_star / SURVEY.md §8d): cells/clk/SM = min(64 / ALU-pipe instr
+            per cell, 128 / issued instr per cell) from the committed SASS counts (profiles/sass_counts.json) x SMs x SM
+            clock sampled during the timed region; the HBM view of the same launch (algorithmic bytes / kernel time vs
+            MEASURED_PEAKS.json) is reported beside it — for the traceback configs that is the packed traceback stream.
+  cpu_baseline  the reference's own C++ classes (oracle/_ref/ref_align) on the host cores, bounded sample (config 4: the C
+            port, because the reference's banded class is not executable).
 
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
 """
@@ -33,8 +37,22 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 METRIC = "GCUPS"
-R_LEN, Q_LEN = 150, 150
-WEIGHTS = dict(match=3, mismatch=-1, gap_open=-2)
+
+# BASELINE.json configs (1-based numbering of SURVEY.md §8d): shapes, weights, outputs, the kernel that dominates the step
+WORKLOADS = {
+    2: dict(algo="LSW", R=150, Q=150, pairs=1_000_000, weights=dict(match=3, mismatch=-1, gap_open=-2), strings=False, seed=0x5EED0002,
+            gen="uniform", dtype="int16x2", kernel="sr_lsw_kernel<G=8,K=19>", sass="shortread_s16x2:G=8,K=19,track={track},xormode=False",
+            title="LinearSmithWaterman batch: {pairs} pairs x (150x150) bp per GPU, score{ends}, match 3 / mismatch -1 / gap -2",
+            cpu_per_core=0.045e9),
+    3: dict(algo="ANW", R=1000, Q=1000, pairs=100_000, weights=dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1), strings=True, seed=0x5EED0003,
+            gen=(0.02, 0.005, 0.005), dtype="int16x2", kernel="pw_nw_kernel<ANW,TB,K=8> (+ pw_bt_kernel)", sass="pairwf_s16x2:algo=1,traceback=True,K=8",
+            title="AffineNeedlemanWunsch (Gotoh H/E/F) batch: {pairs} pairs x (1000x1000) bp per GPU, full 4-bit traceback + alignment strings, "
+                  "match 3 / mismatch -1 / open -3 / extend -1", cpu_per_core=0.024e9, tb_bytes_per_cell=0.5),
+    4: dict(algo="BSW", R=10000, Q=10000, pairs=10_000, weights=dict(match=3, mismatch=-1, gap_open=-2, band=64), strings=True, seed=0x5EED0004,
+            gen=(0.05, 0.01, 0.01), dtype="int32", kernel="band_sw_kernel<M=2,EXTRA,TB> (+ band_bt_kernel)", sass="band_s32:M=2,extra=True,traceback=True",
+            title="BandedSmithWaterman band 64: {pairs} pairs x (10 kbp x 10 kbp) per GPU, 2-bit traceback + alignment strings, in-band cells, "
+                  "match 3 / mismatch -1 / gap -2", cpu_per_core=0.05e9, tb_bytes_per_cell=0.25),
+}
 
 
 def env_int(name, default):
@@ -101,47 +119,71 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
 
 
-def sass_counts(track=True):
-    """ALU-pipe and issued instructions per cell of the short-read kernel, from the committed SASS counts."""
+def sass_counts(key):
+    """ALU-pipe and issued instructions per cell of a kernel's hot loop, from the committed SASS counts."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
-        k = d[f"shortread_s16x2:G=8,K=19,track={track},xormode=False"]
+        k = d[key]
         return k["alu_per_cell"], k["issue_per_cell"]
     except Exception:
         return None, None
 
 
-# ---- CPU reference arm ------------------------------------------------------------------------------------
-def run_cpu_reference(blob, pairs, n_sample, threads):
-    """Reference C++ classes (oracle/_ref/ref_align, compiled from the unmodified sources) on `threads` host
-    threads over the first n_sample pairs; falls back to the C port (oracle/liboracle.so) if the binary is
-    absent.  Returns (gcups, kind, seconds)."""
+def make_inputs(wl, n_pairs, seed):
+    """(blob, pairs) in parseInput's output form for `n_pairs` pairs of the workload."""
+    from dpx_gpu_genomics_project_b200 import synth
+    if wl["gen"] == "uniform":
+        return synth.uniform_blob_pairs(n_pairs, wl["R"], wl["Q"], seed)
     import oracle_lib as ol
-    n_sample = int(min(n_sample, len(pairs)))
-    cells = float((pairs["referenceSize"][:n_sample].astype(np.int64) * pairs["querySize"][:n_sample]).sum())
-    if ol.have_ref_binary():
-        from dpx_gpu_genomics_project_b200 import synth
+    sub, ins, dele = wl["gen"]
+    img = synth.mutated_fixed_file_bytes(n_pairs, wl["R"], wl["Q"], seed, sub, ins, dele)
+    return ol.parse_image(img)
+
+
+def total_cells(wl, pairs):
+    r = pairs["referenceSize"].astype(np.int64); q = pairs["querySize"].astype(np.int64)
+    if wl["algo"] != "BSW":
+        return float((r * q).sum())
+    W = wl["weights"]["band"]                      # in-band cells: sum_i |{j in [1,R] : |i-j| <= W}|  (uniform lengths here)
+    Q, R = int(q[0]), int(r[0])
+    i = np.arange(1, Q + 1, dtype=np.int64)
+    per_pair = float(np.maximum(0, np.minimum(R, i + W) - np.maximum(1, i - W) + 1).sum())
+    return per_pair * len(pairs)
+
+
+# ---- CPU reference arm ------------------------------------------------------------------------------------
+def run_cpu_reference(wl, blob, pairs, n_sample, threads):
+    """Reference C++ classes (oracle/_ref/ref_align, compiled from the unmodified sources) on `threads` host threads over the
+    first n_sample pairs; the C port (oracle/liboracle.so) when the binary is absent or the algorithm is the banded one
+    (c++/BandedSmithWaterman.cpp is not executable).  Returns (gcups, kind, seconds)."""
+    import oracle_lib as ol
+    from dpx_gpu_genomics_project_b200 import synth
+    n_sample = int(max(1, min(n_sample, len(pairs))))
+    cells = total_cells(wl, pairs[:n_sample])
+    w = wl["weights"]
+    if wl["algo"] != "BSW" and ol.have_ref_binary():
         end = int(pairs["queryIdx"][n_sample - 1] + pairs["querySize"][n_sample - 1] + 1)
         with tempfile.NamedTemporaryFile(prefix="dpx_cpu_", suffix=".txt", delete=False) as f:
             f.write(synth.blob_to_file_bytes(blob[:end]).tobytes())
             path = f.name
         try:
-            cmd = [ol.REF_ALIGN, "-algo", "LSW", "-pairs", path, "-match", str(WEIGHTS["match"]), "-mismatch", str(WEIGHTS["mismatch"]),
-                   "-open", str(WEIGHTS["gap_open"]), "-threads", str(threads), "-noheader"]
+            cmd = [ol.REF_ALIGN, "-algo", wl["algo"], "-pairs", path, "-match", str(w["match"]), "-mismatch", str(w["mismatch"]),
+                   "-open", str(w["gap_open"]), "-extend", str(w.get("gap_extend", -1)), "-threads", str(threads), "-noheader"]
             p = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, check=True)
             usec = float(p.stderr.decode().split("ALIGN_USEC")[1].split()[0])
         finally:
             os.unlink(path)
         return cells / (usec * 1e-6) / 1e9, "reference", usec * 1e-6
+    algo = {"LNW": ol.LNW, "ANW": ol.ANW, "LSW": ol.LSW, "BSW": ol.BSW}[wl["algo"]]
     t0 = time.perf_counter()
-    ol.align_batch(ol.params(ol.LSW, **WEIGHTS), blob, pairs[:n_sample], strings=False, threads=threads)
+    ol.align_batch(ol.params(algo, **w), blob, pairs[:n_sample], strings=wl["strings"], threads=threads, bandmem=(wl["algo"] == "BSW"))
     dt = time.perf_counter() - t0
     return cells / dt / 1e9, "port", dt
 
 
-def cpu_sample_size(n_pairs, cores, seconds=12.0):
-    per_core = 0.045e9                       # reference LSW ~0.05 GCUPS / core (BASELINE.md §2)
-    return int(max(2000, min(n_pairs, per_core * cores * seconds / (R_LEN * Q_LEN))))
+def cpu_sample_size(wl, n_pairs, cores, seconds=12.0):
+    cells_per_pair = wl["R"] * wl["Q"] if wl["algo"] != "BSW" else wl["Q"] * (2 * wl["weights"]["band"] + 1)
+    return int(max(min(n_pairs, 2 * cores), min(n_pairs, wl["cpu_per_core"] * cores * seconds / cells_per_pair)))
 
 
 def main():
@@ -150,35 +192,40 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dpx", choices=["dpx", "reference"])
-    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json config number (SURVEY.md §8d)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--score-only", action="store_true", help="omit end coordinates (no position tracking)")
+    ap.add_argument("--score-only", action="store_true", help="config 2: omit end coordinates; configs 3/4: no traceback / strings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "dpx":
         args.warmup = 3
+    wl = dict(WORKLOADS[args.config])
+    n_pairs = args.pairs or wl["pairs"]
+    want_strings = wl["strings"] and not args.score_only
+    if args.config != 2 and args.steps > 10 and args.impl == "dpx":
+        args.steps = 10                                       # traceback configs: ~10-60 ms per step plus the strings download in e2e
 
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     n_gpus = max(args.gpus, world)
     cores = os.cpu_count() or 1
-    from dpx_gpu_genomics_project_b200 import synth
 
-    config = {"workload": f"LinearSmithWaterman batch: {args.pairs} pairs x ({R_LEN}x{Q_LEN}) bp per GPU, score"
-                          + ("" if args.score_only else " + end coords") + ", match 3 / mismatch -1 / gap -2",
-              "pairs_per_gpu": args.pairs, "R": R_LEN, "Q": Q_LEN, "sharding": f"independent pairs x{n_gpus} (no collective)",
-              "l2": "256 MiB memset between timed steps", "seed": "0x5EED0002 + rank"}
+    ends = "" if (args.config == 2 and args.score_only) else (" + end coords" if args.config == 2 else "")
+    config = {"workload": wl["title"].format(pairs=n_pairs, ends=ends) + ("" if want_strings or not wl["strings"] else " [score only]"),
+              "baseline_config": args.config, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
+              "sharding": f"independent pairs x{n_gpus} (no collective)", "l2": "256 MiB memset between timed steps",
+              "seed": f"{wl['seed']:#x} + rank"}
 
     # ---------------------------------------------------------------------------------------------------
     if args.impl == "reference":
         if rank != 0:
             return
-        blob, pairs = synth.uniform_blob_pairs(min(args.pairs, 400_000), R_LEN, Q_LEN, 0x5EED0002)
-        n_s = cpu_sample_size(len(pairs), cores, seconds=8.0)
+        n_s = cpu_sample_size(wl, n_pairs, cores, seconds=8.0)
+        blob, pairs = make_inputs(wl, n_s, wl["seed"])
         vals, secs = [], []
-        for _ in range(max(1, min(args.warmup, 1))):
-            run_cpu_reference(blob, pairs, max(2000, n_s // 8), cores)
+        run_cpu_reference(wl, blob, pairs, max(2, n_s // 8), cores)       # warm-up
         kind = "reference"
         for _ in range(max(1, args.steps if args.steps <= 5 else 3)):
-            v, kind, dt = run_cpu_reference(blob, pairs, n_s, cores)
+            v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, cores)
             vals.append(v); secs.append(dt)
         v = float(np.mean(vals))
         print(json.dumps({
@@ -203,10 +250,14 @@ def main():
         import torch.distributed as dist
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
 
-    blob, pairs = synth.uniform_blob_pairs(args.pairs, R_LEN, Q_LEN, 0x5EED0002 + rank)
-    cells = float(args.pairs) * R_LEN * Q_LEN
-    flags = api.OUT_SCORE | (0 if args.score_only else api.OUT_END_COORDS)
-    params = api.make_params(api.LSW, flags=flags, **WEIGHTS)
+    blob, pairs = make_inputs(wl, n_pairs, wl["seed"] + rank)
+    cells = total_cells(wl, pairs)
+    algo = {"LNW": api.LNW, "ANW": api.ANW, "LSW": api.LSW, "BSW": api.BSW}[wl["algo"]]
+    if args.config == 2:
+        flags = api.OUT_SCORE | (0 if args.score_only else api.OUT_END_COORDS)
+    else:
+        flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if want_strings else 0)
+    params = api.make_params(algo, flags=flags, **wl["weights"])
 
     eng = api.Engine(local)
     stream = torch.cuda.Stream()                         # a real (non-default) stream shared by torch events and the library
@@ -242,30 +293,50 @@ def main():
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     ms_total = float(sum(ms_steps))
     batch.sync()
-    kernel_ms = float(batch.stats()["fill_ms"])          # library's own event pair around the last fill kernel
+    st_last = batch.stats()
+    fill_ms = float(st_last["fill_ms"])                  # library's own event pairs around the fill kernel(s) of the last step
+    bt_ms = float(st_last["backtrack_ms"])
+    tb_bytes = float(st_last["traceback_bytes"])
 
     # result check of the timed configuration on a sample (outside the timed region)
-    res = batch.fetch()
+    import oracle_lib as ol
+    n_chk = 2000 if args.config == 2 else (64 if args.config == 3 else 8)
+    res = batch.fetch() if not want_strings else None
+    oalgo = {"LNW": ol.LNW, "ANW": ol.ANW, "LSW": ol.LSW, "BSW": ol.BSW}[wl["algo"]]
 
     # ---- e2e: one-call ABI, pinned host buffers, H2D + D2H inside ------------------------------------------
-    e2e_steps = max(2, min(5, args.steps))
-    pin_blob = torch.from_numpy(blob).pin_memory()
-    pin_pairs = torch.from_numpy(pairs.view(np.int32)).pin_memory()
+    e2e_steps = max(2, min(5 if args.config == 2 else 3, args.steps))
+    pin_blob = torch.from_numpy(np.ascontiguousarray(blob)).pin_memory()
+    pin_pairs = torch.from_numpy(np.ascontiguousarray(pairs).view(np.int32)).pin_memory()
     nb, npairs_bytes = pin_blob.numel(), pin_pairs.numel() * 4
     blob_p = pin_blob.numpy()
     pairs_p = pin_pairs.numpy().view(api.PAIR_DTYPE)
-    out_scores = torch.empty(args.pairs, dtype=torch.int32).pin_memory()
-    out_rc = torch.empty((args.pairs, 2), dtype=torch.int32).pin_memory()
+    out_scores = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
+    out_rc = torch.empty((n_pairs, 2), dtype=torch.int32).pin_memory()
     import ctypes as C
     L = eng.L
+    str_bytes = int(3 * (pairs["referenceSize"].astype(np.int64) + pairs["querySize"] + 1).sum()) if want_strings else 0
+    e2e_first_strings = []
 
-    def e2e_once():
-        st = L.dpx_align_batch(eng.ctx, C.byref(params), blob_p.ctypes.data, nb, pairs_p.ctypes.data, args.pairs,
-                               out_scores.numpy().ctypes.data, out_rc.numpy().ctypes.data, None, None)
+    def e2e_once(keep=False):
+        sb, so = C.c_void_p(), C.c_void_p()
+        st = L.dpx_align_batch(eng.ctx, C.byref(params), blob_p.ctypes.data, nb, pairs_p.ctypes.data, n_pairs,
+                               out_scores.numpy().ctypes.data, out_rc.numpy().ctypes.data,
+                               C.byref(sb) if want_strings else None, C.byref(so) if want_strings else None)
         if st != 0:
             raise RuntimeError(f"dpx_align_batch failed: {st} {L.dpx_last_error(eng.ctx)}")
+        if want_strings:
+            if keep:
+                last = int(np.frombuffer(C.string_at(so.value + (3 * n_pairs - 1) * 8, 8), dtype=np.uint64)[0])
+                e2e_first_strings.append(last + len(C.string_at(sb.value + last)) + 1)      # size of the compacted blob
+                offs = np.frombuffer(C.string_at(so, 3 * n_chk * 8), dtype=np.uint64)
+                for i in range(n_chk):
+                    e2e_first_strings.append(tuple(C.string_at(sb.value + int(offs[3 * i + k])) for k in range(3)))
+            L.dpx_free(sb); L.dpx_free(so)
 
-    e2e_once()
+    e2e_once(keep=True)
+    if want_strings:
+        str_bytes = e2e_first_strings.pop(0)              # what actually crosses PCIe: the compacted strings
     # context for the e2e number: what a bare pinned H2D copy of the same input bytes costs on this box
     dev_blob = torch.empty(nb, dtype=torch.uint8, device="cuda")
     c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -281,13 +352,14 @@ def main():
         e2e_once()
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    assert (out_scores.numpy() == res.scores).all(), "e2e and staged paths disagree"
+    if res is not None:
+        assert (out_scores.numpy() == res.scores).all(), "e2e and staged paths disagree"
 
     # ---- reduce over ranks -------------------------------------------------------------------------------
     if dist is not None:
-        t = torch.tensor([ms_total, e2e_s, kernel_ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_total, e2e_s, fill_ms, bt_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, kernel_ms = float(t[0]), float(t[1]), float(t[2])
+        ms_total, e2e_s, fill_ms, bt_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
     ms_per_step = ms_total / args.steps
     value = cells * world / (ms_per_step * 1e-3) / 1e9
     e2e_value = cells * world / e2e_s / 1e9
@@ -298,46 +370,61 @@ def main():
         return
 
     # ---- parity spot check against the oracle (outside every timed region) --------------------------------
-    import oracle_lib as ol
-    n_chk = 2000
-    s_ref, e_ref, _ = ol.align_batch(ol.params(ol.LSW, **WEIGHTS), blob, pairs[:n_chk], strings=False, threads=min(cores, 16))
-    parity_ok = bool((res.scores[:n_chk] == s_ref).all() and (args.score_only or (res.end_row_col[:n_chk] == e_ref).all()))
+    s_ref, e_ref, t_ref = ol.align_batch(ol.params(oalgo, **wl["weights"]), blob, pairs[:n_chk], strings=want_strings, threads=min(cores, 16))
+    parity_ok = bool((out_scores.numpy()[:n_chk] == s_ref).all())
+    if wl["algo"] in ("LSW", "BSW") and not (args.config == 2 and args.score_only):
+        parity_ok = parity_ok and bool((out_rc.numpy()[:n_chk] == e_ref).all())
+    if want_strings:
+        parity_ok = parity_ok and e2e_first_strings == t_ref
 
     # ---- roofline ---------------------------------------------------------------------------------------
     clocks = sampler.result()
     peaks, peaks_src = measured_peaks()
     f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-    alu_pc, issue_pc = sass_counts(track=not args.score_only)
+    sass_key = wl["sass"].format(track=not args.score_only)
+    if args.config != 2 and not want_strings:
+        sass_key = sass_key.replace("traceback=True", "traceback=False")
+    alu_pc, issue_pc = sass_counts(sass_key)
     sms = torch.cuda.get_device_properties(local).multi_processor_count
-    kernel_gcups = cells / (ms_per_step * 1e-3) / 1e9         # per GPU, the step is one launch of the fill kernel
-    roofline = {"bound": "dpx_issue", "achieved": kernel_gcups, "unit": "GCUPS", "kernel": "sr_lsw_kernel<G=8,K=19>",
-                "traffic": None}
+    kern_ms = fill_ms if fill_ms > 0 else ms_per_step          # the dominant kernel = the fill kernel(s) of one step
+    cells_rank = cells
+    kernel_gcups = cells_rank / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "dpx_issue", "achieved": kernel_gcups, "unit": "GCUPS", "kernel": wl["kernel"].split(" (+")[0], "traffic": None,
+                "kernel_ms": kern_ms}
     if alu_pc:
-        cells_clk_sm = min(64.0 / alu_pc, 128.0 / issue_pc)
+        slot_eff = (2 * wl["weights"]["band"] + 1) / 160.0 if args.config == 4 else 1.0   # band 64: 129 diagonals on 5 slots x 32 lanes
+        cells_clk_sm = min(64.0 / alu_pc, 128.0 / issue_pc) * slot_eff
         peak = cells_clk_sm * sms * f_mhz * 1e6 / 1e9
         roofline.update({"peak": peak, "frac": kernel_gcups / peak,
                          "model": {"alu_pipe_lanes_per_clk_per_sm": 64, "issue_lanes_per_clk_per_sm": 128,
-                                   "alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc,
-                                   "sms": sms, "sm_mhz": f_mhz, "source": "profiles/sass_counts.json + profiles/r01_dpx_microbench*.json"}})
-    # HBM view of the same launch: algorithmic bytes = 2-bit bases + the index entry + 12 B of results per pair
-    algo_bytes = args.pairs * ((R_LEN + Q_LEN) * 0.25 + 16 + 8 + 12)
-    hbm_ach = algo_bytes / (ms_per_step * 1e-3) / 1e9
+                                   "alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "slot_efficiency": slot_eff,
+                                   "sms": sms, "sm_mhz": f_mhz, "sass_key": sass_key,
+                                   "source": "profiles/sass_counts.json + profiles/r01_dpx_microbench*.json"}})
+    if args.config == 2:
+        # HBM view: algorithmic bytes = 2-bit bases + the index entry + 12 B of results per pair
+        algo_bytes = n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 16 + 8 + 12)
+    else:
+        # HBM view: the packed traceback stream (0.5 B/cell Gotoh, 0.25 B/cell linear / banded) written once by the fill kernel
+        algo_bytes = cells_rank * wl["tb_bytes_per_cell"] if want_strings else n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 28)
+    hbm_ach = algo_bytes / (kern_ms * 1e-3) / 1e9
     roofline["hbm"] = {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                       "peak_source": f"MEASURED_PEAKS.json ({peaks_src})", "algorithmic_bytes_per_launch": algo_bytes}
+                       "peak_source": f"MEASURED_PEAKS.json ({peaks_src})", "algorithmic_bytes_per_launch": algo_bytes,
+                       "slab_bytes_written": tb_bytes if want_strings else None}
 
+    d2h = n_pairs * 12 + str_bytes + (3 * 8 * n_pairs if want_strings else 0)
     out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "int16x2", "data": "synthetic", "config": config, "clocks": clocks,
+           "dtype": wl["dtype"], "data": "synthetic", "config": config, "clocks": clocks,
            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(nb + npairs_bytes),
-                   "d2h_bytes_per_step": int(args.pairs * 12), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                   "api": "dpx_align_batch (C ABI), pinned host buffers",
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "api": "dpx_align_batch (C ABI), pinned host input buffers" + (", library-allocated string blob" if want_strings else ""),
                    "bare_h2d_copy_ms": h2d_ms, "bare_h2d_gbs": nb / (h2d_ms * 1e-3) / 1e9},
            "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-           "kernel_ms_last_step": kernel_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}
+           "fill_ms_last_step": fill_ms, "backtrack_ms_last_step": bt_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}
 
     if not args.no_cpu_baseline and world == 1:
-        n_s = cpu_sample_size(args.pairs, cores)
-        v, kind, dt = run_cpu_reference(blob, pairs, n_s, cores)
+        n_s = cpu_sample_size(wl, n_pairs, cores)
+        v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, cores)
         out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind, "seconds": dt,
                                "sample": f"first {n_s} pairs of the same workload, {cores} host threads, align loop only"}
     print(json.dumps(out))

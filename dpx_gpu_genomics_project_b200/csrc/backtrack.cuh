@@ -125,6 +125,33 @@ __global__ void __launch_bounds__(256) str_offsets_kernel(const dpx_seq_pair* __
     out[3 * i] = b; out[3 * i + 1] = b + F; out[3 * i + 2] = b + 2 * F;
 }
 
+// Compacted string output: pair i owns 3 * (len_i + 1) bytes (REF, REL, QRY, each NUL-terminated), pairs in index order.
+__global__ void __launch_bounds__(256) str_len_kernel(const dpx_seq_pair* __restrict__ pairs, int n, const int32_t* __restrict__ str_start,
+                                                      unsigned long long* __restrict__ len3) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { len3[i] = 0; return; }
+    const unsigned long long F = (unsigned long long)pairs[i].querySize + (unsigned long long)pairs[i].referenceSize + 1ull;
+    len3[i] = 3ull * (F - (unsigned long long)str_start[i]);          // F - start = alignment length + NUL
+}
+
+__global__ void __launch_bounds__(256) str_compact_kernel(const dpx_seq_pair* __restrict__ pairs, int n, const char* __restrict__ slab,
+                                                          const unsigned long long* __restrict__ str_off, const int32_t* __restrict__ str_start,
+                                                          const unsigned long long* __restrict__ coff, char* __restrict__ out,
+                                                          unsigned long long* __restrict__ offs) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        const unsigned long long F = (unsigned long long)pairs[i].querySize + (unsigned long long)pairs[i].referenceSize + 1ull;
+        const unsigned long long L = F - (unsigned long long)str_start[i];
+        const char* __restrict__ src = slab + str_off[i] + (unsigned long long)str_start[i];
+        char* __restrict__ dst = out + coff[i];
+        for (int k = 0; k < 3; ++k)
+            for (unsigned long long x = lane; x < L; x += 32) dst[k * L + x] = src[k * F + x];
+        if (lane < 3) offs[3 * i + lane] = coff[i] + lane * L;
+    }
+}
+
 // sort key of the schedule: longer queries first, then longer references (descending via bitwise not)
 __global__ void __launch_bounds__(256) sched_keys_kernel(const dpx_seq_pair* __restrict__ pairs, int n, unsigned long long* __restrict__ keys, int32_t* __restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -50,6 +50,46 @@ struct DevPool {
     void clear_all() { for (auto& kv : size_) cudaFree(kv.first); size_.clear(); free_.clear(); }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Host blobs the library hands out (strings_blob / string_offsets) are page-locked, so their D2H copy runs at PCIe
+// speed instead of through the driver's pageable staging; dpx_free returns them to this process-wide cache (bounded),
+// so a driver that aligns batch after batch does not pay cudaHostAlloc each time.  Anything not allocated here (the
+// parser's malloc'ed arrays) still goes to free().
+#include <mutex>
+struct HostCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_;
+    std::unordered_map<void*, size_t> live_;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = (size_t)6 << 30;
+    void* take(size_t bytes) {
+        bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto it = free_.lower_bound(bytes);
+            if (it != free_.end() && it->first <= 2 * bytes + (1u << 20)) {
+                void* p = it->second; const size_t sz = it->first; free_.erase(it); cached_bytes -= sz; live_[p] = sz; return p;
+            }
+        }
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        std::lock_guard<std::mutex> g(mu);
+        live_[p] = bytes;
+        return p;
+    }
+    bool give_back(void* p) {
+        std::unique_lock<std::mutex> g(mu);
+        auto it = live_.find(p);
+        if (it == live_.end()) return false;
+        const size_t sz = it->second; live_.erase(it);
+        if (cached_bytes + sz <= kMaxCached) { free_.emplace(sz, p); cached_bytes += sz; return true; }
+        g.unlock();
+        cudaFreeHost(p);
+        return true;
+    }
+};
+static HostCache g_host;
+
 struct dpx_ctx {
     int device = 0;
     int sm_count = 0;
@@ -187,7 +227,7 @@ int dpx_set_stream(dpx_ctx* ctx, void* s) {
     return DPX_OK;
 }
 
-void dpx_free(void* p) { free(p); }
+void dpx_free(void* p) { if (p && !g_host.give_back(p)) free(p); }
 
 // ---- parser (replaces c++/parseInput.cpp:9-119) -------------------------------------------------
 int dpx_parse_input(const char* path, dpx_seq_pair** pairs_out, char** seq_out, dpx_input_info* info) {
@@ -1163,27 +1203,45 @@ int dpx_batch_fetch(dpx_batch* b, int32_t* scores, int32_t* end_rc, char** strin
     { int s = batch_fetch_async(b, scores, end_rc); if (s) return s; }
     const bool want_strings = (b->params.flags & DPX_OUT_STRINGS) && strings_blob && string_offsets;
     char* blob = nullptr; size_t* offs = nullptr;
+    auto drop = [&]() { if (blob) dpx_free(blob); if (offs) dpx_free(offs); blob = nullptr; offs = nullptr; };
     if (want_strings) {
-        const size_t bytes = n ? (size_t)b->info.str_bytes : 0;
-        blob = (char*)malloc(std::max<size_t>(bytes, 1));
-        offs = (size_t*)malloc(std::max<size_t>(3 * n, 1) * sizeof(size_t));
-        if (!blob || !offs) { free(blob); free(offs); return DPX_ERR_NOMEM; }
+        // The slab keeps 3 fields of Q+R+1 bytes per pair; what goes back to the host is the compacted form (3 NUL-terminated
+        // strings of the alignment's own length per pair, in pair order) plus its offset table: a scan of the lengths, one copy
+        // kernel, and two D2H copies into page-locked host memory.
+        unsigned long long total = 0;
+        unsigned long long *d_len = nullptr, *d_coff = nullptr, *d_offs = nullptr; char* d_compact = nullptr; void* tmp = nullptr;
+        auto release = [&]() { ctx->pool.release(d_len); ctx->pool.release(d_coff); ctx->pool.release(d_offs); ctx->pool.release(d_compact); ctx->pool.release(tmp); };
         if (n) {
-            unsigned long long* d_offs = nullptr;
-            if (!pool_alloc(ctx, &d_offs, 3 * n)) { free(blob); free(offs); return DPX_ERR_NOMEM; }
-            str_offsets_kernel<<<(int)((n + 255) / 256), 256, 0, b->stream>>>(b->d_pairs, (int)n, b->d_str_off, b->d_str_start, d_offs);
-            static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+            if (!pool_alloc(ctx, &d_len, n + 1) || !pool_alloc(ctx, &d_coff, n + 1) || !pool_alloc(ctx, &d_offs, 3 * n)) { release(); return DPX_ERR_NOMEM; }
+            str_len_kernel<<<(int)((n + 1 + 255) / 256), 256, 0, b->stream>>>(b->d_pairs, (int)n, b->d_str_start, d_len);
+            size_t tmp_bytes = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_coff, (int)n + 1, b->stream);
+            tmp = ctx->pool.alloc(tmp_bytes);
+            if (!tmp) { release(); return DPX_ERR_NOMEM; }
+            cudaError_t e0 = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_coff, (int)n + 1, b->stream);
+            cudaError_t e1 = cudaMemcpyAsync(&total, d_coff + n, sizeof(total), cudaMemcpyDeviceToHost, b->stream);
+            cudaError_t e2 = cudaStreamSynchronize(b->stream);
+            if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) { release(); ctx->err = "string compaction failed"; return DPX_ERR_CUDA; }
+        }
+        static_assert(sizeof(size_t) == sizeof(unsigned long long), "size_t must be 64-bit");
+        blob = (char*)g_host.take(std::max<size_t>((size_t)total, 1));
+        offs = (size_t*)g_host.take(std::max<size_t>(3 * n, 1) * sizeof(size_t));
+        if (!blob) blob = (char*)malloc(std::max<size_t>((size_t)total, 1));
+        if (!offs) offs = (size_t*)malloc(std::max<size_t>(3 * n, 1) * sizeof(size_t));
+        if (!blob || !offs) { release(); drop(); return DPX_ERR_NOMEM; }
+        if (n) {
+            if (!pool_alloc(ctx, &d_compact, (size_t)total + 16)) { release(); drop(); return DPX_ERR_NOMEM; }
+            str_compact_kernel<<<(int)std::min<size_t>((n + 7) / 8, (size_t)ctx->sm_count * 16), 256, 0, b->stream>>>(
+                b->d_pairs, (int)n, b->d_strings, b->d_str_off, b->d_str_start, d_coff, d_compact, d_offs);
             cudaError_t e1 = cudaMemcpyAsync(offs, d_offs, 3 * n * sizeof(size_t), cudaMemcpyDeviceToHost, b->stream);
-            cudaError_t e2 = cudaMemcpyAsync(blob, b->d_strings, bytes, cudaMemcpyDeviceToHost, b->stream);
+            cudaError_t e2 = cudaMemcpyAsync(blob, d_compact, (size_t)total, cudaMemcpyDeviceToHost, b->stream);
             cudaError_t e3 = cudaStreamSynchronize(b->stream);
-            ctx->pool.release(d_offs);
-            if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) {
-                free(blob); free(offs); ctx->err = "string download failed"; return DPX_ERR_CUDA;
-            }
+            release();
+            if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { drop(); ctx->err = "string download failed"; return DPX_ERR_CUDA; }
         }
     }
     int st = dpx_batch_sync(b);
-    if (st) { free(blob); free(offs); return st; }
+    if (st) { drop(); return st; }
     if (want_strings) { *strings_blob = blob; *string_offsets = offs; }
     return DPX_OK;
 }

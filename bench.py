@@ -134,10 +134,8 @@ def make_inputs(wl, n_pairs, seed):
     from dpx_gpu_genomics_project_b200 import synth
     if wl["gen"] == "uniform":
         return synth.uniform_blob_pairs(n_pairs, wl["R"], wl["Q"], seed)
-    import oracle_lib as ol
     sub, ins, dele = wl["gen"]
-    img = synth.mutated_fixed_file_bytes(n_pairs, wl["R"], wl["Q"], seed, sub, ins, dele)
-    return ol.parse_image(img)
+    return synth.mutated_blob_pairs(n_pairs, wl["R"], wl["Q"], seed, sub, ins, dele)
 
 
 def total_cells(wl, pairs):

@@ -155,6 +155,21 @@ def uniform_blob_pairs(n_pairs: int, R: int, Q: int, seed: int, alphabet: bytes 
     return img, pairs
 
 
+def mutated_blob_pairs(n_pairs: int, R: int, Q: int, seed: int, sub: float, ins: float, dele: float, alphabet: bytes = b"0123"):
+    """mutated_fixed_file_bytes in parseInput's output form: (blob with '\\n' -> 0, seqPair index)."""
+    img = mutated_fixed_file_bytes(n_pairs, R, Q, seed, sub, ins, dele, alphabet)
+    rec = 2 + R + 1 + Q + 1
+    m = img.reshape(n_pairs, rec)
+    m[:, 1] = 0; m[:, 2 + R] = 0; m[:, rec - 1] = 0
+    pairs = np.zeros(n_pairs, dtype=[("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
+    base = np.arange(n_pairs, dtype=np.int64) * rec
+    pairs["referenceIdx"] = base + 2
+    pairs["referenceSize"] = R
+    pairs["queryIdx"] = base + 3 + R
+    pairs["querySize"] = Q
+    return img, pairs
+
+
 def blob_to_file_bytes(blob: np.ndarray) -> np.ndarray:
     """Inverse of the parser's newline->NUL rewrite for generator-made blobs (no NUL inside sequences)."""
     out = blob.copy()

@@ -1018,14 +1018,18 @@ static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
 
 static long long pow2_at_least(long long v) { long long p = 64; while (p < v) p <<= 1; return p; }
 
-// K: columns per lane.  Fewer columns per lane = more warps = more of the GPU busy, but more shuffles per cell; take the
-// largest K in {16,8,4,2} that still gives at least ~8 warps per SM, never more warps than can be co-resident per pass.
+// K: columns per lane.  A warp's row step costs about 43 + 14 K cycles whether it is measured as latency (one warp per SM
+// sub-partition) or as issue slots (several), so a chain of nw = R / 32K warps advances one row every
+// (43 + 14 K) * max(1, nw / (4 * SMs)) cycles (fit of tools/long_sweep.py on B200).  Take the K that minimises it; ties go to the
+// wider lane (fewer shuffles per cell).
 static int long_pick_k(dpx_ctx* ctx, long long R_local) {
+    int best_k = 16; double best = 1e300;
     for (int K : {16, 8, 4, 2}) {
-        const long long nw = (R_local + 32LL * K - 1) / (32LL * K);
-        if (nw >= 8LL * ctx->sm_count || K == 2) return K;
+        const double nw = (double)((R_local + 32LL * K - 1) / (32LL * K));
+        const double cost = (43.0 + 14.0 * K) * std::max(1.0, nw / (4.0 * ctx->sm_count));
+        if (cost < best * 0.999) { best = cost; best_k = K; }
     }
-    return 2;
+    return best_k;
 }
 
 static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,

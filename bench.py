@@ -409,6 +409,15 @@ def main():
                        "peak_source": f"MEASURED_PEAKS.json ({peaks_src})", "algorithmic_bytes_per_launch": algo_bytes,
                        "slab_bytes_written": tb_bytes if want_strings else None}
 
+    try:                                                      # DRAM traffic of the dominant kernel, from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[str(args.config)]
+        if want_strings or args.config == 2:
+            per_launch = tr["dram_bytes_per_pair"] * n_pairs if "dram_bytes_per_pair" in tr else tr["dram_bytes_per_cell"] * cells_rank
+            roofline["traffic"] = per_launch
+            roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, scaled from the capture's size)"
+            roofline["traffic_source"] = tr["source"]
+    except Exception:
+        pass
     d2h = n_pairs * 12 + str_bytes + (3 * 8 * n_pairs if want_strings else 0)
     out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -730,6 +730,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             tab[xormode ? 0 : 3] = (uint8_t)(int8_t)ms;
             sa.lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
             sa.lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
+            sa.ms_byte = (uint32_t)(ms & 0xff); sa.xs_byte = (uint32_t)(xs & 0xff);
             auto pk = [](int v) { return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16); };
             sa.one = 1u; sa.kbits = kbits; sa.kmul = 1u << kbits; sa.B = B; sa.B2 = pk(B); sa.Bg2 = pk(B + g);
             sa.G2 = (uint32_t)(g & 0xffff) | ((uint32_t)((g - 1) & 0xffff) << 16);

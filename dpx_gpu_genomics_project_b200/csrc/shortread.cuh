@@ -42,7 +42,8 @@ struct SrArgs {
     const dpx_seq_pair* pairs;
     const int32_t* order;                // schedule (nullable = identity); slot s = schedule positions 2s, 2s+1
     int n_pairs, n_slots;
-    uint32_t lut_lo, lut_hi;             // prmt table: byte 3 (XORMODE: byte 0) = match - gap, others = mismatch - gap
+    uint32_t lut_lo, lut_hi;             // (unused by the per-row tables; kept for the ABI of the launcher)
+    uint32_t ms_byte, xs_byte;           // (match - gap) & 0xff, (mismatch - gap) & 0xff
     uint32_t B2, Bg2, G2;                // packed bias, bias + gap, and the add constant ((gap-1)<<16 | gap&0xffff)
     int B;
     uint32_t one;                        // 1 (run-time constant for the FMA-pipe adds)
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
     const int gib = threadIdx.x / G;
     uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride;
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(sr_smem + (size_t)GPB * a.bnd_stride) + (size_t)gib * a.rsel_stride;
-    const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, lut_lo = a.lut_lo, lut_hi = a.lut_hi, one = a.one;
+    const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, one = a.one;
+    const uint32_t ms1 = a.ms_byte, xs4 = a.xs_byte * 0x01010101u;
     const int kmask = (1 << a.kbits) - 1;             // all position bits of an int16 key
     const int smask = (1 << (a.kbits - 1)) - 1;       // step-code bits (the bit above them marks the upper row of a pair)
     const uint32_t kmul = a.kmul;
@@ -119,16 +121,12 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
             //   only where row AND column are pads); every table byte is >= 0 so the high byte is the constant
             //   selector 8 (sign of byte 0) and no nibble can carry into the other pair's half.
             // XOR mode: r (pad 5) with the sign-replicating copy r|8 in the odd nibbles; q ^ r == 0 iff match.
-            uint32_t cA, cB;
-            if (XORMODE) {
-                cA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 5u;
-                cB = (j >= 1 && j <= RB) ? get2(refB, j - 1) : 5u;
-                rsel[e] = (uint16_t)(cA | ((cA | 8u) << 4) | (cB << 8) | ((cB | 8u) << 12));
-            } else {
-                cA = (j >= 1 && j <= RA) ? 3u - get2(refA, j - 1) : 4u;
-                cB = (j >= 1 && j <= RB) ? 3u - get2(refB, j - 1) : 4u;
-                rsel[e] = (uint16_t)(cA | 0x80u | (cB << 8) | 0x8000u);
-            }
+            // selector of the per-row score tables (below): nibble 0 = reference base of pair A (bytes 0..3 of the row's table
+            // pair), nibble 2 = 4 + base of pair B (bytes 4..7); nibbles 1 / 3 = the same index | 8 = "replicate that byte's
+            // sign", i.e. the int16 sign extension.  Pad columns select the sign of byte 0 / 4: 0 or -1, below any real score.
+            const uint32_t nA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 8u;
+            const uint32_t nB = (j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
+            rsel[e] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
         }
         if (passes > 1)
             for (int e = gl; e < Rw + G + 2; e += G) bnd[e] = Bg2;
@@ -138,14 +136,15 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
 
         for (int p = 0; p < passes; ++p) {
             const int i0 = p * G * K + gl * K;                  // matrix row of register row r is i0 + r + 1
-            uint32_t qsel[K], hgA[K], hgB[K], best[(K + 1) / 2];
+            uint32_t ta[K], tb[K], hgA[K], hgB[K], best[(K + 1) / 2];   // ta / tb: (score - gap) of this row's base against bases 0..3
             uint32_t laneKeyA = 0, laneKeyB = 0;                 // score<<(k+12) | (31-row)<<(k+7) | (255-blk)<<(k-1) | code
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
                 const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
                 const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
-                qsel[r] = XORMODE ? (qa * 0x11u + qb * 0x1100u) : (qa | (qb << 8));
+                ta[r] = (qa < 4u) ? ((xs4 & ~(0xffu << (8 * qa))) | (ms1 << (8 * qa))) : xs4;
+                tb[r] = (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
                 hgA[r] = Bg2; hgB[r] = Bg2;
             }
             #pragma unroll
@@ -167,8 +166,7 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                 topprev = top;                                                                           \
                 _Pragma("unroll")                                                                        \
                 for (int r = 0; r < K; ++r) {                                                            \
-                    const uint32_t x = XORMODE ? (qsel[r] ^ rs) : fma_add(qsel[r], one, rs);             \
-                    const uint32_t sc = prmt_b32(lut_lo, lut_hi, x);                                     \
+                    const uint32_t sc = prmt_b32(ta[r], tb[r], rs);          /* both pairs' scores, sign-extended */ \
                     const uint32_t e = __viaddmax_s16x2(diag, sc, OLD[r]);   /* off the row chain */     \
                     const uint32_t h = __vimax3_s16x2(e, upg, B2);           /* chain: h -> hg -> h */   \
                     diag = OLD[r];                                                                       \

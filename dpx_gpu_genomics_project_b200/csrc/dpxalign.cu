@@ -580,7 +580,7 @@ static int ensure_str_off(dpx_batch* b) {
 
 
 // ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
-struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc; int b0, b1, bstep, dec_sub, dec_add; };
+struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc, addc3; int b0, b1, bstep, dec_sub, dec_add; };
 
 static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
     if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW) || !b->packed2 || getenv("DPX_NO_PAIRWF")) return false;
@@ -590,7 +590,7 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     if (open >= 0 || ge > 0 || go > 0) return false;             // the add constant must be negative (always-carry rule)
     const long long code = aff ? 3 : 1;
     const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
-    if (tm < 0 || tm > 255 || tx < 0 || tx > 255) return false;
+    if (tm < 0 || tm > 127 || tx < 0 || tx > 127) return false;     // table bytes are sign-extended by the selector
     const int K = 8;
     const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
     // lowest value any stored quantity can take (gaps-only path bounds H from below) and the highest score
@@ -600,16 +600,13 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
     const long long B = -4 * lo + margin;
     if (4 * hi + B + 16 > 32767) return false;
-    uint8_t tab[8];
-    for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)tx;
-    tab[3] = (uint8_t)tm;
     pl->K = K;
-    pl->lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
-    pl->lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
+    pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
     auto pk = [](long long v) { return (uint32_t)(v & 0xffff) * 0x00010001u; };
     pl->ext2 = aff ? pk(4 * ge) : pk(1);
     const long long c = aff ? 4 * open : 4 * open - 2;           // (h' | 3) + c -> code 3 (Gotoh) / code 1 (linear)
     pl->addc = (uint32_t)(c & 0xffff) | ((uint32_t)((c - 1) & 0xffff) << 16);
+    pl->addc3 = (uint32_t)((c + 3) & 0xffff) | ((uint32_t)((c + 2) & 0xffff) << 16);
     pl->b0 = (int)(4 * open + B + code);
     pl->b1 = aff ? (int)(4 * (go + open) + B + code) : pl->b0;
     pl->bstep = (int)(4 * (aff ? ge : go));
@@ -769,7 +766,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             }
             PwArgs a{};
             a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
-            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc;
+            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu;
             a.one = 1u; a.two = 2u; a.four = 4u; a.eight = 8u; a.sixteen = 16u;
             a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
             a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;

@@ -56,9 +56,11 @@ struct PwArgs {
     const dpx_seq_pair* pairs;
     const int32_t* order;                // schedule (nullable = identity)
     int first, count;                    // schedule positions [first, first + count) of this launch; slot s = positions first+2s, first+2s+1
-    uint32_t lut_lo, lut_hi;             // prmt table: byte 3 = match entry, every other byte = mismatch entry
+    uint32_t lut_lo, lut_hi;             // low byte of lut_lo = mismatch entry, low byte of lut_hi = match entry (4*(s - open) - code)
     uint32_t ext2;                       // Gotoh: packed 4*ge; linear: packed 1
-    uint32_t addc;                       // carry-compensated add constant: Gotoh 4*goe, linear 4*g - 2
+    uint32_t addc;                       // carry-compensated add constant: Gotoh 4*goe, linear 4*g - 2   (applied to h' | 3)
+    uint32_t addc3;                      // the same + 3                                                  (applied to h' - code)
+    uint32_t minus1;                     // 0xffffffff: run-time multiplier for FMA-pipe subtractions
     uint32_t one, two, four, eight, sixteen;   // run-time multipliers: keep shifts / adds on the FMA pipe as IMAD
     int b0, b1, bstep;                   // border(idx) = idx == 0 ? b0 : b1 + bstep * idx   (stored form, one half)
     int dec_sub, dec_add;                // score = ((half - dec_sub) >> 2) + dec_add
@@ -90,7 +92,8 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
     uint32_t* __restrict__ bndH = pw_smem + (size_t)wib * a.bnd_stride * (AFF ? 2 : 1);
     uint32_t* __restrict__ bndD = bndH + a.bnd_stride;
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (size_t)4 * a.bnd_stride * (AFF ? 2 : 1)) + (size_t)wib * a.rsel_stride;
-    const uint32_t lut_lo = a.lut_lo, lut_hi = a.lut_hi, one = a.one, ext2 = a.ext2, addc = a.addc;
+    const uint32_t one = a.one, ext2 = a.ext2, addc = a.addc, addc3 = a.addc3, minus1 = a.minus1;
+    const uint32_t ms1 = a.lut_hi & 0xffu, xs4 = (a.lut_lo & 0xffu) * 0x01010101u;     // table entries: match, mismatch
     const uint32_t two = a.two, four = a.four, eight = a.eight, sixteen = a.sixteen;
     const int n_slots = (a.count + 1) >> 1;
     const PwGeom geo = PwGeom::make(K, CB);
@@ -123,9 +126,12 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
         __syncwarp();
         for (int e = lane; e < nsteps2 + 32; e += 32) {
             const int j = e - 31;
-            const uint32_t cA = (j >= 1 && j <= RA) ? 3u - get2(refA, j - 1) : 4u;
-            const uint32_t cB = (j >= 1 && j <= RB) ? 3u - get2(refB, j - 1) : 4u;
-            rsel[e] = (uint16_t)(cA | 0x80u | (cB << 8) | 0x8000u);
+            // selector of the per-row score tables: nibble 0 = reference base of pair A (bytes 0..3 of the row's table pair),
+            // nibble 2 = 4 + base of pair B (bytes 4..7), nibbles 1 / 3 = the same index | 8 (sign extension; entries are >= 0).
+            // Pad columns select the sign of byte 0 / 4 = 0: below any real entry.
+            const uint32_t nA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 8u;
+            const uint32_t nB = (j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
+            rsel[e] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
         }
         __syncwarp();
 
@@ -135,13 +141,14 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
 
         for (int p = 0; p < passes; ++p) {
             const int i0 = p * 32 * K + lane * K;                // rows above this lane's block; its rows are i0+1 .. i0+K
-            uint32_t qsel[K], hA[K], hB[K], Ic[AFF ? K : 1];
+            uint32_t ta[K], tb[K], hA[K], hB[K], Ic[AFF ? K : 1];   // ta / tb: table entry of this row's base against bases 0..3
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
                 const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
                 const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
-                qsel[r] = qa | (qb << 8);
+                ta[r] = (qa < 4u) ? ((xs4 & ~(0xffu << (8 * qa))) | (ms1 << (8 * qa))) : xs4;
+                tb[r] = (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
                 hA[r] = pw_pack(a.b1 + a.bstep * (i + 1));       // column 0 border of matrix row i+1
                 hB[r] = hA[r];
                 if constexpr (AFF) Ic[r] = 0x00020002u;                    // I[i][0] never wins: column 1 always opens (:201-205)
@@ -169,29 +176,33 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                     topprev = topH;                                                                                  \
                     _Pragma("unroll")                                                                                \
                     for (int r = 0; r < K; ++r) {                                                                    \
-                        const uint32_t x = fma_add(qsel[r], one, rs);                                                \
-                        const uint32_t sc = prmt_b32(lut_lo, lut_hi, x);                                             \
+                        const uint32_t sc = prmt_b32(ta[r], tb[r], rs);                                              \
                         uint32_t h;                                                                                  \
-                        if constexpr (AFF) {                                                                             \
+                        if constexpr (AFF) {                                                                         \
                             const uint32_t ds = fma_add(diag, one, sc);                                              \
                             const uint32_t Dn = __viaddmax_s16x2(upD, ext2, up);                                     \
                             const uint32_t In = __viaddmax_s16x2(Ic[r], ext2, OLD[r]);                               \
                             const uint32_t Dc = Dn & 0xFFFDFFFDu, Icn = In & 0xFFFEFFFEu;                            \
                             h = __vimax3_s16x2(ds, Dc, Icn);                                                         \
                             upD = Dc; Ic[r] = Icn;                                                                   \
-                            if (TB) {                                                                                \
-                                const uint32_t x2 = fma_mul(Dn, two), y8 = fma_mul(In, eight);                       \
-                                const uint32_t u = (x2 & 0x00040004u) | (h & ~0x00040004u);                          \
-                                const uint32_t v = (y8 & 0x00080008u) | (u & ~0x00080008u);                          \
-                                acc[r / CPH] = fma_add(acc[r / CPH], sixteen, v & 0x000F000Fu);                       \
+                            if (TB) {   /* nibble = dir + 4 * (D opened) + 8 * (I opened): Dn - Dc = 2 * opened, In - Icn = opened */ \
+                                const uint32_t t = h & 0x00030003u;                                                  \
+                                acc[r / CPH] = fma_add(acc[r / CPH], sixteen, t);                                    \
+                                acc[r / CPH] = fma_add(fma_add(Dc, minus1, Dn), two, acc[r / CPH]);                  \
+                                acc[r / CPH] = fma_add(fma_add(Icn, minus1, In), eight, acc[r / CPH]);               \
+                                NEW[r] = fma_add(h | 0x00030003u, one, addc);                                        \
                             }                                                                                        \
                         } else {                                                                                     \
                             const uint32_t m = __viaddmax_s16x2(diag, sc, up);                                       \
                             h = __viaddmax_s16x2(OLD[r], ext2, m);                                                   \
-                            if (TB) acc[r / CPH] = fma_add(acc[r / CPH], four, h & 0x00030003u);                     \
+                            if (TB) {                                                                                \
+                                const uint32_t t = h & 0x00030003u;                                                  \
+                                acc[r / CPH] = fma_add(acc[r / CPH], four, t);                                       \
+                                NEW[r] = fma_add(fma_add(t, minus1, h), one, addc3);                                 \
+                            }                                                                                        \
                         }                                                                                            \
                         diag = OLD[r];                                                                               \
-                        NEW[r] = fma_add(h | 0x00030003u, one, addc);                                                \
+                        if (!TB) NEW[r] = fma_add(h | 0x00030003u, one, addc);                                       \
                         up = NEW[r];                                                                                 \
                     }                                                                                                \
                     botH = up; botD = upD;                                                                           \

@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
     L.dpx_batch_sync.restype = C.c_int; L.dpx_batch_sync.argtypes = [vp]
     L.dpx_batch_fetch.restype = C.c_int; L.dpx_batch_fetch.argtypes = [vp, vp, vp, C.POINTER(vp), C.POINTER(vp)]
     L.dpx_batch_free.restype = None; L.dpx_batch_free.argtypes = [vp]
+    L.dpx_batch_fetch_text.restype = C.c_int; L.dpx_batch_fetch_text.argtypes = [vp, C.c_longlong, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.dpx_align_batch_text.restype = C.c_int
+    L.dpx_align_batch_text.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_longlong, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.dpx_batch_stats.restype = C.c_int; L.dpx_batch_stats.argtypes = [vp, C.POINTER(RunStats)]
     L.dpx_align_long_pair.restype = C.c_int
     L.dpx_align_long_pair.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,

@@ -118,6 +118,18 @@ class Engine:
                                       C.byref(sb) if want else None, C.byref(so) if want else None), self.ctx)
         return BatchResult(scores, end_rc, self._take_strings(sb, so, n) if want else None)
 
+    def align_batch_text(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray, first_index: int = 0) -> bytes:
+        """The reference's stdout blocks for the batch ("<i> | <score>\\n" + REF/REL/QRY lines), formatted on the GPU."""
+        sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        txt, nb = C.c_void_p(), C.c_size_t()
+        _check(self.L.dpx_align_batch_text(self.ctx, C.byref(params), sequences.ctypes.data, sequences.size, pairs.ctypes.data, len(pairs),
+                                           first_index, None, None, C.byref(txt), C.byref(nb)), self.ctx)
+        try:
+            return C.string_at(txt, nb.value)
+        finally:
+            self.L.dpx_free(txt)
+
     def _take_strings(self, sb, so, n):
         try:
             offs = np.frombuffer(C.string_at(so, 3 * n * C.sizeof(C.c_size_t)), dtype=np.uint64) if n else []

@@ -152,6 +152,65 @@ __global__ void __launch_bounds__(256) str_compact_kernel(const dpx_seq_pair* __
     }
 }
 
+// ---- formatted output: the reference's stdout block of every pair, written on the device --------------------------------
+//   "<index> | <score>\n"  then (with strings)  REF "\n" REL "\n" QRY "\n"     c++/LinearNeedlemanWunsch.cpp:207-213;
+//   a Smith-Waterman score of 0 prints three empty lines (c++/LinearSmithWaterman.cpp:253-257) = three empty strings here.
+__device__ __forceinline__ int dec_digits(long long v) {           // characters of printf("%lld")
+    int n = v < 0 ? 2 : 1;
+    unsigned long long a = v < 0 ? (unsigned long long)(-v) : (unsigned long long)v;
+    while (a >= 10) { a /= 10; ++n; }
+    return n;
+}
+__device__ __forceinline__ char* put_dec(char* p, long long v) {   // writes the digits, returns the end
+    const int n = dec_digits(v);
+    unsigned long long a = v < 0 ? (unsigned long long)(-v) : (unsigned long long)v;
+    for (int k = n - 1; k >= (v < 0 ? 1 : 0); --k) { p[k] = (char)('0' + a % 10); a /= 10; }
+    if (v < 0) p[0] = '-';
+    return p + n;
+}
+
+__global__ void __launch_bounds__(256) text_len_kernel(const dpx_seq_pair* __restrict__ pairs, int n, long long first_index,
+                                                       const int32_t* __restrict__ scores, const int32_t* __restrict__ str_start /* null: no strings */,
+                                                       unsigned long long* __restrict__ len) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    if (i == n) { len[i] = 0; return; }
+    unsigned long long l = (unsigned long long)(dec_digits(first_index + i) + 3 + dec_digits(scores[i]) + 1);
+    if (str_start) {
+        const unsigned long long F = (unsigned long long)pairs[i].querySize + (unsigned long long)pairs[i].referenceSize + 1ull;
+        l += 3ull * (F - (unsigned long long)str_start[i]);           // alignment length + newline, three times
+    }
+    len[i] = l;
+}
+
+__global__ void __launch_bounds__(256) text_write_kernel(const dpx_seq_pair* __restrict__ pairs, int n, long long first_index,
+                                                         const int32_t* __restrict__ scores, const char* __restrict__ slab,
+                                                         const unsigned long long* __restrict__ str_off, const int32_t* __restrict__ str_start,
+                                                         const unsigned long long* __restrict__ toff, char* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < n; i += nwarps) {
+        char* __restrict__ dst = out + toff[i];
+        const int hdr = dec_digits(first_index + i) + 3 + dec_digits(scores[i]) + 1;
+        if (lane == 0) {
+            char* p = put_dec(dst, first_index + i);
+            p[0] = ' '; p[1] = '|'; p[2] = ' ';
+            p = put_dec(p + 3, scores[i]);
+            p[0] = '\n';
+        }
+        if (str_start) {
+            const unsigned long long F = (unsigned long long)pairs[i].querySize + (unsigned long long)pairs[i].referenceSize + 1ull;
+            const unsigned long long L = F - 1ull - (unsigned long long)str_start[i];
+            const char* __restrict__ src = slab + str_off[i] + (unsigned long long)str_start[i];
+            for (int k = 0; k < 3; ++k) {
+                char* __restrict__ d = dst + hdr + k * (L + 1);
+                for (unsigned long long x = lane; x < L; x += 32) d[x] = src[k * F + x];
+                if (lane == 0) d[L] = '\n';
+            }
+        }
+    }
+}
+
 // sort key of the schedule: longer queries first, then longer references (descending via bitwise not)
 __global__ void __launch_bounds__(256) sched_keys_kernel(const dpx_seq_pair* __restrict__ pairs, int n, unsigned long long* __restrict__ keys, int32_t* __restrict__ ids) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -1248,6 +1248,63 @@ int dpx_batch_fetch(dpx_batch* b, int32_t* scores, int32_t* end_rc, char** strin
     return DPX_OK;
 }
 
+// The reference's stdout blocks for the whole batch, formatted on the device: one scan of the block
+// lengths, one write kernel, one D2H copy into a page-locked blob.
+int dpx_batch_fetch_text(dpx_batch* b, long long first_index, char** text, size_t* text_bytes) {
+    if (!b || !b->ran || !text || !text_bytes) return DPX_ERR_INVALID;
+    dpx_ctx* ctx = b->ctx;
+    const size_t n = b->n_pairs;
+    CU(cudaSetDevice(ctx->device));
+    *text = nullptr; *text_bytes = 0;
+    const bool strings = (b->params.flags & DPX_OUT_STRINGS) != 0;
+    unsigned long long total = 0;
+    unsigned long long *d_len = nullptr, *d_off = nullptr; char* d_text = nullptr; void* tmp = nullptr;
+    auto release = [&]() { ctx->pool.release(d_len); ctx->pool.release(d_off); ctx->pool.release(d_text); ctx->pool.release(tmp); };
+    if (n) {
+        if (!pool_alloc(ctx, &d_len, n + 1) || !pool_alloc(ctx, &d_off, n + 1)) { release(); return DPX_ERR_NOMEM; }
+        text_len_kernel<<<(int)((n + 1 + 255) / 256), 256, 0, b->stream>>>(b->d_pairs, (int)n, first_index, b->d_scores, strings ? b->d_str_start : nullptr, d_len);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_off, (int)n + 1, b->stream);
+        tmp = ctx->pool.alloc(tmp_bytes);
+        if (!tmp) { release(); return DPX_ERR_NOMEM; }
+        cudaError_t e0 = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_off, (int)n + 1, b->stream);
+        cudaError_t e1 = cudaMemcpyAsync(&total, d_off + n, sizeof(total), cudaMemcpyDeviceToHost, b->stream);
+        cudaError_t e2 = cudaStreamSynchronize(b->stream);
+        if (e0 != cudaSuccess || e1 != cudaSuccess || e2 != cudaSuccess) { release(); ctx->err = "text formatting failed"; return DPX_ERR_CUDA; }
+    }
+    char* host = (char*)g_host.take(std::max<size_t>((size_t)total + 1, 1));
+    if (!host) host = (char*)malloc(std::max<size_t>((size_t)total + 1, 1));
+    if (!host) { release(); return DPX_ERR_NOMEM; }
+    if (n) {
+        if (!pool_alloc(ctx, &d_text, (size_t)total + 16)) { release(); dpx_free(host); return DPX_ERR_NOMEM; }
+        text_write_kernel<<<(int)std::min<size_t>((n + 7) / 8, (size_t)ctx->sm_count * 16), 256, 0, b->stream>>>(
+            b->d_pairs, (int)n, first_index, b->d_scores, b->d_strings, b->d_str_off, strings ? b->d_str_start : nullptr, d_off, d_text);
+        cudaError_t e1 = cudaMemcpyAsync(host, d_text, (size_t)total, cudaMemcpyDeviceToHost, b->stream);
+        cudaError_t e2 = cudaStreamSynchronize(b->stream);
+        release();
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { dpx_free(host); ctx->err = "text download failed"; return DPX_ERR_CUDA; }
+    }
+    host[total] = 0;
+    int st = dpx_batch_sync(b);
+    if (st) { dpx_free(host); return st; }
+    *text = host; *text_bytes = (size_t)total;
+    return DPX_OK;
+}
+
+int dpx_align_batch_text(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
+                         const dpx_seq_pair* pairs, size_t n_pairs, long long first_index,
+                         int32_t* scores, int32_t* end_row_col, char** text, size_t* text_bytes) {
+    if (!ctx || !params || !text || !text_bytes || (!sequences && n_bytes) || (!pairs && n_pairs) || n_pairs > 0x7fffffffu) return DPX_ERR_INVALID;
+    dpx_batch* b = nullptr;
+    int st = dpx_batch_upload(ctx, sequences, n_bytes, pairs, n_pairs, &b);
+    if (st) return st;
+    st = dpx_batch_run(b, params);
+    if (!st && (scores || end_row_col)) { st = batch_fetch_async(b, scores, end_row_col); }
+    if (!st) st = dpx_batch_fetch_text(b, first_index, text, text_bytes);
+    dpx_batch_free(b);
+    return st;
+}
+
 // One call, host buffers in and out.  Score / end-cell requests on large batches are cut into chunks of
 // consecutive pairs that alternate between two streams, so the H2D copy of chunk k+1 (and the host's scan of
 // its byte range) overlaps the kernels of chunk k; everything else takes the single-batch route.

@@ -52,24 +52,14 @@ int main(int argc, char* argv[]) {
     dpx_params p = dpxhost::make_params(algo, matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight, band);
     if (scores_only) p.flags = DPX_OUT_SCORE | DPX_OUT_END_COORDS;
     const size_t n = fileInfo.numPairs;
-    std::vector<int32_t> scores(n), rc(2 * n);
-    char* strings = nullptr; size_t* offs = nullptr;
+    // the whole stdout block of the batch is formatted on the GPU and comes back as one buffer
+    char* text = nullptr; size_t text_bytes = 0;
     dpx_ctx* ctx = dpxhost::engine();
-    const int st = dpx_align_batch(ctx, &p, sequences, fileInfo.numBytes, reinterpret_cast<const dpx_seq_pair*>(sequenceIdxs), n,
-                                   scores.data(), rc.data(), scores_only ? nullptr : &strings, scores_only ? nullptr : &offs);
+    const int st = dpx_align_batch_text(ctx, &p, sequences, fileInfo.numBytes, reinterpret_cast<const dpx_seq_pair*>(sequenceIdxs), n,
+                                        0, nullptr, nullptr, &text, &text_bytes);
     if (st != DPX_OK) { fprintf(stderr, "dpxalign: %s (%s)\n", dpx_strerror(st), dpx_last_error(ctx)); exit(1); }
-
-    std::string out;
-    out.reserve(1 << 20);
-    for (size_t i = 0; i < n; ++i) {
-        out += std::to_string(i); out += " | "; out += std::to_string(scores[i]); out += '\n';
-        if (!scores_only) {
-            for (int k = 0; k < 3; ++k) { out += strings + offs[3 * i + k]; out += '\n'; }
-        }
-        if (out.size() > (1u << 20)) { fwrite(out.data(), 1, out.size(), stdout); out.clear(); }
-    }
-    fwrite(out.data(), 1, out.size(), stdout);
-    dpx_free(strings); dpx_free(offs);
+    fwrite(text, 1, text_bytes, stdout);
+    dpx_free(text);
 
     const long long usec = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     printf("Elapsed time (usec): %lld\n", usec);

@@ -140,6 +140,17 @@ int         dpx_batch_fetch(dpx_batch* b, int32_t* scores, int32_t* end_row_col,
                             char** strings_blob, size_t** string_offsets);
 void        dpx_batch_free(dpx_batch* b);
 
+/* ---- formatted output: the exact bytes the reference prints for the batch, formatted on the GPU.
+ * Per pair "<first_index + i> | <score>\n" (c++/LinearNeedlemanWunsch.cpp:207-209: printf("%d | ") + cout << score) followed,
+ * when the run had DPX_OUT_STRINGS, by REF "\n" REL "\n" QRY "\n" (:210-213); a Smith-Waterman score of 0 gives three empty
+ * lines (c++/LinearSmithWaterman.cpp:253-257).  *text is library-allocated (dpx_free), *text_bytes its length (a NUL follows).
+ * dpx_align_batch_text = upload + run + fetch_text in one call; scores / end_row_col may be NULL. */
+int         dpx_batch_fetch_text(dpx_batch* b, long long first_index, char** text, size_t* text_bytes);
+int         dpx_align_batch_text(dpx_ctx* ctx, const dpx_params* params,
+                                 const char* sequences, size_t n_bytes,
+                                 const dpx_seq_pair* pairs, size_t n_pairs, long long first_index,
+                                 int32_t* scores, int32_t* end_row_col, char** text, size_t* text_bytes);
+
 /* Statistics of the last dpx_batch_run on this batch (after dpx_batch_sync). */
 typedef struct {
     double   fill_ms;          /* CUDA-event time of the fill kernel(s) */

@@ -298,3 +298,25 @@ def test_one_call_pipeline_redoes_when_alphabet_grows(eng, late_symbol):
     for sl in (slice(0, 3000), slice(n - 6000, n)):
         s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs[sl], strings=False, threads=8)
         assert (one.scores[sl] == s).all() and (one.end_row_col[sl] == e).all()
+
+
+@pytest.mark.parametrize("algo", [api.LNW, api.LSW, api.ANW, api.BSW])
+def test_gpu_formatted_text_equals_host_formatting(eng, algo):
+    """dpx_align_batch_text: the reference's stdout blocks written by the GPU (digits, separators, strings, empty SW lines)."""
+    blob, pairs = random_pairs(0x7E87 + algo, 333, 120)
+    w = dict(KW.get(algo, dict(gap_open=-2)))
+    if algo == api.BSW:
+        w["band"] = 9
+    res = eng.align_batch(api.make_params(algo, flags=ALL, **w), blob, pairs)
+    assert eng.align_batch_text(api.make_params(algo, flags=ALL, **w), blob, pairs) == res.text()
+    assert eng.align_batch_text(api.make_params(algo, flags=ALL, **w), blob, pairs, first_index=99990) == res.text(99990)
+    lines = b"".join(b"%d | %d\n" % (i, int(s)) for i, s in enumerate(res.scores))
+    assert eng.align_batch_text(api.make_params(algo, flags=api.OUT_SCORE, **w), blob, pairs) == lines
+
+
+def test_gpu_formatted_text_golden(eng):
+    for algo in (api.LNW, api.LSW, api.ANW):
+        p = api.parse_input(os.path.join(GOLD, "adversarial.in.txt"))
+        want = open(os.path.join(GOLD, f"adversarial.{NAMES[algo]}.out.txt"), "rb").read()
+        assert eng.align_batch_text(api.make_params(algo, flags=ALL, **KW[algo]), p.sequences, p.pairs) == want
+    assert eng.align_batch_text(api.make_params(api.LNW, flags=ALL), np.zeros(0, np.uint8), np.zeros(0, api.PAIR_DTYPE)) == b""

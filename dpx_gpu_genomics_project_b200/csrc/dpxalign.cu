@@ -580,21 +580,25 @@ static int ensure_str_off(dpx_batch* b) {
 
 
 // ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
-struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc, addc3; int b0, b1, bstep, dec_sub, dec_add; };
+struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
 
 static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
-    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW) || !b->packed2 || getenv("DPX_NO_PAIRWF")) return false;
+    const bool sw = p->algo == DPX_ALGO_LSW;
+    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || !b->packed2 || getenv("DPX_NO_PAIRWF")) return false;
+    if (sw && !(p->flags & DPX_OUT_STRINGS)) return false;      // score / end cell alone: the short-read kernel (or the int32 wavefront)
     const bool aff = p->algo == DPX_ALGO_ANW;
     const long long m = p->match, x = p->mismatch, go = p->gap_open, ge = aff ? p->gap_extend : 0;
     const long long open = aff ? go + ge : go;                   // cost of the first gap column: "goe" (Gotoh) or g (linear)
     if (open >= 0 || ge > 0 || go > 0) return false;             // the add constant must be negative (always-carry rule)
+    if (sw && !(m > 0 && x < 0)) return false;                   // pads must stay strictly below the maximum
     const long long code = aff ? 3 : 1;
     const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
     if (tm < 0 || tm > 127 || tx < 0 || tx > 127) return false;     // table bytes are sign-extended by the selector
     const int K = 8;
     const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
-    // lowest value any stored quantity can take (gaps-only path bounds H from below) and the highest score
-    const long long lo = aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
+    // lowest value any stored quantity can take (gaps-only path bounds H from below; Smith-Waterman: H >= 0) and the highest score
+    const long long lo = sw ? go - 2
+                       : aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
                              : (Qp + Rp + 1) * go + std::min<long long>(x, 0) - 2;
     const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
     const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
@@ -607,10 +611,11 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long c = aff ? 4 * open : 4 * open - 2;           // (h' | 3) + c -> code 3 (Gotoh) / code 1 (linear)
     pl->addc = (uint32_t)(c & 0xffff) | ((uint32_t)((c - 1) & 0xffff) << 16);
     pl->addc3 = (uint32_t)((c + 3) & 0xffff) | ((uint32_t)((c + 2) & 0xffff) << 16);
+    pl->zero2 = pk(B + 3);
     pl->b0 = (int)(4 * open + B + code);
     pl->b1 = aff ? (int)(4 * (go + open) + B + code) : pl->b0;
-    pl->bstep = (int)(4 * (aff ? ge : go));
-    pl->dec_sub = (int)(B + code); pl->dec_add = (int)(-open);
+    pl->bstep = sw ? 0 : (int)(4 * (aff ? ge : go));             // Smith-Waterman borders are 0 everywhere
+    pl->dec_sub = (int)(sw ? B : B + code); pl->dec_add = (int)(sw ? 0 : -open);
     return true;
 }
 
@@ -766,7 +771,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             }
             PwArgs a{};
             a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
-            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu;
+            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu; a.zero2 = pl.zero2;
             a.one = 1u; a.two = 2u; a.four = 4u; a.eight = 8u; a.sixteen = 16u;
             a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
             a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
@@ -783,7 +788,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 CU(cudaEventRecord(s, st));
                 const int n_slots = (a.count + 1) / 2;
                 int r;
-                if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, st, a, smem, n_slots);
+                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, st, a, smem, n_slots);
+                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, st, a, smem, n_slots);
                 else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, st, a, smem, n_slots);
                 if (r) return r;
                 CU(cudaEventRecord(e, st));
@@ -792,10 +798,12 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     PwBtArgs t{};
                     t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.K = pl.K;
                     t.tb = b->d_tb; t.tb_stride = tbs; t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
+                    t.scores = b->d_scores; t.end_rc = b->d_end_rc;
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, st));
                     const int bt_blocks = (a.count + 127) / 128;
-                    if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, st>>>(t);
                     else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, st>>>(t);
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, st));

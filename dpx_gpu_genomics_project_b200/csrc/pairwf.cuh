@@ -24,6 +24,12 @@
 //   Linear  m  = viaddmax(Hg[diag], tab, Hg[up])   diag code 0 / up code 1;  h' = viaddmax(Hg[left], 1, m)  left code 2
 //           Hg = (h' | 3) + 4g - 2           "H + gap", code 1
 //   => per cell-pair 5 ALU-pipe + 3 FMA-pipe instructions.
+//   Smith-Waterman (c++/LinearSmithWaterman.cpp:70-114, tie-break UP > LEFT > DIAG by equality with H, NONE iff H == 0):
+//           m  = viaddmax(Hg[diag], tab, Hg[left])   diag code 0 / left code 1;  h' = vimax3(m, Hg[up] + 1, zero)  up code 2,
+//           "zero" = BIAS + 3 is the STOP code;  Hg = (h' - code) + 4g + 1.  End cell (first strict maximum in row-major order,
+//           :145-157): every register row keeps its running maximum of clean(h') with one predicate-returning VIMNMX.S16x2 and
+//           the step at which it last grew (two SEL); rows, lanes and passes are merged by (score desc, row asc, column asc).
+//   => per cell-pair 7 ALU-pipe + 4 FMA-pipe instructions.
 // All adds that are not fused into a DPX instruction are plain 32-bit IMADs on the FMA pipe: every stored value is
 // biased positive (>= the largest |constant|), so adding a negative constant ALWAYS carries out of the low half (the
 // constant's high half is pre-decremented) and adding a table entry (>= 0) NEVER does.
@@ -40,6 +46,7 @@ namespace dpx {
 
 constexpr uint32_t PW_DIAG = 0, PW_UP = 1, PW_LEFT = 2;     // direction codes of this kernel family
 constexpr uint32_t PW_DOPEN = 4, PW_IOPEN = 8;
+constexpr uint32_t PW_SW_DIAG = 0, PW_SW_LEFT = 1, PW_SW_UP = 2, PW_SW_STOP = 3;   // Smith-Waterman codes of this family
 
 struct PwGeom {
     int K, CB, W;                // rows per lane, code bits, words per lane-step
@@ -61,6 +68,7 @@ struct PwArgs {
     uint32_t addc;                       // carry-compensated add constant: Gotoh 4*goe, linear 4*g - 2   (applied to h' | 3)
     uint32_t addc3;                      // the same + 3                                                  (applied to h' - code)
     uint32_t minus1;                     // 0xffffffff: run-time multiplier for FMA-pipe subtractions
+    uint32_t zero2;                      // Smith-Waterman: packed BIAS + 3 (H = 0 with the STOP code)
     uint32_t one, two, four, eight, sixteen;   // run-time multipliers: keep shifts / adds on the FMA pipe as IMAD
     int b0, b1, bstep;                   // border(idx) = idx == 0 ? b0 : b1 + bstep * idx   (stored form, one half)
     int dec_sub, dec_add;                // score = ((half - dec_sub) >> 2) + dec_add
@@ -77,12 +85,31 @@ __device__ __forceinline__ uint32_t fma_mul(uint32_t a, uint32_t m) {
     asm("mad.lo.u32 %0, %1, %2, 0;" : "=r"(d) : "r"(a), "r"(m));
     return d;
 }
+// max.s16x2 with the two "a >= b" predicates (VIMNMX.S16x2 Rd, P1, P2).  Same PTX as CUDA's __vibmax_s16x2, but with
+// early-clobber outputs: the header's asm reads `a` after writing the result, so an in-place update (a = vibmax(a, b))
+// lets the register allocator overlap them and the predicates come out always true.
+__device__ __forceinline__ uint32_t vibmax_s16x2_safe(uint32_t a, uint32_t b, bool* ge_hi, bool* ge_lo) {
+    uint32_t val, phi, plo;
+    asm("{.reg .pred pu, pv; \n\t"
+        ".reg .s16 rs0, rs1, rs2, rs3; \n\t"
+        "max.s16x2 %0, %3, %4; \n\t"
+        "mov.b32 {rs0, rs1}, %0; \n\t"
+        "mov.b32 {rs2, rs3}, %3; \n\t"
+        "setp.eq.s16 pv, rs0, rs2; \n\t"
+        "setp.eq.s16 pu, rs1, rs3; \n\t"
+        "selp.b32 %1, 1, 0, pu; \n\t"
+        "selp.b32 %2, 1, 0, pv;} \n\t"
+        : "=&r"(val), "=&r"(phi), "=&r"(plo) : "r"(a), "r"(b));
+    *ge_hi = (bool)phi; *ge_lo = (bool)plo;
+    return val;
+}
 __device__ __forceinline__ uint32_t pw_pack(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
 
 template <int ALGO, bool TB, int K>
 __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
     extern __shared__ uint32_t pw_smem[];
     constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
+    constexpr bool SW = (ALGO == DPX_ALGO_LSW);
     constexpr int CB = AFF ? 4 : 2;
     constexpr int CPH = 16 / CB;                   // cells per half-word
     constexpr int W = K / CPH;
@@ -92,7 +119,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
     uint32_t* __restrict__ bndH = pw_smem + (size_t)wib * a.bnd_stride * (AFF ? 2 : 1);
     uint32_t* __restrict__ bndD = bndH + a.bnd_stride;
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (size_t)4 * a.bnd_stride * (AFF ? 2 : 1)) + (size_t)wib * a.rsel_stride;
-    const uint32_t one = a.one, ext2 = a.ext2, addc = a.addc, addc3 = a.addc3, minus1 = a.minus1;
+    const uint32_t one = a.one, ext2 = a.ext2, addc = a.addc, addc3 = a.addc3, minus1 = a.minus1, zero2 = a.zero2;
     const uint32_t ms1 = a.lut_hi & 0xffu, xs4 = (a.lut_lo & 0xffu) * 0x01010101u;     // table entries: match, mismatch
     const uint32_t two = a.two, four = a.four, eight = a.eight, sixteen = a.sixteen;
     const int n_slots = (a.count + 1) >> 1;
@@ -139,9 +166,14 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
         const int ppA = (QA > 0) ? (QA - 1) / (32 * K) : -1, glA = (QA > 0) ? ((QA - 1) / K) & 31 : -1, rrA = (QA > 0) ? (QA - 1) % K : 0;
         const int ppB = (QB > 0) ? (QB - 1) / (32 * K) : -1, glB = (QB > 0) ? ((QB - 1) / K) & 31 : -1, rrB = (QB > 0) ? (QB - 1) % K : 0;
 
+        int swA = 0, swRowA = 0, swColA = 0, swB = 0, swRowB = 0, swColB = 0;     // SW: this lane's best (clean stored score, row, column)
+
         for (int p = 0; p < passes; ++p) {
             const int i0 = p * 32 * K + lane * K;                // rows above this lane's block; its rows are i0+1 .. i0+K
             uint32_t ta[K], tb[K], hA[K], hB[K], Ic[AFF ? K : 1];   // ta / tb: table entry of this row's base against bases 0..3
+            uint32_t bestv[SW ? K : 1]; int stA[SW ? K : 1], stB[SW ? K : 1];        // SW: per-row running maximum and the step it last grew at
+            #pragma unroll
+            for (int r = 0; r < (SW ? K : 1); ++r) { bestv[r] = 0; stA[r] = 0; stB[r] = 0; }
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
@@ -168,7 +200,9 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                 for (int w = 0; w < W; ++w) acc[w] = 0;                                                              \
                 if (j >= 1) {                                                                                        \
                     if (lane == 0) {                                                                                 \
-                        if (p == 0) { topH = pw_pack(a.b1 + a.bstep * j); topD = 0x00010001u; }  /* row 0 border; D[0][j] never wins (:185-189) */ \
+                        /* row 0 border (D[0][j] never wins, :185-189), or the previous pass's last row; columns beyond the   \
+                           duo are pads whose row was never written: give them border values so they stay in range */      \
+                        if (p == 0 || j > Rw) { topH = pw_pack(a.b1 + a.bstep * j); topD = 0x00010001u; }                \
                         else { topH = bndH[j]; if (AFF) topD = bndD[j]; }                                            \
                     }                                                                                                \
                     const uint32_t rs = rsel[(S) - lane + 32];                                                       \
@@ -192,6 +226,17 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                                 acc[r / CPH] = fma_add(fma_add(Icn, minus1, In), eight, acc[r / CPH]);               \
                                 NEW[r] = fma_add(h | 0x00030003u, one, addc);                                        \
                             }                                                                                        \
+                        } else if constexpr (SW) {                                                                   \
+                            const uint32_t m = __viaddmax_s16x2(diag, sc, OLD[r]);          /* diag 0 / left 1 */    \
+                            h = __vimax3_s16x2(m, fma_add(up, one, ext2), zero2);           /* up 2 / zero 3 */      \
+                            const uint32_t t = h & 0x00030003u;                                                      \
+                            const uint32_t hq = fma_add(t, minus1, h);                      /* clean: 4H + BIAS */   \
+                            if (TB) acc[r / CPH] = fma_add(acc[r / CPH], four, t);                                   \
+                            NEW[r] = fma_add(hq, one, addc3);                                                        \
+                            bool keepHi, keepLo;                                            /* best >= hq: no new maximum */ \
+                            bestv[r] = vibmax_s16x2_safe(bestv[r], hq, &keepHi, &keepLo);                            \
+                            stA[r] = keepLo ? stA[r] : (S);                                                          \
+                            stB[r] = keepHi ? stB[r] : (S);                                                          \
                         } else {                                                                                     \
                             const uint32_t m = __viaddmax_s16x2(diag, sc, up);                                       \
                             h = __viaddmax_s16x2(OLD[r], ext2, m);                                                   \
@@ -202,7 +247,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                             }                                                                                        \
                         }                                                                                            \
                         diag = OLD[r];                                                                               \
-                        if (!TB) NEW[r] = fma_add(h | 0x00030003u, one, addc);                                       \
+                        if (!TB && !SW) NEW[r] = fma_add(h | 0x00030003u, one, addc);                                \
                         up = NEW[r];                                                                                 \
                     }                                                                                                \
                     botH = up; botD = upD;                                                                           \
@@ -227,13 +272,13 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                     DPX_PW_STEP(s, hA, hB)
                     DPX_PW_STEP(s + 1, hB, hA)
                 }
-                if (sA >= 0 && s == eA && lane == glA) {
+                if (!SW && sA >= 0 && s == eA && lane == glA) {
                     uint32_t v = 0;
                     #pragma unroll
                     for (int r = 0; r < K; ++r) if (r == rrA) v = (sA & 1) ? hA[r] : hB[r];
                     a.scores[pa] = (((int)(v & 0xffffu) - a.dec_sub) >> 2) + a.dec_add;
                 }
-                if (sB >= 0 && s == eB && lane == glB) {
+                if (!SW && sB >= 0 && s == eB && lane == glB) {
                     uint32_t v = 0;
                     #pragma unroll
                     for (int r = 0; r < K; ++r) if (r == rrB) v = (sB & 1) ? hA[r] : hB[r];
@@ -241,9 +286,38 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                 }
             }
 #undef DPX_PW_STEP
+            if constexpr (SW) {
+                // rows of this pass into the lane's best: higher score, then smaller row (rows ascend with r and with the pass)
+                #pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int vA = (int)(bestv[r] & 0xffffu), vB = (int)(bestv[r] >> 16);
+                    if (i0 + r < QA && vA > swA) { swA = vA; swRowA = i0 + r + 1; swColA = stA[r] - lane + 1; }
+                    if (i0 + r < QB && vB > swB) { swB = vB; swRowB = i0 + r + 1; swColB = stB[r] - lane + 1; }
+                }
+            }
             __syncwarp();
         }
 
+        if constexpr (SW) {
+            // merge the lanes: higher score, then smaller row, then smaller column; score 0 (= the bias) has no end cell
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int oA = __shfl_xor_sync(FULL, swA, off), orA = __shfl_xor_sync(FULL, swRowA, off), ocA = __shfl_xor_sync(FULL, swColA, off);
+                const int oB = __shfl_xor_sync(FULL, swB, off), orB = __shfl_xor_sync(FULL, swRowB, off), ocB = __shfl_xor_sync(FULL, swColB, off);
+                if (oA > swA || (oA == swA && (orA < swRowA || (orA == swRowA && ocA < swColA)))) { swA = oA; swRowA = orA; swColA = ocA; }
+                if (oB > swB || (oB == swB && (orB < swRowB || (orB == swRowB && ocB < swColB)))) { swB = oB; swRowB = orB; swColB = ocB; }
+            }
+            if (lane == 0) {
+                const int sa = swA > a.dec_sub ? (swA - a.dec_sub) >> 2 : 0, sb = swB > a.dec_sub ? (swB - a.dec_sub) >> 2 : 0;
+                a.scores[pa] = sa;
+                if (a.end_rc) { a.end_rc[2 * pa] = sa > 0 ? swRowA : 0; a.end_rc[2 * pa + 1] = sa > 0 ? swColA : 0; }
+                if (pb >= 0) {
+                    a.scores[pb] = sb;
+                    if (a.end_rc) { a.end_rc[2 * pb] = sb > 0 ? swRowB : 0; a.end_rc[2 * pb + 1] = sb > 0 ? swColB : 0; }
+                }
+            }
+            continue;
+        }
         // pairs with an empty sequence: the score is a pure border cell, nothing was captured above
         if (lane == 0) {
             if (QA == 0 || RA == 0) { const int n = QA + RA; a.scores[pa] = (((n == 0 ? a.b0 : a.b1 + a.bstep * n) - a.dec_sub) >> 2) + a.dec_add; }
@@ -265,6 +339,7 @@ struct PwBtArgs {
     const int32_t* order;
     int first, count;
     int K;
+    const int32_t* scores; const int32_t* end_rc;   // Smith-Waterman: start cells
     const uint32_t* tb;
     unsigned long long tb_stride;        // words per slot
     char* strings;
@@ -312,7 +387,20 @@ __global__ void __launch_bounds__(128) pw_bt_kernel(const PwBtArgs a) {
     auto emit_left = [&](int j)        { --p; o0[p] = ref[j - 1]; o1[p] = ' '; o2[p] = '_'; };
 
     int i = Q, j = R;
-    if (!AFF) {
+    if (ALGO == DPX_ALGO_LSW) {
+        // c++/LinearSmithWaterman.cpp:163-226: from the end cell apply the cell's direction, stop when the next cell's H is 0
+        if (a.scores[pid] > 0) {
+            i = a.end_rc[2 * pid]; j = a.end_rc[2 * pid + 1];
+            uint32_t c = code(i, j);
+            while (c != PW_SW_STOP) {
+                if (c == PW_SW_DIAG) { emit_diag(i, j); --i; --j; }
+                else if (c == PW_SW_UP) { emit_up(i); --i; }
+                else { emit_left(j); --j; }
+                if (i == 0 || j == 0) break;
+                c = code(i, j);
+            }
+        }
+    } else if (!AFF) {
         while (i != 0 || j != 0) {
             const uint32_t c = (i == 0) ? PW_LEFT : (j == 0) ? PW_UP : code(i, j);
             if (c == PW_DIAG) { emit_diag(i, j); --i; --j; }

@@ -1,4 +1,4 @@
-"""GPU parity of the packed two-pair Needleman-Wunsch / Gotoh kernels (csrc/pairwf.cuh: int16x2, directions in the low
+"""GPU parity of the packed two-pair Needleman-Wunsch / Gotoh / Smith-Waterman-with-traceback kernels (csrc/pairwf.cuh: int16x2, directions in the low
 score bits) against the CPU oracle: scores and the three alignment strings, bit-exact.  Covers ragged duos, odd pair
 counts, empty sequences, several passes (Q > 256), tie-heavy alphabets, weight sets at the edge of the kernel's range,
 and the fall-back to the int32 wavefront kernel when a batch does not fit."""
@@ -24,7 +24,7 @@ def _check(eng, algo, blob, pairs, want_kernel=None, **w):
     b = eng.upload(blob, pairs)
     for flags in (ALL, api.OUT_SCORE | api.OUT_END_COORDS):
         b.run(api.make_params(algo, flags=flags, **w)); b.sync()
-        if want_kernel is not None:
+        if want_kernel is not None and (algo != api.LSW or flags & api.OUT_STRINGS):      # LSW without strings: short-read kernel
             assert b.stats()["kernel_id"] == want_kernel
         res = b.fetch()
         s, e, t = ol.align_batch(ol.params(algo, **w), blob, pairs, strings=bool(flags & api.OUT_STRINGS), threads=8)
@@ -54,26 +54,28 @@ def _ragged(seed, n, lo, hi, alphabet=b"0123", related=True):
 WEIGHTS = {
     api.LNW: [dict(match=3, mismatch=-1, gap_open=-2), dict(match=1, mismatch=-1, gap_open=-2), dict(match=5, mismatch=-3, gap_open=-4),
               dict(match=2, mismatch=0, gap_open=-1)],
+    api.LSW: [dict(match=3, mismatch=-1, gap_open=-2), dict(match=1, mismatch=-1, gap_open=-2), dict(match=5, mismatch=-3, gap_open=-4),
+              dict(match=2, mismatch=-1, gap_open=-2)],
     api.ANW: [dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1), dict(match=2, mismatch=-2, gap_open=-2, gap_extend=-1),
               dict(match=4, mismatch=-1, gap_open=0, gap_extend=-2), dict(match=1, mismatch=-1, gap_open=-4, gap_extend=0)],
 }
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 @pytest.mark.parametrize("wi", [0, 1, 2, 3])
 def test_ragged_batches(eng, algo, wi):
     blob, pairs = _ragged(100 + wi, 301, 1, 120)
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][wi])
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 @pytest.mark.parametrize("alphabet", [b"0", b"01", b"012"])
 def test_tie_heavy_alphabets(eng, algo, alphabet):
     blob, pairs = _ragged(7, 200, 1, 90, alphabet, related=False)
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][0])
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 def test_multi_pass_queries(eng, algo):
     """Q > 256 rows takes several passes through the shared-memory boundary row; R, Q around the pass and step edges."""
     pp = []
@@ -87,7 +89,7 @@ def test_multi_pass_queries(eng, algo):
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][0])
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 def test_config3_shape(eng, algo):
     """BASELINE config 3 shape (1000 x 1000, mutated 2% / 0.5% / 0.5%), a small batch with an odd pair count."""
     img = synth.mutated_fixed_file_bytes(33, 1000, 1000, 0x5EED0003, 0.02, 0.005, 0.005)
@@ -95,18 +97,18 @@ def test_config3_shape(eng, algo):
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][0])
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 def test_empty_sequences_inside_a_batch(eng, algo):
     pp = [(b"", b""), (b"0123", b""), (b"", b"3210"), (b"0", b"0"), (b"0123012301", b"0123012301"), (b"", b"1")]
     blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][0])
 
 
-@pytest.mark.parametrize("algo", [api.LNW, api.ANW])
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 def test_out_of_range_batches_fall_back_to_the_int32_kernel(eng, algo):
     # scores beyond the int16 budget (4 * (hi - lo) must stay below 2^15) or a mismatch worse than a gap open
-    blob, pairs = _ragged(5, 6, 2500, 2600)
+    blob, pairs = _ragged(5, 6, 2800, 2900)
     _check(eng, algo, blob, pairs, KERNEL_WAVEFRONT, **WEIGHTS[algo][0])
     blob, pairs = _ragged(6, 50, 1, 80)
-    w = dict(match=3, mismatch=-9, gap_open=-2) if algo == api.LNW else dict(match=3, mismatch=-9, gap_open=-2, gap_extend=-1)
+    w = dict(match=3, mismatch=-9, gap_open=-2, gap_extend=-1) if algo == api.ANW else dict(match=3, mismatch=-9, gap_open=-2)
     _check(eng, algo, blob, pairs, KERNEL_WAVEFRONT, **w)

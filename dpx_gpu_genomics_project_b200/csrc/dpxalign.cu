@@ -129,7 +129,8 @@ struct dpx_batch {
     // device outputs
     int32_t* d_scores = nullptr;
     int32_t* d_end_rc = nullptr;
-    uint32_t* d_tb = nullptr;
+    uint32_t* d_tb = nullptr; size_t tb_words = 0;   // traceback slab (one or two chunk buffers) and its capacity
+    std::vector<cudaEvent_t> ev_sync;                // fill-done / backtrack-done events of the chunk pipeline
     char* d_strings = nullptr;
     unsigned long long* d_str_off = nullptr;
     int32_t* d_str_start = nullptr;
@@ -339,6 +340,7 @@ static void batch_release(dpx_batch* b) {
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
     P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
     for (auto e : b->ev) cudaEventDestroy(e);
+    for (auto e : b->ev_sync) cudaEventDestroy(e);
     if (b->ev_begin) cudaEventDestroy(b->ev_begin);
     if (b->ev_end) cudaEventDestroy(b->ev_end);
     if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
@@ -689,7 +691,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     b->params = *p; b->ran = true;
     b->stats = dpx_run_stats{};
     for (auto e : b->ev) cudaEventDestroy(e);
-    b->ev.clear(); b->ev_kind.clear();
+    for (auto e : b->ev_sync) cudaEventDestroy(e);
+    b->ev.clear(); b->ev_kind.clear(); b->ev_sync.clear();
     const bool want_strings = (p->flags & DPX_OUT_STRINGS) != 0;
     const int algo = p->algo;
     const int CB = (algo == DPX_ALGO_ANW) ? 4 : 2;
@@ -762,12 +765,33 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             const bool aff = algo == DPX_ALGO_ANW;
             const PwGeom geo = PwGeom::make(pl.K, aff ? 4 : 2);
             const unsigned long long tbs = want_strings ? geo.words(b->max_q, b->max_r) : 0;
-            size_t per_chunk = n;
+            // Traceback runs are cut into chunks over TWO slab buffers: the backtrack of chunk c runs on a second stream while
+            // the fill kernel of chunk c+1 writes the other buffer (the walk is latency-bound and leaves the issue slots to the fill).
+            size_t per_chunk = n; int nbuf = 1;
             if (want_strings) {
-                size_t slots = std::max<size_t>(1, std::min<size_t>((n + 1) / 2, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tbs, 1)));
-                per_chunk = 2 * slots;
-                if (!b->d_tb && !pool_alloc(ctx, &b->d_tb, slots * (size_t)tbs)) return DPX_ERR_NOMEM;
+                const size_t slots_total = (n + 1) / 2;
+                const size_t max_slots = std::max<size_t>(1, (ctx->tb_budget_bytes / 2 / 4) / std::max<unsigned long long>(tbs, 1));
+                size_t nchunks = (slots_total + max_slots - 1) / max_slots;
+                if (!getenv("DPX_SERIAL_CHUNKS"))                                               // (set by bench.py to time the fill kernel alone)
+                    nchunks = std::max<size_t>(nchunks, std::min<size_t>(8, n / 16384));        // >= 16k pairs per chunk: whole waves of warps
+                const size_t slots = (slots_total + nchunks - 1) / nchunks;
+                per_chunk = 2 * slots; nbuf = (nchunks > 1 && !getenv("DPX_SERIAL_CHUNKS")) ? 2 : 1;
+                const size_t need = (size_t)nbuf * slots * (size_t)tbs;
+                if (b->d_tb && b->tb_words < need) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
+                if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, need)) return DPX_ERR_NOMEM; b->tb_words = need; }
                 b->stats.traceback_bytes = (uint64_t)((n + 1) / 2) * tbs * 4;
+            }
+            // streams of the chunk pipeline: fills alternate between the batch stream and a second one (the tail of one fill
+            // overlaps the head of the next), walks run on a third
+            cudaStream_t bt_st = nbuf > 1 ? ctx->aux_stream[0] : st;
+            cudaStream_t fill2_st = nbuf > 1 ? ctx->aux_stream[1] : st;
+            auto sync_event = [&](cudaEvent_t* ev) -> int { CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming)); b->ev_sync.push_back(*ev); return DPX_OK; };
+            std::vector<cudaEvent_t> bt_done, fill_done;
+            if (nbuf > 1) {
+                cudaEvent_t start;
+                { int r2 = sync_event(&start); if (r2) return r2; }
+                CU(cudaEventRecord(start, st));
+                CU(cudaStreamWaitEvent(fill2_st, start, 0));
             }
             PwArgs a{};
             a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
@@ -782,34 +806,51 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             for (size_t first = 0; first < n; first += per_chunk, ++c) {
                 a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
                 a.counter = counters + (c % 64);
-                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
+                a.tb = want_strings ? b->d_tb + (size_t)(c % nbuf) * (per_chunk / 2) * (size_t)tbs : nullptr;
+                cudaStream_t fst = (c & 1) ? fill2_st : st;
+                if (nbuf > 1 && c >= nbuf) CU(cudaStreamWaitEvent(fst, bt_done[c - nbuf], 0));     // the buffer's previous walk is over
+                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), fst));
                 cudaEvent_t s, e;
                 { int r = add_event_pair(0, &s, &e); if (r) return r; }
-                CU(cudaEventRecord(s, st));
+                CU(cudaEventRecord(s, fst));
                 const int n_slots = (a.count + 1) / 2;
                 int r;
-                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, st, a, smem, n_slots);
-                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, st, a, smem, n_slots);
-                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, st, a, smem, n_slots) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, st, a, smem, n_slots);
+                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, fst, a, smem, n_slots);
+                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots);
+                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, fst, a, smem, n_slots) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, fst, a, smem, n_slots);
                 if (r) return r;
-                CU(cudaEventRecord(e, st));
+                CU(cudaEventRecord(e, fst));
                 b->stats.kernel_launches++;
                 if (want_strings) {
+                    if (nbuf > 1) {
+                        cudaEvent_t filled;
+                        { int r2 = sync_event(&filled); if (r2) return r2; }
+                        CU(cudaEventRecord(filled, fst));
+                        CU(cudaStreamWaitEvent(bt_st, filled, 0));
+                        fill_done.push_back(filled);
+                    }
                     PwBtArgs t{};
                     t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.K = pl.K;
-                    t.tb = b->d_tb; t.tb_stride = tbs; t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
+                    t.tb = a.tb; t.tb_stride = tbs; t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
                     t.scores = b->d_scores; t.end_rc = b->d_end_rc;
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
-                    CU(cudaEventRecord(s, st));
+                    CU(cudaEventRecord(s, bt_st));
                     const int bt_blocks = (a.count + 127) / 128;
-                    if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8><<<bt_blocks, 128, 0, st>>>(t);
-                    else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, st>>>(t);
-                    else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, st>>>(t);
+                    if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
+                    else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
+                    else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
                     CU(cudaGetLastError());
-                    CU(cudaEventRecord(e, st));
+                    CU(cudaEventRecord(e, bt_st));
                     b->stats.kernel_launches++;
+                    if (nbuf > 1) {
+                        cudaEvent_t walked;
+                        { int r2 = sync_event(&walked); if (r2) return r2; }
+                        CU(cudaEventRecord(walked, bt_st));
+                        bt_done.push_back(walked);
+                    }
                 }
             }
+            for (size_t k = 0; k < bt_done.size(); ++k) CU(cudaStreamWaitEvent(st, bt_done[k], 0));     // the batch stream ends after every walk
             CU(cudaEventRecord(b->ev_end, st));
             return DPX_OK;
         }
@@ -834,7 +875,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             size_t per_chunk = n;
             if (want_strings) {
                 per_chunk = std::max<size_t>(1, std::min<size_t>(n, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tbs, 1)));
-                if (!b->d_tb && !pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tbs)) return DPX_ERR_NOMEM;
+                if (b->d_tb && b->tb_words < per_chunk * (size_t)tbs) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
+                if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tbs)) return DPX_ERR_NOMEM; b->tb_words = per_chunk * (size_t)tbs; }
                 b->stats.traceback_bytes = (uint64_t)n * tbs * 4;
             }
             BandArgs a{};
@@ -878,7 +920,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     size_t per_chunk = n;
     if (want_strings) {
         per_chunk = std::max<size_t>(1, std::min<size_t>(n, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tb_stride, 1)));
-        if (!b->d_tb && !pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tb_stride)) return DPX_ERR_NOMEM;
+        if (b->d_tb && b->tb_words < per_chunk * (size_t)tb_stride) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
+        if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tb_stride)) return DPX_ERR_NOMEM; b->tb_words = per_chunk * (size_t)tb_stride; }
         b->stats.traceback_bytes = (uint64_t)n * tb_stride * 4;
     }
 

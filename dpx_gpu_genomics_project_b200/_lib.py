@@ -92,6 +92,9 @@ def lib() -> C.CDLL:
     L.dpx_batch_fetch_text.restype = C.c_int; L.dpx_batch_fetch_text.argtypes = [vp, C.c_longlong, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.dpx_align_batch_text.restype = C.c_int
     L.dpx_align_batch_text.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_longlong, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.dpx_batch_upload_image.restype = C.c_int; L.dpx_batch_upload_image.argtypes = [vp, vp, C.c_size_t, C.POINTER(vp), C.POINTER(InputInfo)]
+    L.dpx_align_file_text.restype = C.c_int
+    L.dpx_align_file_text.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_longlong, C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(InputInfo)]
     L.dpx_batch_stats.restype = C.c_int; L.dpx_batch_stats.argtypes = [vp, C.POINTER(RunStats)]
     L.dpx_align_long_pair.restype = C.c_int
     L.dpx_align_long_pair.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,

@@ -130,6 +130,19 @@ class Engine:
         finally:
             self.L.dpx_free(txt)
 
+    def align_file_text(self, params: _lib.Params, path: str, first_index: int = 0):
+        """(text, info): the reference driver's stdout blocks for a whole input file; parser, alignment and formatting on the GPU."""
+        txt, nb, info = C.c_void_p(), C.c_size_t(), _lib.InputInfo()
+        _check(self.L.dpx_align_file_text(self.ctx, C.byref(params), path.encode(), first_index, C.byref(txt), C.byref(nb), C.byref(info)), self.ctx)
+        try:
+            return C.string_at(txt, nb.value), {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_}
+        finally:
+            self.L.dpx_free(txt)
+
+    def upload_image(self, image: bytes) -> "Batch":
+        """Batch from a file image (3 lines per pair); the parser runs on the device."""
+        return Batch(self, None, None, image=image)
+
     def _take_strings(self, sb, so, n):
         try:
             offs = np.frombuffer(C.string_at(so, 3 * n * C.sizeof(C.c_size_t)), dtype=np.uint64) if n else []
@@ -166,15 +179,21 @@ class Engine:
 class Batch:
     """Pairs resident in HBM (dpx_batch): upload once, run any number of times, fetch."""
 
-    def __init__(self, eng: Engine, sequences: np.ndarray, pairs: np.ndarray):
+    def __init__(self, eng: Engine, sequences, pairs, image: bytes | None = None):
         self.eng = eng
+        self.h = C.c_void_p()
+        self.params = None
+        if image is not None:
+            info = _lib.InputInfo()
+            _check(eng.L.dpx_batch_upload_image(eng.ctx, image, len(image), C.byref(self.h), C.byref(info)), eng.ctx)
+            self.n = info.numPairs
+            self.info = {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_}
+            return
         self.n = len(pairs)
         self._seq = np.ascontiguousarray(sequences, dtype=np.uint8)
         self._pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
-        self.h = C.c_void_p()
         _check(eng.L.dpx_batch_upload(eng.ctx, self._seq.ctypes.data, self._seq.size, self._pairs.ctypes.data, self.n,
                                       C.byref(self.h)), eng.ctx)
-        self.params = None
 
     def run(self, params: _lib.Params):
         self.params = params

@@ -13,6 +13,8 @@
 #include <unordered_map>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 
 #include "common.cuh"
 #include "dpx_ops.cuh"
@@ -1209,6 +1211,104 @@ int dpx_batch_upload(dpx_ctx* ctx, const char* sequences, size_t n_bytes, const 
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
     return batch_create(ctx, ctx->stream, 0, sequences, 0, (long long)n_bytes, pairs, n_pairs, out);
+}
+
+// ---- file-level entry points: the parser runs on the device ------------------------------------------
+static void fill_input_info(const dpx_batch* b, size_t n_bytes, dpx_input_info* info) {
+    if (!info) return;
+    dpx_input_info in{};
+    in.numPairs = b->n_pairs; in.numBytes = n_bytes;
+    if (b->n_pairs) {
+        in.numCells = (size_t)b->info.cells;
+        in.maxReferenceLength = (size_t)b->max_r; in.maxQueryLength = (size_t)b->max_q;
+        in.minReferenceLength = (size_t)b->min_r; in.minQueryLength = (size_t)b->min_q;
+        in.avgReferenceLength = (double)b->info.sum_r / (double)b->n_pairs; in.avgQueryLength = (double)b->info.sum_q / (double)b->n_pairs;
+    } else { in.minReferenceLength = SIZE_MAX; in.minQueryLength = SIZE_MAX; }
+    *info = in;
+}
+
+int dpx_batch_upload_image(dpx_ctx* ctx, const char* image, size_t n_bytes, dpx_batch** out, dpx_input_info* info) {
+    if (!ctx || !out || (!image && n_bytes) || n_bytes >= 0x7fffffffull) return DPX_ERR_INVALID;
+    *out = nullptr;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    dpx_batch* b = new dpx_batch();
+    b->ctx = ctx; b->stream = st; b->lane = 0; b->byte_lo = 0; b->byte_hi = (long long)n_bytes;
+    int* d_nl = nullptr; int* d_count = nullptr; void* tmp = nullptr;
+    auto fail = [&](int s) { cudaStreamSynchronize(st); ctx->pool.release(d_nl); ctx->pool.release(d_count); ctx->pool.release(tmp); batch_release(b); return s; };
+#define CUI_(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail(e__ == cudaErrorMemoryAllocation ? DPX_ERR_NOMEM : DPX_ERR_CUDA); } } while (0)
+    if (!pool_alloc(ctx, &b->d_blob_alloc, n_bytes + 16)) return fail(DPX_ERR_NOMEM);
+    b->d_blob = b->d_blob_alloc;
+    CUI_(cudaEventCreate(&b->ev_begin)); CUI_(cudaEventCreate(&b->ev_end));
+    int n_lines = 0;
+    if (n_bytes) {
+        CUI_(cudaMemcpyAsync(b->d_blob_alloc, image, n_bytes, cudaMemcpyHostToDevice, st));
+        // pass 1 counts the newlines (so the position list is sized exactly), pass 2 lists them
+        if (!pool_alloc(ctx, &d_count, 1)) return fail(DPX_ERR_NOMEM);
+        CUI_(cudaMemsetAsync(d_count, 0, sizeof(int), st));
+        count_newlines_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_blob_alloc, (long long)n_bytes, d_count);
+        CUI_(cudaGetLastError());
+        CUI_(cudaMemcpyAsync(&n_lines, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUI_(cudaStreamSynchronize(st));
+        if (n_lines % 3 != 0) return fail(DPX_ERR_FORMAT);                // parseInput.cpp:38-41
+        if (!pool_alloc(ctx, &d_nl, (size_t)n_lines + 2)) return fail(DPX_ERR_NOMEM);
+        size_t tmp_bytes = 0;
+        cub::CountingInputIterator<int> idx(0);
+        cub::DeviceSelect::If(nullptr, tmp_bytes, idx, d_nl, d_count, (int)n_bytes, IsNewline{b->d_blob_alloc}, st);
+        tmp = ctx->pool.alloc(tmp_bytes);
+        if (!tmp) return fail(DPX_ERR_NOMEM);
+        CUI_(cub::DeviceSelect::If(tmp, tmp_bytes, idx, d_nl, d_count, (int)n_bytes, IsNewline{b->d_blob_alloc}, st));
+    }
+    const size_t n_pairs = std::min<size_t>((size_t)n_lines / 3, 10000000); // INPUT_CAP, parseInput.cpp:7,102-105
+    b->n_pairs = n_pairs;
+    if (!pool_alloc(ctx, &b->d_pairs, n_pairs) || !pool_alloc(ctx, &b->d_scores, n_pairs) || !pool_alloc(ctx, &b->d_end_rc, 2 * n_pairs)) return fail(DPX_ERR_NOMEM);
+    if (n_pairs) {
+        pairs_from_newlines_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(d_nl, (int)n_pairs, b->d_pairs);
+        CUI_(cudaGetLastError());
+        if (!pool_alloc(ctx, &b->d_info, 1) || !pool_alloc(ctx, &b->d_pk_off, n_pairs + 1) || !pool_alloc(ctx, &b->d_str_len, n_pairs + 1)) return fail(DPX_ERR_NOMEM);
+        CUI_(cudaMemsetAsync(b->d_info, 0, sizeof(BatchInfo), st));
+        const int pblocks = (int)std::min<size_t>((n_pairs + 7) / 8, (size_t)ctx->sm_count * 8);
+        prep_kernel<<<pblocks, 256, 0, st>>>(b->d_blob, 0, (long long)n_bytes, b->d_pairs, (int)n_pairs, b->d_info, b->d_pk_off, b->d_str_len);
+        CUI_(cudaGetLastError());
+        CUI_(cudaMemcpyAsync(ctx->h_info[0], b->d_info, sizeof(BatchInfo), cudaMemcpyDeviceToHost, st));
+    }
+#undef CUI_
+    ctx->pool.release(d_count); ctx->pool.release(tmp); d_count = nullptr; tmp = nullptr;
+    int* keep_nl = d_nl; d_nl = nullptr;
+    int s = batch_finish(b);                     // waits for the stream, ranks the alphabet, packs; releases b on failure
+    ctx->pool.release(keep_nl);
+    if (s) return s;
+    fill_input_info(b, n_bytes, info);
+    *out = b;
+    return DPX_OK;
+}
+
+int dpx_align_file_text(dpx_ctx* ctx, const dpx_params* params, const char* path, long long first_index,
+                        char** text, size_t* text_bytes, dpx_input_info* info) {
+    if (!ctx || !params || !path || !text || !text_bytes) return DPX_ERR_INVALID;
+    *text = nullptr; *text_bytes = 0;
+    FILE* f = fopen(path, "rb");
+    if (!f) return DPX_ERR_IO;
+    if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return DPX_ERR_IO; }
+    const long sz = ftell(f);
+    if (sz < 0) { fclose(f); return DPX_ERR_IO; }
+    rewind(f);
+    char* img = (char*)g_host.take((size_t)sz + 1);               // page-locked: the upload runs at PCIe speed
+    const bool pinned = img != nullptr;
+    if (!img) img = (char*)malloc((size_t)sz + 1);
+    if (!img) { fclose(f); return DPX_ERR_NOMEM; }
+    const size_t got = fread(img, 1, (size_t)sz, f);
+    fclose(f);
+    auto drop = [&]() { if (pinned) g_host.give_back(img); else free(img); };
+    if (got != (size_t)sz) { drop(); return DPX_ERR_IO; }
+    dpx_batch* b = nullptr;
+    int st = dpx_batch_upload_image(ctx, img, got, &b, info);
+    drop();
+    if (st) return st;
+    st = dpx_batch_run(b, params);
+    if (!st) st = dpx_batch_fetch_text(b, first_index, text, text_bytes);
+    dpx_batch_free(b);
+    return st;
 }
 
 int dpx_batch_run(dpx_batch* b, const dpx_params* p) {

@@ -26,22 +26,23 @@ struct BatchInfo {
     unsigned long long str_bytes;          // sum 3*(Q+R+1)
     int invalid;
     int pad;
+    unsigned long long sum_r, sum_q;       // sum of reference / query lengths (inputInfo averages)
 };
 
 __global__ void __launch_bounds__(256) prep_kernel(const uint8_t* __restrict__ blob, long long byte_lo, long long byte_hi,
                                                    const dpx_seq_pair* __restrict__ pairs, int n_pairs, BatchInfo* __restrict__ info,
                                                    unsigned long long* __restrict__ pk_words, unsigned long long* __restrict__ str_len) {
     __shared__ uint32_t sh[8];
-    __shared__ unsigned long long sh_cells, sh_words, sh_str;
+    __shared__ unsigned long long sh_cells, sh_words, sh_str, sh_sumr, sh_sumq;
     __shared__ int sh_maxr, sh_maxq, sh_minr, sh_minq, sh_bad;
     if (threadIdx.x < 8) sh[threadIdx.x] = 0;
-    if (threadIdx.x == 0) { sh_cells = 0; sh_words = 0; sh_str = 0; sh_maxr = 0; sh_maxq = 0; sh_minr = 0; sh_minq = 0; sh_bad = 0; }
+    if (threadIdx.x == 0) { sh_cells = 0; sh_words = 0; sh_str = 0; sh_sumr = 0; sh_sumq = 0; sh_maxr = 0; sh_maxq = 0; sh_minr = 0; sh_minq = 0; sh_bad = 0; }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     uint32_t loc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    unsigned long long cells = 0, words = 0, strb = 0;
+    unsigned long long cells = 0, words = 0, strb = 0, sumr = 0, sumq = 0;
     int maxr = 0, maxq = 0, minr = 0, minq = 0, bad = 0;
     for (int p = warp; p < n_pairs; p += nwarps) {
         const dpx_seq_pair pr = pairs[p];
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const uint8_t* __restrict__ b
             if (pk_words) pk_words[p] = w;
             if (str_len) str_len[p] = sl;
             cells += (unsigned long long)pr.referenceSize * (unsigned long long)pr.querySize; words += w; strb += sl;
+            sumr += (unsigned long long)pr.referenceSize; sumq += (unsigned long long)pr.querySize;
             maxr = max(maxr, pr.referenceSize); maxq = max(maxq, pr.querySize);
             minr = max(minr, 0x7fffffff - pr.referenceSize); minq = max(minq, 0x7fffffff - pr.querySize);
         }
@@ -67,13 +69,14 @@ __global__ void __launch_bounds__(256) prep_kernel(const uint8_t* __restrict__ b
     }
     if (__any_sync(0xffffffffu, bad)) { if (lane == 0) atomicOr(&sh_bad, 1); }
     if (lane == 0) {
-        atomicAdd(&sh_cells, cells); atomicAdd(&sh_words, words); atomicAdd(&sh_str, strb);
+        atomicAdd(&sh_cells, cells); atomicAdd(&sh_words, words); atomicAdd(&sh_str, strb); atomicAdd(&sh_sumr, sumr); atomicAdd(&sh_sumq, sumq);
         atomicMax(&sh_maxr, maxr); atomicMax(&sh_maxq, maxq); atomicMax(&sh_minr, minr); atomicMax(&sh_minq, minq);
     }
     __syncthreads();
     if (threadIdx.x < 8 && sh[threadIdx.x]) atomicOr(&info->present[threadIdx.x], sh[threadIdx.x]);
     if (threadIdx.x == 0) {
         atomicAdd(&info->cells, sh_cells); atomicAdd(&info->packed_words, sh_words); atomicAdd(&info->str_bytes, sh_str);
+        atomicAdd(&info->sum_r, sh_sumr); atomicAdd(&info->sum_q, sh_sumq);
         atomicMax(&info->max_r, sh_maxr); atomicMax(&info->max_q, sh_maxq);
         atomicMax(&info->min_r_inv, sh_minr); atomicMax(&info->min_q_inv, sh_minq);
         if (sh_bad) atomicOr(&info->invalid, 1);
@@ -101,6 +104,31 @@ __global__ void __launch_bounds__(256) present_kernel(const uint8_t* __restrict_
     }
     __syncthreads();
     if (threadIdx.x < 8 && sh[threadIdx.x]) atomicOr(&present[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ---- parser on the device (replaces the byte loop of c++/parseInput.cpp:78-113) ---------------------------------------
+// The file image is uploaded as is; a stream compaction lists the newline positions, three consecutive newlines make a pair:
+//   header \n REF \n QRY \n    ->  referenceIdx = nl[3k] + 1, referenceSize = nl[3k+1] - referenceIdx, queryIdx = nl[3k+1] + 1, ...
+struct IsNewline {
+    const uint8_t* blob;
+    __device__ __forceinline__ bool operator()(int i) const { return blob[i] == (uint8_t)'\n'; }
+};
+
+__global__ void __launch_bounds__(256) count_newlines_kernel(const uint8_t* __restrict__ blob, long long n, int* __restrict__ count) {
+    int c = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) c += (blob[i] == (uint8_t)'\n');
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+__global__ void __launch_bounds__(256) pairs_from_newlines_kernel(const int* __restrict__ nl, int n_pairs, dpx_seq_pair* __restrict__ pairs) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const int h = nl[3 * k], r = nl[3 * k + 1], q = nl[3 * k + 2];
+    dpx_seq_pair p;
+    p.referenceIdx = h + 1; p.referenceSize = r - (h + 1);
+    p.queryIdx = r + 1;     p.querySize = q - (r + 1);
+    pairs[k] = p;
 }
 
 struct PackLut { uint8_t code[256]; };

@@ -43,20 +43,18 @@ int main(int argc, char* argv[]) {
     if (!pairFileName) { fprintf(stderr, "missing -pairs <InSeqFile>\n"); exit(EXIT_FAILURE); }
 
     printf("Parsing input file: %s\n", pairFileName);
-    seqPair* sequenceIdxs; char* sequences;
-    inputInfo fileInfo = parseInput(pairFileName, sequenceIdxs, sequences);
-
     const auto t0 = std::chrono::steady_clock::now();
     printf("Pair # | Score\n");
 
+    // The file goes to the GPU as is: parser (newline scan, seqPair index, 2-bit pack), alignment, backtrack and the formatting of
+    // the stdout blocks all run on the device; one text buffer comes back (reference: parseInput + the per-pair loop, main.cpp:157-252).
     dpx_params p = dpxhost::make_params(algo, matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight, band);
     if (scores_only) p.flags = DPX_OUT_SCORE | DPX_OUT_END_COORDS;
-    const size_t n = fileInfo.numPairs;
-    // the whole stdout block of the batch is formatted on the GPU and comes back as one buffer
     char* text = nullptr; size_t text_bytes = 0;
     dpx_ctx* ctx = dpxhost::engine();
-    const int st = dpx_align_batch_text(ctx, &p, sequences, fileInfo.numBytes, reinterpret_cast<const dpx_seq_pair*>(sequenceIdxs), n,
-                                        0, nullptr, nullptr, &text, &text_bytes);
+    const int st = dpx_align_file_text(ctx, &p, pairFileName, 0, &text, &text_bytes, nullptr);
+    if (st == DPX_ERR_IO) { fprintf(stderr, "Could not open file: %s\n", pairFileName); exit(1); }                      // parseInput.cpp:12-15
+    if (st == DPX_ERR_FORMAT) { fprintf(stderr, "Number of lines not a multiple of 3: %s\n", pairFileName); exit(1); }  // :38-41
     if (st != DPX_OK) { fprintf(stderr, "dpxalign: %s (%s)\n", dpx_strerror(st), dpx_last_error(ctx)); exit(1); }
     fwrite(text, 1, text_bytes, stdout);
     dpx_free(text);
@@ -64,6 +62,5 @@ int main(int argc, char* argv[]) {
     const long long usec = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
     printf("Elapsed time (usec): %lld\n", usec);
     printf("Cleaning up\n");
-    cleanupParsedFile(sequenceIdxs, sequences);
     return 0;
 }

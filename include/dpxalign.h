@@ -151,6 +151,16 @@ int         dpx_align_batch_text(dpx_ctx* ctx, const dpx_params* params,
                                  const dpx_seq_pair* pairs, size_t n_pairs, long long first_index,
                                  int32_t* scores, int32_t* end_row_col, char** text, size_t* text_bytes);
 
+/* ---- parser on the GPU: replaces the two fread passes + byte loop of c++/parseInput.cpp:17-113.
+ * dpx_batch_upload_image takes the FILE IMAGE (repeated "header\nREF\nQRY\n", newlines still in place): the newline scan, the
+ * seqPair index, the alphabet scan and the 2-bit pack all run on the device; the batch then behaves like one made by
+ * dpx_batch_upload (run / fetch / fetch_text).  DPX_ERR_FORMAT when the number of lines is not a multiple of 3
+ * (parseInput.cpp:38-41); at most 10 000 000 pairs are taken (INPUT_CAP, :7,102-105).  info may be NULL.
+ * dpx_align_file_text = read the file + upload_image + run + fetch_text: what the drop-in driver does for a whole input file. */
+int         dpx_batch_upload_image(dpx_ctx* ctx, const char* file_image, size_t n_bytes, dpx_batch** out, dpx_input_info* info);
+int         dpx_align_file_text(dpx_ctx* ctx, const dpx_params* params, const char* path, long long first_index,
+                                char** text, size_t* text_bytes, dpx_input_info* info);
+
 /* Statistics of the last dpx_batch_run on this batch (after dpx_batch_sync). */
 typedef struct {
     double   fill_ms;          /* CUDA-event time of the fill kernel(s) */

@@ -320,3 +320,32 @@ def test_gpu_formatted_text_golden(eng):
         want = open(os.path.join(GOLD, f"adversarial.{NAMES[algo]}.out.txt"), "rb").read()
         assert eng.align_batch_text(api.make_params(algo, flags=ALL, **KW[algo]), p.sequences, p.pairs) == want
     assert eng.align_batch_text(api.make_params(api.LNW, flags=ALL), np.zeros(0, np.uint8), np.zeros(0, api.PAIR_DTYPE)) == b""
+
+
+def test_device_parser_matches_host_parser(eng, tmp_path):
+    """dpx_batch_upload_image / dpx_align_file_text: newline scan + seqPair index + pack on the GPU give the same batch as
+    parseInput + dpx_batch_upload (c++/parseInput.cpp:78-113), including inputInfo and the format error."""
+    for name in ("adversarial", "cfg1_small", "mid", "shapes"):
+        path = os.path.join(GOLD, f"{name}.in.txt")
+        img = open(path, "rb").read()
+        p = api.parse_input(path)
+        for algo in (api.LNW, api.LSW, api.ANW):
+            want = eng.align_batch(api.make_params(algo, flags=ALL, **KW[algo]), p.sequences, p.pairs).text()
+            b = eng.upload_image(img)
+            assert b.n == len(p.pairs)
+            for k in ("numPairs", "numBytes", "numCells", "minReferenceLength", "maxReferenceLength", "minQueryLength", "maxQueryLength"):
+                assert b.info[k] == p.info[k], k
+            assert abs(b.info["avgReferenceLength"] - p.info["avgReferenceLength"]) < 1e-9
+            b.run(api.make_params(algo, flags=ALL, **KW[algo])); b.sync()
+            assert b.fetch().text() == want
+            b.free()
+            text, info = eng.align_file_text(api.make_params(algo, flags=ALL, **KW[algo]), path)
+            assert text == want and info["numPairs"] == len(p.pairs)
+    bad = tmp_path / "bad.txt"
+    bad.write_bytes(b"0\n0123\n0123\n1\n0123\n")
+    with pytest.raises(api.DpxError) as e:
+        eng.align_file_text(api.make_params(api.LNW, flags=ALL), str(bad))
+    assert e.value.status == -6
+    empty = tmp_path / "empty.txt"
+    empty.write_bytes(b"")
+    assert eng.align_file_text(api.make_params(api.LNW, flags=ALL), str(empty))[0] == b""

@@ -512,7 +512,7 @@ template <int G, int K>
 static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xormode) {
     const int gpb = 128 / G;
     a.bnd_stride = b->max_r + G + 2;
-    a.rsel_stride = (b->max_r + 2 * G + 2 + 1) & ~1;
+    a.rsel_stride = (b->max_r + 2 * G + 18 + 1) & ~1;          // the table is written 16 entries (one packed word) at a time
     const size_t smem = (size_t)gpb * ((size_t)a.bnd_stride * 4 + (size_t)a.rsel_stride * 2);
     auto launch = [&](auto kern) -> int {
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

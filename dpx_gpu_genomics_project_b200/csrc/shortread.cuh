@@ -70,6 +70,12 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t b
     return d;
 }
 
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {       // PTX shl clamps the amount: n >= 32 gives 0
+    uint32_t d;
+    asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t get2(const uint32_t* __restrict__ w, int k) { return (w[k >> 4] >> (2 * (k & 15))) & 3u; }
 
 template <int G, int K, bool TRACK, bool XORMODE>
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
     uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride;
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(sr_smem + (size_t)GPB * a.bnd_stride) + (size_t)gib * a.rsel_stride;
     const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, one = a.one;
-    const uint32_t ms1 = a.ms_byte, xs4 = a.xs_byte * 0x01010101u;
+    const uint32_t xs4 = a.xs_byte * 0x01010101u, dms = (a.ms_byte ^ a.xs_byte) & 0xffu;      // xor: no byte carries, any signs
     const int kmask = (1 << a.kbits) - 1;             // all position bits of an int16 key
     const int smask = (1 << (a.kbits - 1)) - 1;       // step-code bits (the bit above them marks the upper row of a pair)
     const uint32_t kmul = a.kmul;
@@ -115,18 +121,21 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
 
         // ---- per-group column table: entry e <-> column j = e - (G-1); pads never match ---------------
         __syncwarp();
-        for (int e = gl; e < Rw + 2 * G + 2; e += G) {
-            const int j = e - (G - 1);
-            // ADD mode: c = 3 - r (pad 4); q + c == 3 iff match; sums stay <= 8 (8 -> sign-replicate of byte 0 = 0,
-            //   only where row AND column are pads); every table byte is >= 0 so the high byte is the constant
-            //   selector 8 (sign of byte 0) and no nibble can carry into the other pair's half.
-            // XOR mode: r (pad 5) with the sign-replicating copy r|8 in the odd nibbles; q ^ r == 0 iff match.
-            // selector of the per-row score tables (below): nibble 0 = reference base of pair A (bytes 0..3 of the row's table
-            // pair), nibble 2 = 4 + base of pair B (bytes 4..7); nibbles 1 / 3 = the same index | 8 = "replicate that byte's
-            // sign", i.e. the int16 sign extension.  Pad columns select the sign of byte 0 / 4: 0 or -1, below any real score.
-            const uint32_t nA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 8u;
-            const uint32_t nB = (j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
-            rsel[e] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
+        // selector of the per-row score tables (below): nibble 0 = reference base of pair A (bytes 0..3 of the row's table pair),
+        // nibble 2 = 4 + base of pair B (bytes 4..7); nibbles 1 / 3 = the same index | 8 = "replicate that byte's sign", i.e. the
+        // int16 sign extension.  Pad columns select the sign of byte 0 / 4: 0 or -1, below any real score.
+        // Built one packed word (16 bases) per lane at a time: base k of the reference is entry e = k + G.
+        for (int e = gl; e < G; e += G) rsel[e] = (uint16_t)0xcc88u;                       // columns j <= 0
+        for (int c = gl; 16 * c < Rw + G + 2; c += G) {
+            const int k0 = 16 * c;
+            const uint32_t wA = (k0 < RA) ? refA[c] : 0u, wB = (k0 < RB) ? refB[c] : 0u;
+            const int nvA = RA - k0, nvB = RB - k0;                                         // bases of this word that exist
+            #pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const uint32_t nA = (t < nvA) ? ((wA >> (2 * t)) & 3u) : 8u;
+                const uint32_t nB = (t < nvB) ? (4u + ((wB >> (2 * t)) & 3u)) : 12u;
+                rsel[k0 + t + G] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
+            }
         }
         if (passes > 1)
             for (int e = gl; e < Rw + G + 2; e += G) bnd[e] = Bg2;
@@ -143,8 +152,8 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                 const int i = i0 + r;                            // 0-based query index
                 const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
                 const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
-                ta[r] = (qa < 4u) ? ((xs4 & ~(0xffu << (8 * qa))) | (ms1 << (8 * qa))) : xs4;
-                tb[r] = (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
+                ta[r] = xs4 ^ shl_clamp(dms, (qa < 4u) ? 8u * qa : 32u);
+                tb[r] = xs4 ^ shl_clamp(dms, (qb < 4u) ? 8u * qb : 32u);
                 hgA[r] = Bg2; hgB[r] = Bg2;
             }
             #pragma unroll

@@ -170,6 +170,39 @@ def mutated_blob_pairs(n_pairs: int, R: int, Q: int, seed: int, sub: float, ins:
     return img, pairs
 
 
+def ragged_mutated_blob_pairs(n_pairs: int, r_lo: int, r_hi: int, seed: int, sub: float, ins: float, dele: float, alphabet: bytes = b"0123"):
+    """BASELINE config 1 substitute: references of length U[r_lo, r_hi], queries = the reference mutated
+    (per-base substitution / insertion / deletion), in parseInput's output form.  Vectorised over the whole batch: every pair is
+    generated at the maximum length and cut to its own."""
+    a = np.frombuffer(alphabet, dtype=np.uint8)
+    rng = Rng(seed)
+    R = r_lo + rng.below(n_pairs, r_hi - r_lo + 1)
+    Rm = int(R.max())
+    Qm = Rm + Rm // 4 + 8
+    ref = a[rng.below(n_pairs * Rm, len(a))].reshape(n_pairs, Rm)
+    u = rng.uniform(n_pairs * Qm).reshape(n_pairs, Qm)
+    step = np.ones((n_pairs, Qm), dtype=np.int64)
+    step[u < ins] = 0
+    step[(u >= ins) & (u < ins + dele)] = 2
+    src = np.cumsum(step, axis=1) - 1                       # reference index each query base copies (insertions repeat it)
+    rnd = a[rng.below(n_pairs * Qm, len(a))].reshape(n_pairs, Qm)
+    subm = rng.uniform(n_pairs * Qm).reshape(n_pairs, Qm) < sub
+    qry = np.where((step > 0) & ~subm, np.take_along_axis(ref, np.clip(src, 0, Rm - 1), axis=1), rnd)
+    Q = np.maximum(1, (src < R[:, None]).sum(axis=1))       # the query ends where the walk leaves the reference
+    rec = 2 + R + 1 + Q + 1
+    off = np.zeros(n_pairs + 1, dtype=np.int64); np.cumsum(rec, out=off[1:])
+    blob = np.zeros(int(off[-1]), dtype=np.uint8)
+    blob[off[:-1]] = ord("0")
+    pairs = np.zeros(n_pairs, dtype=[("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
+    pairs["referenceIdx"] = off[:-1] + 2; pairs["referenceSize"] = R
+    pairs["queryIdx"] = off[:-1] + 3 + R; pairs["querySize"] = Q
+    col_r = np.arange(Rm)[None, :]; col_q = np.arange(Qm)[None, :]
+    mr = col_r < R[:, None]; mq = col_q < Q[:, None]
+    blob[(pairs["referenceIdx"][:, None] + col_r)[mr]] = ref[mr]
+    blob[(pairs["queryIdx"][:, None] + col_q)[mq]] = qry[mq]
+    return blob, pairs
+
+
 def blob_to_file_bytes(blob: np.ndarray) -> np.ndarray:
     """Inverse of the parser's newline->NUL rewrite for generator-made blobs (no NUL inside sequences)."""
     out = blob.copy()

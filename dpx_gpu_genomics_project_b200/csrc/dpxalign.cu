@@ -584,7 +584,7 @@ static int ensure_str_off(dpx_batch* b) {
 
 
 // ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
-struct PwPlan { int K; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
+struct PwPlan { int K; bool packed; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
 
 static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
     const bool sw = p->algo == DPX_ALGO_LSW;
@@ -607,14 +607,17 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
     const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
     const long long B = -4 * lo + margin;
-    if (4 * hi + B + 16 > 32767) return false;
-    pl->K = K;
+    const bool packed = 4 * hi + B + 16 <= 32767 && !getenv("DPX_PAIRWF_INT32");     // else one pair per warp in int32
+    if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
+    pl->K = K; pl->packed = packed;
     pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
-    auto pk = [](long long v) { return (uint32_t)(v & 0xffff) * 0x00010001u; };
+    auto pk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; };
+    // add constants: packed halves need the always-carry compensation (high half pre-decremented), int32 takes the value itself
+    auto addk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) | ((uint32_t)((v - 1) & 0xffff) << 16) : (uint32_t)v; };
     pl->ext2 = aff ? pk(4 * ge) : pk(1);
     const long long c = aff ? 4 * open : 4 * open - 2;           // (h' | 3) + c -> code 3 (Gotoh) / code 1 (linear)
-    pl->addc = (uint32_t)(c & 0xffff) | ((uint32_t)((c - 1) & 0xffff) << 16);
-    pl->addc3 = (uint32_t)((c + 3) & 0xffff) | ((uint32_t)((c + 2) & 0xffff) << 16);
+    pl->addc = addk(c);
+    pl->addc3 = addk(c + 3);
     pl->zero2 = pk(B + 3);
     pl->b0 = (int)(4 * open + B + code);
     pl->b1 = aff ? (int)(4 * (go + open) + B + code) : pl->b0;
@@ -623,9 +626,9 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     return true;
 }
 
-template <int ALGO, bool TB>
-static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
-    auto kern = pw_nw_kernel<ALGO, TB, 8>;
+template <int ALGO, bool TB, bool PACKED, bool GBND>
+static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
+    auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
@@ -634,6 +637,11 @@ static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t 
     kern<<<blocks, 128, smem, st>>>(a);
     CU(cudaGetLastError());
     return DPX_OK;
+}
+template <int ALGO, bool TB>
+static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots, bool packed) {
+    if (a.bnd_global) return packed ? launch_pairwf_w<ALGO, TB, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, true>(ctx, st, a, smem, n_slots);
+    return packed ? launch_pairwf_w<ALGO, TB, true, false>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false>(ctx, st, a, smem, n_slots);
 }
 
 
@@ -771,17 +779,18 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             // the fill kernel of chunk c+1 writes the other buffer (the walk is latency-bound and leaves the issue slots to the fill).
             size_t per_chunk = n; int nbuf = 1;
             if (want_strings) {
-                const size_t slots_total = (n + 1) / 2;
+                const size_t ppw = pl.packed ? 2 : 1;                                    // pairs per warp
+                const size_t slots_total = (n + ppw - 1) / ppw;
                 const size_t max_slots = std::max<size_t>(1, (ctx->tb_budget_bytes / 2 / 4) / std::max<unsigned long long>(tbs, 1));
                 size_t nchunks = (slots_total + max_slots - 1) / max_slots;
                 if (!getenv("DPX_SERIAL_CHUNKS"))                                               // (set by bench.py to time the fill kernel alone)
                     nchunks = std::max<size_t>(nchunks, std::min<size_t>(8, n / 16384));        // >= 16k pairs per chunk: whole waves of warps
                 const size_t slots = (slots_total + nchunks - 1) / nchunks;
-                per_chunk = 2 * slots; nbuf = (nchunks > 1 && !getenv("DPX_SERIAL_CHUNKS")) ? 2 : 1;
+                per_chunk = ppw * slots; nbuf = (nchunks > 1 && !getenv("DPX_SERIAL_CHUNKS")) ? 2 : 1;
                 const size_t need = (size_t)nbuf * slots * (size_t)tbs;
                 if (b->d_tb && b->tb_words < need) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
                 if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, need)) return DPX_ERR_NOMEM; b->tb_words = need; }
-                b->stats.traceback_bytes = (uint64_t)((n + 1) / 2) * tbs * 4;
+                b->stats.traceback_bytes = (uint64_t)slots_total * tbs * 4;
             }
             // streams of the chunk pipeline: fills alternate between the batch stream and a second one (the tail of one fill
             // overlaps the head of the next), walks run on a third
@@ -802,24 +811,34 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
             a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
             a.bnd_stride = b->max_r + 36; a.rsel_stride = (b->max_r + 68) & ~1;
-            const size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
-            b->stats.kernel_id = DPX_KERNEL_PAIR_S16X2;
+            size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
+            if (smem > 44 * 1024) {
+                // long references: the boundary rows would leave fewer than 5 blocks per SM; keep them in a per-warp global buffer
+                const size_t warps = (size_t)ctx->sm_count * 16 * 4, need = warps * (size_t)a.bnd_stride * (aff ? 2 : 1);
+                if (ctx->boundary_ints[b->lane] < need) {
+                    if (ctx->boundary[b->lane]) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->boundary[b->lane]); ctx->boundary[b->lane] = nullptr; ctx->boundary_ints[b->lane] = 0; }
+                    CU(cudaMalloc(&ctx->boundary[b->lane], need * sizeof(int32_t))); ctx->boundary_ints[b->lane] = need;
+                }
+                a.bnd_global = reinterpret_cast<uint32_t*>(ctx->boundary[b->lane]);
+                smem = (size_t)4 * a.rsel_stride * 2;
+            }
+            b->stats.kernel_id = pl.packed ? DPX_KERNEL_PAIR_S16X2 : DPX_KERNEL_PAIR_S32;
             int c = 0;
             for (size_t first = 0; first < n; first += per_chunk, ++c) {
                 a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
                 a.counter = counters + (c % 64);
-                a.tb = want_strings ? b->d_tb + (size_t)(c % nbuf) * (per_chunk / 2) * (size_t)tbs : nullptr;
+                a.tb = want_strings ? b->d_tb + (size_t)(c % nbuf) * (per_chunk / (pl.packed ? 2 : 1)) * (size_t)tbs : nullptr;
                 cudaStream_t fst = (c & 1) ? fill2_st : st;
                 if (nbuf > 1 && c >= nbuf) CU(cudaStreamWaitEvent(fst, bt_done[c - nbuf], 0));     // the buffer's previous walk is over
                 CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), fst));
                 cudaEvent_t s, e;
                 { int r = add_event_pair(0, &s, &e); if (r) return r; }
                 CU(cudaEventRecord(s, fst));
-                const int n_slots = (a.count + 1) / 2;
+                const int n_slots = pl.packed ? (a.count + 1) / 2 : a.count;
                 int r;
-                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, fst, a, smem, n_slots);
-                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots);
-                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, fst, a, smem, n_slots) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, fst, a, smem, n_slots);
+                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, fst, a, smem, n_slots, pl.packed);
+                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots, pl.packed);
+                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, fst, a, smem, n_slots, pl.packed);
                 if (r) return r;
                 CU(cudaEventRecord(e, fst));
                 b->stats.kernel_launches++;
@@ -838,9 +857,15 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, bt_st));
                     const int bt_blocks = (a.count + 127) / 128;
-                    if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
-                    else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
-                    else     pw_bt_kernel<DPX_ALGO_LNW, 8><<<bt_blocks, 128, 0, bt_st>>>(t);
+                    if (pl.packed) {
+                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
+                    } else {
+                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
+                    }
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, bt_st));
                     b->stats.kernel_launches++;

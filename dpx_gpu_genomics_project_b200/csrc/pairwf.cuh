@@ -78,6 +78,7 @@ struct PwArgs {
     unsigned long long tb_stride;        // words per slot
     unsigned int* counter;
     int bnd_stride, rsel_stride;         // per-warp shared-memory strides (uint32 / uint16 entries)
+    uint32_t* bnd_global;                // null: boundary rows live in shared memory
 };
 
 __device__ __forceinline__ uint32_t fma_mul(uint32_t a, uint32_t m) {
@@ -103,10 +104,25 @@ __device__ __forceinline__ uint32_t vibmax_s16x2_safe(uint32_t a, uint32_t b, bo
     *ge_hi = (bool)phi; *ge_lo = (bool)plo;
     return val;
 }
-__device__ __forceinline__ uint32_t pw_pack(int v) { return (uint32_t)(v & 0xffff) * 0x00010001u; }
 
-template <int ALGO, bool TB, int K>
+// One kernel source for both arithmetic widths: PACKED = two pairs per warp in int16x2 halves, !PACKED = one pair in int32
+// (same recurrences, codes and traceback layout with the upper half of every word unused; for scores beyond the int16 budget).
+template <bool P> __device__ __forceinline__ uint32_t pw_addmax(uint32_t a, uint32_t b, uint32_t c) {
+    return P ? __viaddmax_s16x2(a, b, c) : (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);
+}
+template <bool P> __device__ __forceinline__ uint32_t pw_max3(uint32_t a, uint32_t b, uint32_t c) {
+    return P ? __vimax3_s16x2(a, b, c) : (uint32_t)__vimax3_s32((int)a, (int)b, (int)c);
+}
+template <bool P> __device__ __forceinline__ uint32_t pw_bmax(uint32_t a, uint32_t b, bool* ge_hi, bool* ge_lo) {
+    if (P) return vibmax_s16x2_safe(a, b, ge_hi, ge_lo);
+    *ge_hi = true; *ge_lo = (int)a >= (int)b;
+    return (uint32_t)max((int)a, (int)b);
+}
+template <bool P> __device__ __forceinline__ uint32_t pw_val(int v) { return P ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; }
+
+template <int ALGO, bool TB, int K, bool PACKED, bool GBND>
 __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
+    constexpr uint32_t REP1 = PACKED ? 0x00010001u : 1u, REP2 = 2u * REP1, REP3 = 3u * REP1;   // a small constant in every lane of a register
     extern __shared__ uint32_t pw_smem[];
     constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
     constexpr bool SW = (ALGO == DPX_ALGO_LSW);
@@ -116,13 +132,16 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
     static_assert(K % CPH == 0, "K must fill whole traceback words");
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    uint32_t* __restrict__ bndH = pw_smem + (size_t)wib * a.bnd_stride * (AFF ? 2 : 1);
+    // pass-to-pass boundary rows: shared memory while they leave room for >= 5 blocks per SM, else a per-warp global buffer (L2)
+    // (GBND is a template flag so that the common case keeps provably-shared pointers: LDS / STS, not generic loads)
+    uint32_t* __restrict__ bndH = GBND ? a.bnd_global + ((size_t)blockIdx.x * 4 + wib) * a.bnd_stride * (AFF ? 2 : 1)
+                                       : pw_smem + (size_t)wib * a.bnd_stride * (AFF ? 2 : 1);
     uint32_t* __restrict__ bndD = bndH + a.bnd_stride;
-    uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (size_t)4 * a.bnd_stride * (AFF ? 2 : 1)) + (size_t)wib * a.rsel_stride;
+    uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (GBND ? 0 : (size_t)4 * a.bnd_stride * (AFF ? 2 : 1))) + (size_t)wib * a.rsel_stride;
     const uint32_t one = a.one, ext2 = a.ext2, addc = a.addc, addc3 = a.addc3, minus1 = a.minus1, zero2 = a.zero2;
     const uint32_t ms1 = a.lut_hi & 0xffu, xs4 = (a.lut_lo & 0xffu) * 0x01010101u;     // table entries: match, mismatch
     const uint32_t two = a.two, four = a.four, eight = a.eight, sixteen = a.sixteen;
-    const int n_slots = (a.count + 1) >> 1;
+    const int n_slots = PACKED ? (a.count + 1) >> 1 : a.count;     // packed: two pairs per warp; unpacked (int32): one
     const PwGeom geo = PwGeom::make(K, CB);
 
     for (;;) {
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
         if (lane == 0) slot = (int)atomicAdd(a.counter, 1u);
         slot = __shfl_sync(FULL, slot, 0);
         if (slot >= n_slots) break;
-        const int posA = a.first + 2 * slot;
+        const int posA = a.first + (PACKED ? 2 * slot : slot);
         const int pa = a.order ? a.order[posA] : posA;
         int pb = -1, RB = 0, QB = 0;
         const dpx_seq_pair prA = a.pairs[pa];
@@ -138,7 +157,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
         const uint32_t* refA = a.packed + (a.pk_off ? a.pk_off[pa] : (unsigned long long)pa * a.pk_stride);
         const uint32_t* qryA = refA + ((RA + 15) >> 4);
         const uint32_t *refB = refA, *qryB = qryA;
-        if (2 * slot + 1 < a.count) {
+        if (PACKED && 2 * slot + 1 < a.count) {
             pb = a.order ? a.order[posA + 1] : posA + 1;
             const dpx_seq_pair prB = a.pairs[pb];
             RB = prB.referenceSize; QB = prB.querySize;
@@ -158,7 +177,8 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
             // Pad columns select the sign of byte 0 / 4 = 0: below any real entry.
             const uint32_t nA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 8u;
             const uint32_t nB = (j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
-            rsel[e] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
+            rsel[e] = PACKED ? (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12))
+                             : (uint16_t)(nA | ((nA | 8u) * 0x1110u));          // int32: one base, its sign in the three upper bytes
         }
         __syncwarp();
 
@@ -180,13 +200,13 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                 const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
                 const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
                 ta[r] = (qa < 4u) ? ((xs4 & ~(0xffu << (8 * qa))) | (ms1 << (8 * qa))) : xs4;
-                tb[r] = (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
-                hA[r] = pw_pack(a.b1 + a.bstep * (i + 1));       // column 0 border of matrix row i+1
+                tb[r] = !PACKED ? 0u : (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
+                hA[r] = pw_val<PACKED>(a.b1 + a.bstep * (i + 1));       // column 0 border of matrix row i+1
                 hB[r] = hA[r];
-                if constexpr (AFF) Ic[r] = 0x00020002u;                    // I[i][0] never wins: column 1 always opens (:201-205)
+                if constexpr (AFF) Ic[r] = REP2;                    // I[i][0] never wins: column 1 always opens (:201-205)
             }
-            uint32_t botH = hA[K - 1], botD = 0x00010001u;
-            uint32_t topprev = pw_pack(i0 == 0 ? a.b0 : a.b1 + a.bstep * i0);   // H[i0][0]: diagonal of (i0+1, 1)
+            uint32_t botH = hA[K - 1], botD = REP1;
+            uint32_t topprev = pw_val<PACKED>(i0 == 0 ? a.b0 : a.b1 + a.bstep * i0);   // H[i0][0]: diagonal of (i0+1, 1)
             const bool more = (p + 1 < passes);
             uint32_t* __restrict__ tbpp = TB ? (tbp + (size_t)p * nsteps2 * W * 32 + lane) : nullptr;
 
@@ -202,7 +222,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                     if (lane == 0) {                                                                                 \
                         /* row 0 border (D[0][j] never wins, :185-189), or the previous pass's last row; columns beyond the   \
                            duo are pads whose row was never written: give them border values so they stay in range */      \
-                        if (p == 0 || j > Rw) { topH = pw_pack(a.b1 + a.bstep * j); topD = 0x00010001u; }                \
+                        if (p == 0 || j > Rw) { topH = pw_val<PACKED>(a.b1 + a.bstep * j); topD = REP1; }                \
                         else { topH = bndH[j]; if (AFF) topD = bndD[j]; }                                            \
                     }                                                                                                \
                     const uint32_t rs = rsel[(S) - lane + 32];                                                       \
@@ -214,40 +234,40 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                         uint32_t h;                                                                                  \
                         if constexpr (AFF) {                                                                         \
                             const uint32_t ds = fma_add(diag, one, sc);                                              \
-                            const uint32_t Dn = __viaddmax_s16x2(upD, ext2, up);                                     \
-                            const uint32_t In = __viaddmax_s16x2(Ic[r], ext2, OLD[r]);                               \
-                            const uint32_t Dc = Dn & 0xFFFDFFFDu, Icn = In & 0xFFFEFFFEu;                            \
-                            h = __vimax3_s16x2(ds, Dc, Icn);                                                         \
+                            const uint32_t Dn = pw_addmax<PACKED>(upD, ext2, up);                                     \
+                            const uint32_t In = pw_addmax<PACKED>(Ic[r], ext2, OLD[r]);                               \
+                            const uint32_t Dc = Dn & ~REP2, Icn = In & ~REP1;                            \
+                            h = pw_max3<PACKED>(ds, Dc, Icn);                                                         \
                             upD = Dc; Ic[r] = Icn;                                                                   \
                             if (TB) {   /* nibble = dir + 4 * (D opened) + 8 * (I opened): Dn - Dc = 2 * opened, In - Icn = opened */ \
-                                const uint32_t t = h & 0x00030003u;                                                  \
+                                const uint32_t t = h & REP3;                                                  \
                                 acc[r / CPH] = fma_add(acc[r / CPH], sixteen, t);                                    \
                                 acc[r / CPH] = fma_add(fma_add(Dc, minus1, Dn), two, acc[r / CPH]);                  \
                                 acc[r / CPH] = fma_add(fma_add(Icn, minus1, In), eight, acc[r / CPH]);               \
-                                NEW[r] = fma_add(h | 0x00030003u, one, addc);                                        \
+                                NEW[r] = fma_add(h | REP3, one, addc);                                        \
                             }                                                                                        \
                         } else if constexpr (SW) {                                                                   \
-                            const uint32_t m = __viaddmax_s16x2(diag, sc, OLD[r]);          /* diag 0 / left 1 */    \
-                            h = __vimax3_s16x2(m, fma_add(up, one, ext2), zero2);           /* up 2 / zero 3 */      \
-                            const uint32_t t = h & 0x00030003u;                                                      \
+                            const uint32_t m = pw_addmax<PACKED>(diag, sc, OLD[r]);          /* diag 0 / left 1 */    \
+                            h = pw_max3<PACKED>(m, fma_add(up, one, ext2), zero2);           /* up 2 / zero 3 */      \
+                            const uint32_t t = h & REP3;                                                      \
                             const uint32_t hq = fma_add(t, minus1, h);                      /* clean: 4H + BIAS */   \
                             if (TB) acc[r / CPH] = fma_add(acc[r / CPH], four, t);                                   \
                             NEW[r] = fma_add(hq, one, addc3);                                                        \
                             bool keepHi, keepLo;                                            /* best >= hq: no new maximum */ \
-                            bestv[r] = vibmax_s16x2_safe(bestv[r], hq, &keepHi, &keepLo);                            \
+                            bestv[r] = pw_bmax<PACKED>(bestv[r], hq, &keepHi, &keepLo);                            \
                             stA[r] = keepLo ? stA[r] : (S);                                                          \
                             stB[r] = keepHi ? stB[r] : (S);                                                          \
                         } else {                                                                                     \
-                            const uint32_t m = __viaddmax_s16x2(diag, sc, up);                                       \
-                            h = __viaddmax_s16x2(OLD[r], ext2, m);                                                   \
+                            const uint32_t m = pw_addmax<PACKED>(diag, sc, up);                                       \
+                            h = pw_addmax<PACKED>(OLD[r], ext2, m);                                                   \
                             if (TB) {                                                                                \
-                                const uint32_t t = h & 0x00030003u;                                                  \
+                                const uint32_t t = h & REP3;                                                  \
                                 acc[r / CPH] = fma_add(acc[r / CPH], four, t);                                       \
                                 NEW[r] = fma_add(fma_add(t, minus1, h), one, addc3);                                 \
                             }                                                                                        \
                         }                                                                                            \
                         diag = OLD[r];                                                                               \
-                        if (!TB && !SW) NEW[r] = fma_add(h | 0x00030003u, one, addc);                                \
+                        if (!TB && !SW) NEW[r] = fma_add(h | REP3, one, addc);                                \
                         up = NEW[r];                                                                                 \
                     }                                                                                                \
                     botH = up; botD = upD;                                                                           \
@@ -276,7 +296,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                     uint32_t v = 0;
                     #pragma unroll
                     for (int r = 0; r < K; ++r) if (r == rrA) v = (sA & 1) ? hA[r] : hB[r];
-                    a.scores[pa] = (((int)(v & 0xffffu) - a.dec_sub) >> 2) + a.dec_add;
+                    a.scores[pa] = (((PACKED ? (int)(v & 0xffffu) : (int)v) - a.dec_sub) >> 2) + a.dec_add;
                 }
                 if (!SW && sB >= 0 && s == eB && lane == glB) {
                     uint32_t v = 0;
@@ -290,7 +310,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                 // rows of this pass into the lane's best: higher score, then smaller row (rows ascend with r and with the pass)
                 #pragma unroll
                 for (int r = 0; r < K; ++r) {
-                    const int vA = (int)(bestv[r] & 0xffffu), vB = (int)(bestv[r] >> 16);
+                    const int vA = PACKED ? (int)(bestv[r] & 0xffffu) : (int)bestv[r], vB = PACKED ? (int)(bestv[r] >> 16) : 0;
                     if (i0 + r < QA && vA > swA) { swA = vA; swRowA = i0 + r + 1; swColA = stA[r] - lane + 1; }
                     if (i0 + r < QB && vB > swB) { swB = vB; swRowB = i0 + r + 1; swColB = stB[r] - lane + 1; }
                 }
@@ -347,7 +367,7 @@ struct PwBtArgs {
     int32_t* str_start;
 };
 
-template <int ALGO, int K>
+template <int ALGO, int K, bool PACKED>
 __global__ void __launch_bounds__(128) pw_bt_kernel(const PwBtArgs a) {
     constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
     constexpr int CB = AFF ? 4 : 2;
@@ -360,13 +380,13 @@ __global__ void __launch_bounds__(128) pw_bt_kernel(const PwBtArgs a) {
     const dpx_seq_pair pr = a.pairs[pid];
     const int R = pr.referenceSize, Q = pr.querySize;
     int Rw = R;
-    if ((t ^ 1) < a.count) { const int po = a.order ? a.order[a.first + (t ^ 1)] : a.first + (t ^ 1); Rw = max(Rw, a.pairs[po].referenceSize); }
+    if (PACKED && (t ^ 1) < a.count) { const int po = a.order ? a.order[a.first + (t ^ 1)] : a.first + (t ^ 1); Rw = max(Rw, a.pairs[po].referenceSize); }
     const PwGeom geo = PwGeom::make(K, CB);
     const int nsteps2 = geo.nsteps(Rw);
-    const int half = (t & 1) * 16;
+    const int half = PACKED ? (t & 1) * 16 : 0;
     const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
     const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
-    const uint32_t* __restrict__ tb = a.tb + (unsigned long long)(t >> 1) * a.tb_stride;
+    const uint32_t* __restrict__ tb = a.tb + (unsigned long long)(PACKED ? (t >> 1) : t) * a.tb_stride;
 
     const size_t F = (size_t)Q + R + 1;
     char* __restrict__ o0 = a.strings + a.str_off[pid];

@@ -177,6 +177,7 @@ int         dpx_batch_stats(const dpx_batch* b, dpx_run_stats* out);
 #define DPX_KERNEL_SHORT_S16X2    2u  /* thread-per-2-pairs, packed int16x2 DPX */
 #define DPX_KERNEL_BAND_S32       3u  /* banded anti-diagonal, band mapped onto one warp */
 #define DPX_KERNEL_TILED_S32      4u  /* multi-CTA tiled wavefront for one long pair */
+#define DPX_KERNEL_PAIR_S32       6u  /* the same kernel family in int32, one pair per warp (scores beyond the int16 budget) */
 #define DPX_KERNEL_PAIR_S16X2     5u  /* two pairs per warp, packed int16x2, directions in the low score bits (NW / Gotoh + traceback) */
 
 /* ---- one very long pair, score + end cell only (BASELINE config 5) ----------------------

@@ -10,7 +10,7 @@ from dpx_gpu_genomics_project_b200 import api, synth
 
 pytestmark = pytest.mark.gpu
 ALL = api.OUT_SCORE | api.OUT_END_COORDS | api.OUT_STRINGS
-KERNEL_PAIR, KERNEL_WAVEFRONT = 5, 1
+KERNEL_PAIR, KERNEL_PAIR_INT32, KERNEL_WAVEFRONT = 5, 6, 1
 
 
 @pytest.fixture(scope="module")
@@ -105,10 +105,24 @@ def test_empty_sequences_inside_a_batch(eng, algo):
 
 
 @pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
-def test_out_of_range_batches_fall_back_to_the_int32_kernel(eng, algo):
-    # scores beyond the int16 budget (4 * (hi - lo) must stay below 2^15) or a mismatch worse than a gap open
-    blob, pairs = _ragged(5, 6, 2800, 2900)
-    _check(eng, algo, blob, pairs, KERNEL_WAVEFRONT, **WEIGHTS[algo][0])
+def test_out_of_range_batches_take_the_int32_variant_or_the_wavefront_kernel(eng, algo):
+    # scores beyond the int16 budget (4 * (hi - lo) must stay below 2^15): the same kernel in int32, one pair per warp
+    blob, pairs = _ragged(5, 7, 2800, 2900)
+    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])
+    # a mismatch worse than a gap open does not fit the score table: the general wavefront kernel
     blob, pairs = _ragged(6, 50, 1, 80)
     w = dict(match=3, mismatch=-9, gap_open=-2, gap_extend=-1) if algo == api.ANW else dict(match=3, mismatch=-9, gap_open=-2)
     _check(eng, algo, blob, pairs, KERNEL_WAVEFRONT, **w)
+
+
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
+def test_int32_variant_on_the_small_cases(eng, algo, monkeypatch):
+    """DPX_PAIRWF_INT32 forces the one-pair-per-warp int32 instantiation of the same kernels onto inputs the packed one handles."""
+    monkeypatch.setenv("DPX_PAIRWF_INT32", "1")
+    blob, pairs = _ragged(21, 151, 1, 140)
+    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])
+    pp = [(b"", b""), (b"0123", b""), (b"", b"3210"), (b"0", b"0"), (b"0123012301", b"0123012301")]
+    rng = synth.Rng(4)
+    r = synth.random_seq(rng, 600); pp.append((r, synth.mutate(rng, r, 0.04, 0.02, 0.02)))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][1])

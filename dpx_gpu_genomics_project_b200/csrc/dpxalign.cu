@@ -125,6 +125,8 @@ struct dpx_batch {
     const uint8_t* d_blob = nullptr;               // d_blob_alloc - byte_lo: indexable with the seqPair offsets
     dpx_seq_pair* d_pairs = nullptr;
     uint32_t* d_packed = nullptr;
+    uint8_t* d_codes = nullptr;                    // 5..8 symbols: byte codes, same indexing as d_blob (allocated at d_codes_alloc - byte_lo)
+    uint8_t* d_codes_alloc = nullptr;
     unsigned long long* d_pk_off = nullptr; unsigned long long pk_stride = 0;
     unsigned long long* d_str_len = nullptr;       // 3*(Q+R+1) per pair (scanned lazily into d_str_off)
     int32_t* d_order = nullptr;
@@ -338,7 +340,7 @@ int dpx_selftest_dpx(dpx_ctx* ctx) {
 static void batch_release(dpx_batch* b) {
     // returns device memory to the pool; the batch's stream must have drained (callers guarantee it)
     DevPool& P = b->ctx->pool;
-    P.release(b->d_blob_alloc); P.release(b->d_pairs); P.release(b->d_packed); P.release(b->d_pk_off); P.release(b->d_str_len);
+    P.release(b->d_blob_alloc); P.release(b->d_pairs); P.release(b->d_packed); P.release(b->d_codes_alloc); P.release(b->d_pk_off); P.release(b->d_str_len);
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
     P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
     for (auto e : b->ev) cudaEventDestroy(e);
@@ -427,6 +429,14 @@ static int batch_finish(dpx_batch* b) {
         b->packed2 = true;
     } else {
         ctx->pool.release(b->d_pk_off); b->d_pk_off = nullptr;
+        if (nsym <= 8) {
+            // 5..8 symbols: a byte-coded copy of the blob for the WIDE pair-wavefront kernels (pairwf.cuh)
+            const size_t nb = (size_t)(b->byte_hi - b->byte_lo);
+            if (!pool_alloc(ctx, &b->d_codes_alloc, nb + 16)) return fail(DPX_ERR_NOMEM);
+            b->d_codes = b->d_codes_alloc - b->byte_lo;
+            code_bytes_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(b->d_blob_alloc, (long long)nb, b->d_codes_alloc, lut);
+            CUB_(cudaGetLastError());
+        }
     }
     return DPX_OK;
 }
@@ -584,11 +594,12 @@ static int ensure_str_off(dpx_batch* b) {
 
 
 // ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
-struct PwPlan { int K; bool packed; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
+struct PwPlan { int K; bool packed, wide; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
 
 static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
     const bool sw = p->algo == DPX_ALGO_LSW;
-    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || !b->packed2 || getenv("DPX_NO_PAIRWF")) return false;
+    const bool wide = !b->packed2 && b->d_codes != nullptr;       // 5..8 symbols: int32, both table registers for one pair
+    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || (!b->packed2 && !wide) || getenv("DPX_NO_PAIRWF")) return false;
     if (sw && !(p->flags & DPX_OUT_STRINGS)) return false;      // score / end cell alone: the short-read kernel (or the int32 wavefront)
     const bool aff = p->algo == DPX_ALGO_ANW;
     const long long m = p->match, x = p->mismatch, go = p->gap_open, ge = aff ? p->gap_extend : 0;
@@ -607,9 +618,9 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
     const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
     const long long B = -4 * lo + margin;
-    const bool packed = 4 * hi + B + 16 <= 32767 && !getenv("DPX_PAIRWF_INT32");     // else one pair per warp in int32
+    const bool packed = !wide && 4 * hi + B + 16 <= 32767 && !getenv("DPX_PAIRWF_INT32");     // else one pair per warp in int32
     if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
-    pl->K = K; pl->packed = packed;
+    pl->K = K; pl->packed = packed; pl->wide = wide;
     pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
     auto pk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; };
     // add constants: packed halves need the always-carry compensation (high half pre-decremented), int32 takes the value itself
@@ -626,9 +637,9 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     return true;
 }
 
-template <int ALGO, bool TB, bool PACKED, bool GBND>
+template <int ALGO, bool TB, bool PACKED, bool GBND, bool WIDE = false>
 static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
-    auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND>;
+    auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND, WIDE>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
@@ -640,6 +651,7 @@ static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_
 }
 template <int ALGO, bool TB>
 static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots, bool packed) {
+    if (a.codes) return a.bnd_global ? launch_pairwf_w<ALGO, TB, false, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false, true>(ctx, st, a, smem, n_slots);
     if (a.bnd_global) return packed ? launch_pairwf_w<ALGO, TB, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, true>(ctx, st, a, smem, n_slots);
     return packed ? launch_pairwf_w<ALGO, TB, true, false>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false>(ctx, st, a, smem, n_slots);
 }
@@ -811,6 +823,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
             a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
             a.bnd_stride = b->max_r + 36; a.rsel_stride = (b->max_r + 68) & ~1;
+            a.codes = pl.wide ? b->d_codes : nullptr;
             size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
             if (smem > 44 * 1024) {
                 // long references: the boundary rows would leave fewer than 5 blocks per SM; keep them in a per-warp global buffer

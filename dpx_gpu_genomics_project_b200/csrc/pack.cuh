@@ -133,6 +133,14 @@ __global__ void __launch_bounds__(256) pairs_from_newlines_kernel(const int* __r
 
 struct PackLut { uint8_t code[256]; };
 
+// byte -> code (0..7) for every byte of the blob, same indexing as the blob: alphabets of 5..8 symbols
+__global__ void __launch_bounds__(256) code_bytes_kernel(const uint8_t* __restrict__ blob, long long n, uint8_t* __restrict__ codes, const PackLut lut) {
+    __shared__ uint8_t code[256];
+    code[threadIdx.x] = lut.code[threadIdx.x];
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) codes[i] = code[blob[i]] & 7u;
+}
+
 __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ blob, const dpx_seq_pair* __restrict__ pairs,
                                                      int n_pairs, const unsigned long long* __restrict__ pk_off,
                                                      unsigned long long pk_stride,      // used when pk_off == nullptr (uniform lengths)

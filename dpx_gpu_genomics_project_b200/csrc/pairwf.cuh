@@ -30,6 +30,8 @@
 //           :145-157): every register row keeps its running maximum of clean(h') with one predicate-returning VIMNMX.S16x2 and
 //           the step at which it last grew (two SEL); rows, lanes and passes are merged by (score desc, row asc, column asc).
 //   => per cell-pair 7 ALU-pipe + 4 FMA-pipe instructions.
+// Alphabets of 5..8 symbols (the reference's data sets use '0'..'4') run the int32 instantiation with BOTH table registers of a
+// row serving one pair (WIDE): PRMT indexes eight entries, so nothing else in the kernel changes.
 // All adds that are not fused into a DPX instruction are plain 32-bit IMADs on the FMA pipe: every stored value is
 // biased positive (>= the largest |constant|), so adding a negative constant ALWAYS carries out of the low half (the
 // constant's high half is pre-decremented) and adding a table entry (>= 0) NEVER does.
@@ -79,6 +81,7 @@ struct PwArgs {
     unsigned int* counter;
     int bnd_stride, rsel_stride;         // per-warp shared-memory strides (uint32 / uint16 entries)
     uint32_t* bnd_global;                // null: boundary rows live in shared memory
+    const uint8_t* codes;                // WIDE (5..8 symbols): the blob with every byte replaced by its code 0..7
 };
 
 __device__ __forceinline__ uint32_t fma_mul(uint32_t a, uint32_t m) {
@@ -120,8 +123,9 @@ template <bool P> __device__ __forceinline__ uint32_t pw_bmax(uint32_t a, uint32
 }
 template <bool P> __device__ __forceinline__ uint32_t pw_val(int v) { return P ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; }
 
-template <int ALGO, bool TB, int K, bool PACKED, bool GBND>
+template <int ALGO, bool TB, int K, bool PACKED, bool GBND, bool WIDE>
 __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
+    static_assert(!(WIDE && PACKED), "alphabets of 5..8 symbols use both table registers for ONE pair: int32 only");
     constexpr uint32_t REP1 = PACKED ? 0x00010001u : 1u, REP2 = 2u * REP1, REP3 = 3u * REP1;   // a small constant in every lane of a register
     extern __shared__ uint32_t pw_smem[];
     constexpr bool AFF = (ALGO == DPX_ALGO_ANW);
@@ -154,9 +158,11 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
         int pb = -1, RB = 0, QB = 0;
         const dpx_seq_pair prA = a.pairs[pa];
         const int RA = prA.referenceSize, QA = prA.querySize;
-        const uint32_t* refA = a.packed + (a.pk_off ? a.pk_off[pa] : (unsigned long long)pa * a.pk_stride);
-        const uint32_t* qryA = refA + ((RA + 15) >> 4);
+        const uint32_t* refA = WIDE ? nullptr : a.packed + (a.pk_off ? a.pk_off[pa] : (unsigned long long)pa * a.pk_stride);
+        const uint32_t* qryA = WIDE ? nullptr : refA + ((RA + 15) >> 4);
         const uint32_t *refB = refA, *qryB = qryA;
+        const uint8_t* ref8 = WIDE ? a.codes + prA.referenceIdx : nullptr;      // WIDE: one code byte (0..7) per base, blob indexing
+        const uint8_t* qry8 = WIDE ? a.codes + prA.queryIdx : nullptr;
         if (PACKED && 2 * slot + 1 < a.count) {
             pb = a.order ? a.order[posA + 1] : posA + 1;
             const dpx_seq_pair prB = a.pairs[pb];
@@ -175,8 +181,8 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
             // selector of the per-row score tables: nibble 0 = reference base of pair A (bytes 0..3 of the row's table pair),
             // nibble 2 = 4 + base of pair B (bytes 4..7), nibbles 1 / 3 = the same index | 8 (sign extension; entries are >= 0).
             // Pad columns select the sign of byte 0 / 4 = 0: below any real entry.
-            const uint32_t nA = (j >= 1 && j <= RA) ? get2(refA, j - 1) : 8u;
-            const uint32_t nB = (j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
+            const uint32_t nA = (j >= 1 && j <= RA) ? (WIDE ? (uint32_t)ref8[j - 1] : get2(refA, j - 1)) : 8u;
+            const uint32_t nB = (PACKED && j >= 1 && j <= RB) ? 4u + get2(refB, j - 1) : 12u;
             rsel[e] = PACKED ? (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12))
                              : (uint16_t)(nA | ((nA | 8u) * 0x1110u));          // int32: one base, its sign in the three upper bytes
         }
@@ -197,10 +203,11 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
-                const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
-                const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
+                const uint32_t qa = (i < QA) ? (WIDE ? (uint32_t)qry8[i] : get2(qryA, i)) : 8u;
+                const uint32_t qb = (PACKED && i < QB) ? get2(qryB, i) : 8u;
                 ta[r] = (qa < 4u) ? ((xs4 & ~(0xffu << (8 * qa))) | (ms1 << (8 * qa))) : xs4;
-                tb[r] = !PACKED ? 0u : (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
+                if (WIDE) tb[r] = (qa >= 4u && qa < 8u) ? ((xs4 & ~(0xffu << (8 * (qa - 4u)))) | (ms1 << (8 * (qa - 4u)))) : xs4;   // symbols 4..7 of the SAME pair
+                else      tb[r] = !PACKED ? 0u : (qb < 4u) ? ((xs4 & ~(0xffu << (8 * qb))) | (ms1 << (8 * qb))) : xs4;
                 hA[r] = pw_val<PACKED>(a.b1 + a.bstep * (i + 1));       // column 0 border of matrix row i+1
                 hB[r] = hA[r];
                 if constexpr (AFF) Ic[r] = REP2;                    // I[i][0] never wins: column 1 always opens (:201-205)

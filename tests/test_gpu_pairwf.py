@@ -126,3 +126,22 @@ def test_int32_variant_on_the_small_cases(eng, algo, monkeypatch):
     r = synth.random_seq(rng, 600); pp.append((r, synth.mutate(rng, r, 0.04, 0.02, 0.02)))
     blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
     _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][1])
+
+
+@pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
+@pytest.mark.parametrize("alphabet", [b"01234", b"ACGTNacg"])
+def test_five_to_eight_symbol_alphabets_use_the_wide_tables(eng, algo, alphabet):
+    """The reference's data sets use '0'..'4'; 5..8 symbols run the int32 instantiation with both table registers for one pair."""
+    blob, pairs = _ragged(31, 120, 1, 150, alphabet)
+    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])
+    a = alphabet
+    pp = [(b"", b""), (a[:5], b""), (b"", a[4::-1]), (a[4:5], a[4:5]), (a[4:5], a[0:1])]
+    rng = synth.Rng(8)
+    r = synth.random_seq(rng, 700, alphabet); pp.append((r, synth.mutate(rng, r, 0.04, 0.02, 0.02, alphabet)))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp + [(alphabet, alphabet[::-1])]))
+    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][2])
+
+
+def test_nine_symbols_fall_back_to_the_byte_compare_kernel(eng):
+    blob, pairs = _ragged(32, 60, 1, 100, b"012345678")
+    _check(eng, api.LNW, blob, pairs, KERNEL_WAVEFRONT, **WEIGHTS[api.LNW][0])

@@ -11,8 +11,8 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from sass_loops import kernels, loops, opcode  # noqa: E402
 
-WANT = [r"sr_lsw_kernelILi8ELi19ELb1ELb0E", r"sr_lsw_kernelILi8ELi19ELb0ELb0E", r"pw_nw_kernelILi1ELb1ELi8ELb1ELb0E", r"pw_nw_kernelILi0ELb1ELi8ELb1ELb0E",
-        r"pw_nw_kernelILi2ELb1ELi8ELb1ELb0E", r"pw_nw_kernelILi1ELb1ELi8ELb0ELb1E", r"band_sw_kernelILi2ELb1ELb1E", r"band_sw_kernelILi2ELb1ELb0E", r"long_sw_kernelILi16ELb1ELb1E",
+WANT = [r"sr_lsw_kernelILi8ELi19ELb1ELb0E", r"sr_lsw_kernelILi8ELi19ELb0ELb0E", r"pw_nw_kernelILi1ELb1ELi8ELb1ELb0ELb0E", r"pw_nw_kernelILi0ELb1ELi8ELb1ELb0ELb0E",
+        r"pw_nw_kernelILi2ELb1ELi8ELb1ELb0ELb0E", r"pw_nw_kernelILi1ELb1ELi8ELb0ELb1ELb0E", r"band_sw_kernelILi2ELb1ELb1E", r"band_sw_kernelILi2ELb1ELb0E", r"long_sw_kernelILi16ELb1ELb1E",
         r"long_sw_kernelILi8ELb1ELb1E", r"wf_fill_kernelILi1ELb1ELi8E"]
 
 

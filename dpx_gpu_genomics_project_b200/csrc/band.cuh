@@ -125,6 +125,9 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
         uint32_t nq = 0, nr = 0;
         if (nsteps > 0) { nq = qsp[0]; nr = rsp[0]; }
         rw = (rw >> 4) | (nr << (4 * M));                    // window of step 0
+        const uint8_t* __restrict__ qp = qsp; const uint8_t* __restrict__ rp = rsp;
+        uint32_t* __restrict__ tbw = tbp;
+        const uint32_t rsh = 1u << (4 * M);
 
 // After h' is known: Hg = clean(h') + 4g - 2, key = clean(h') * 2^kb + code, and the 2-bit direction joins the step's field.
 // With traceback the low bits are needed anyway (one LOP3), so the cleaning h' - low + 3 runs on the FMA pipe; without,
@@ -144,9 +147,9 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
 
 #define DPX_BAND_STEP(U, ACC)                                                                                        \
         {                                                                                                            \
-            const uint32_t nq1 = qsp[(U) + 1], nr1 = rsp[(U) + 1];             /* next step's bases (streams are padded) */ \
-            qw = fma_mul(qw, sixteen) + nq;                                                                          \
-            const uint32_t rwN = (rw >> 4) | (nr1 << (4 * M));                                                       \
+            const uint32_t nq1 = qp[(U) - ubase + 1], nr1 = rp[(U) - ubase + 1];   /* next step's bases (streams are padded) */ \
+            qw = fma_add(qw, sixteen, nq);                                                                           \
+            const uint32_t rwN = fma_add(nr1, rsh, rw >> 4);                                                         \
             const uint32_t scE = prmt_b32(lut_lo, lut_hi, qw + rw), scO = prmt_b32(lut_lo, lut_hi, qw + rwN);        \
             rw = rwN; nq = nq1;                                                                                      \
             const uint32_t cE = (uint32_t)(2 * (SB - 1 - ((U) - blk0)) + 1);                                         \
@@ -158,13 +161,13 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
             _Pragma("unroll")                                                                                        \
             for (int m = 0; m < M; ++m) {                                                                            \
                 const int left = (m == 0) ? Lrecv : HgO[m - 1];                                                      \
-                const int m1 = __viaddmax_s32(HgE[m], (int)(int8_t)(scE >> (8 * m)), left);                        \
+                const int m1 = __viaddmax_s32(HgE[m], (int)prmt_b32(scE, 0u, 0x8880u | (m * 0x1111u)), left);                        \
                 int h = __vimax3_s32(m1, (int)fma_add((uint32_t)HgO[m], one, 1u), Z);                                \
                 if (PARTIAL) h = min(h, capE[m]);                                                                    \
                 DPX_BAND_TAIL(h, HgE[m], keyE[m], cE, ACC)                                                           \
             }                                                                                                        \
             if (EXTRA) {                                                                                             \
-                const int m1 = __viaddmax_s32(HgX, (int)(int8_t)(scE >> (8 * M)), oldOlast);                       \
+                const int m1 = __viaddmax_s32(HgX, (int)prmt_b32(scE, 0u, 0x8880u | (M * 0x1111u)), oldOlast);                       \
                 const int h = __vimax3_s32(m1, zerog + 1, Z);                                                        \
                 uint32_t keyX;                                                                                       \
                 DPX_BAND_TAIL(h, HgX, keyX, cE, ACC)                                                                 \
@@ -175,7 +178,7 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
             _Pragma("unroll")                                                                                        \
             for (int m = 0; m < M; ++m) {                                                                            \
                 const int upv = (m == M - 1) ? Urecv : HgE[m + 1];                                                   \
-                const int m1 = __viaddmax_s32(HgO[m], (int)(int8_t)(scO >> (8 * m)), HgE[m]);                      \
+                const int m1 = __viaddmax_s32(HgO[m], (int)prmt_b32(scO, 0u, 0x8880u | (m * 0x1111u)), HgE[m]);                      \
                 int h = __vimax3_s32(m1, (int)fma_add((uint32_t)upv, one, 1u), Z);                                   \
                 if (PARTIAL) h = min(h, capO[m]);                                                                    \
                 uint32_t keyO;                                                                                       \
@@ -188,10 +191,12 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
             const int u_end = min(blk0 + SB, nsteps);
             #pragma unroll 1
             for (int u = blk0; u < u_end; u += 2) {
+                const int ubase = u;                              // qp / rp walk the streams: constant offsets inside the step pair
                 uint32_t acc0, acc1;
                 DPX_BAND_STEP(u, acc0)
                 DPX_BAND_STEP(u + 1, acc1)
-                if (TB) __stcs(tbp + (size_t)(u >> 1) * 32, acc0 | (acc1 << 16));
+                qp += 2; rp += 2;
+                if (TB) { __stcs(tbw, acc0 | (acc1 << 16)); tbw += 32; }
             }
             // fold the block's keys into the lane's (score, row, col)
             auto fold = [&](uint32_t key, int m) {

@@ -261,6 +261,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t saddr) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ void sts_u8(uint32_t saddr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(saddr), "r"(v) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
@@ -293,6 +297,9 @@ __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
     char* outw = reinterpret_cast<char*>(bt_smem + BAND_BT_WIN_WORDS + 2 * BAND_BT_CRING * 32);
     char* out = outw + lane * BAND_BT_OUT_STRIDE;                // this walker's 3 x MOVES characters, filled from the back
     const uintptr_t blob_lo = (uintptr_t)a.blob_lo;
+    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(s_lut), win_s = (uint32_t)__cvta_generic_to_shared(win);
+    const uint32_t rring_s = (uint32_t)__cvta_generic_to_shared(rring), qring_s = (uint32_t)__cvta_generic_to_shared(qring);
+    const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out);
 
     int pid = 0, i = 0, j = 0, done = 1;
     const uint8_t *ref = nullptr, *qry = nullptr;
@@ -340,28 +347,32 @@ __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
             if (fresh) cp_async_wait<0>(); else cp_async_wait<1>();
         }
         __syncwarp();
+        // the walk proper: 32-bit shared-space addresses and 32-bit sequence positions keep the dependent chain short
+        //   lut -> window word -> code -> next (c, u);  the two sequence bytes and the three stores hang off the side
         int cnt = 0;
+        uint32_t rpos = (uint32_t)(uintptr_t)(ref + j - 1), qpos = (uint32_t)(uintptr_t)(qry + i - 1);   // low address bits index the rings
         #pragma unroll 1
         for (int mv = 0; mv < BAND_BT_MOVES; ++mv) {
             if (__all_sync(FULL, done)) break;
             if (done) continue;
-            const uint32_t e = s_lut[c];
-            const int wl = (int)(e & 0xffu) - lane_lo;
-            const uint32_t w = ((unsigned)wl < (unsigned)BAND_BT_LANES) ? win[((u >> 1) & (BAND_BT_RING - 1)) * 128 + wl]
-                                                                        : __ldg(tb + (size_t)(u >> 1) * 32 + (e & 0xffu));
-            const uint32_t code = (w >> ((u & 1) * 16 + (e >> 8))) & 3u;
+            const uint32_t e = lds_u16(lut_s + 2u * (uint32_t)c);
+            const uint32_t wl = (e & 0xffu) - (uint32_t)lane_lo;
+            const uint32_t w = (wl < (uint32_t)BAND_BT_LANES) ? lds_u32(win_s + ((((uint32_t)u >> 1) & (BAND_BT_RING - 1)) << 9) + 4u * wl)
+                                                              : __ldg(tb + (size_t)(u >> 1) * 32 + (e & 0xffu));
+            const uint32_t code = (w >> (((uint32_t)u & 1u) * 16u + (e >> 8))) & 3u;
             if (code == BD_STOP) { done = 1; continue; }
-            const uintptr_t ar = (uintptr_t)(ref + j - 1), aq = (uintptr_t)(qry + i - 1);
-            const char rc = (char)((rring[((ar >> 4) & (BAND_BT_CRING / 4 - 1)) * 128 + ((ar >> 2) & 3)] >> (8 * (ar & 3))) & 0xffu);
-            const char qc = (char)((qring[((aq >> 4) & (BAND_BT_CRING / 4 - 1)) * 128 + ((aq >> 2) & 3)] >> (8 * (aq & 3))) & 0xffu);
+            const uint32_t rc = lds_u8(rring_s + ((rpos & 0x70u) << 5) + (rpos & 15u));
+            const uint32_t qc = lds_u8(qring_s + ((qpos & 0x70u) << 5) + (qpos & 15u));
             ++cnt;
-            out[BAND_BT_MOVES - cnt] = (code == BD_UP) ? '_' : rc;
-            out[2 * BAND_BT_MOVES - cnt] = (code == BD_DIAG) ? ((rc == qc) ? '*' : '|') : ' ';
-            out[3 * BAND_BT_MOVES - cnt] = (code == BD_LEFT) ? '_' : qc;
+            const uint32_t o = out_s + (uint32_t)(BAND_BT_MOVES - cnt);
+            sts_u8(o, (code == BD_UP) ? (uint32_t)'_' : rc);
+            sts_u8(o + BAND_BT_MOVES, (code == BD_DIAG) ? ((rc == qc) ? (uint32_t)'*' : (uint32_t)'|') : (uint32_t)' ');
+            sts_u8(o + 2 * BAND_BT_MOVES, (code == BD_LEFT) ? (uint32_t)'_' : qc);
+            const int di = (code != BD_LEFT), dj = (code != BD_UP);
             u -= ((code == BD_DIAG) | ((c & 1) ^ 1));
             c += (code == BD_UP) - (code == BD_LEFT);
-            i -= (code != BD_LEFT); j -= (code != BD_UP);
-            if (i == 0 || j == 0 || c < 0 || c > 2 * W) done = 1;   // the next cell is a border or out-of-band cell: H == 0
+            i -= di; j -= dj; qpos -= (uint32_t)di; rpos -= (uint32_t)dj;
+            if (i == 0 || j == 0 || (unsigned)c > (unsigned)(2 * W)) done = 1;   // the next cell is a border or out-of-band cell: H == 0
         }
         __syncwarp();
         // flush: the warp writes every walker's new characters with coalesced byte stores (positions [p - cnt, p) of each field)

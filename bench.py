@@ -446,6 +446,8 @@ def main():
            "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(nb + npairs_bytes),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                    "api": "dpx_align_batch (C ABI), pinned host input buffers" + (", library-allocated string blob" if want_strings else ""),
+                   "h2d_note": "bytes of the host buffers handed to the call; when the seqPair index of a chunk is an arithmetic progression "
+                               "(fixed-length records) the library rebuilds it on the device instead of copying its 16 B per pair",
                    "bare_h2d_copy_ms": h2d_ms, "bare_h2d_gbs": nb / (h2d_ms * 1e-3) / 1e9},
            "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
            "fill_ms_serialised": fill_ms, "backtrack_ms_serialised": bt_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}

@@ -445,8 +445,10 @@ static int batch_finish(dpx_batch* b) {
 // scan of the index (uniform lengths).  Part 1 queues the copies; part 2 (once the alphabet map of the call is known)
 // queues the pack kernel, which raises *d_unknown when it meets a byte outside that map (the caller then redoes the
 // call the slow way).
+// `stride` > 0: the chunk's index is an arithmetic progression (pair k at pairs[0] + k * stride, same sizes), so it is rebuilt
+// on the device instead of crossing PCIe (16 bytes per pair: 5 % of a 150 x 150 batch's input).
 static int batch_known_copy(dpx_ctx* ctx, cudaStream_t st, int lane, const char* sequences, long long byte_lo, long long byte_hi,
-                            const dpx_seq_pair* pairs, size_t n_pairs, int R, int Q, dpx_batch** out) {
+                            const dpx_seq_pair* pairs, size_t n_pairs, int R, int Q, long long stride, dpx_batch** out) {
     dpx_batch* b = new dpx_batch();
     b->ctx = ctx; b->stream = st; b->lane = lane; b->n_pairs = n_pairs; b->byte_lo = byte_lo; b->byte_hi = byte_hi;
     auto fail = [&](int s) { cudaStreamSynchronize(st); batch_release(b); return s; };
@@ -462,7 +464,12 @@ static int batch_known_copy(dpx_ctx* ctx, cudaStream_t st, int lane, const char*
     CUB_(cudaEventCreate(&b->ev_begin)); CUB_(cudaEventCreate(&b->ev_end));
     CUB_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
     if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
-    CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (stride > 0) {
+        regular_pairs_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(b->d_pairs, (int)n_pairs, pairs[0], (int)stride);
+        CUB_(cudaGetLastError());
+    } else {
+        CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
     CUB_(cudaEventRecord(b->ev_h2d, ctx->copy_stream));
     CUB_(cudaStreamWaitEvent(st, b->ev_h2d, 0));
     *out = b;
@@ -1554,8 +1561,14 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
         const long long ta = now_us();
         long long lo = (long long)n_bytes, hi = 0;
         int minr = 0x7fffffff, maxr = -1, minq = 0x7fffffff, maxq = -1;
+        // is the index an arithmetic progression?  (fixed-length files: every record has the same size)
+        const long long stride0 = p1 - p0 > 1 ? (long long)pairs[p0 + 1].referenceIdx - pairs[p0].referenceIdx : 1;
+        const long long qoff0 = (long long)pairs[p0].queryIdx - pairs[p0].referenceIdx;
+        bool regular = stride0 > 0 && stride0 < 0x7fffffff;
         for (size_t i = p0; i < p1; ++i) {
             const dpx_seq_pair& q = pairs[i];
+            regular = regular && (long long)q.referenceIdx == (long long)pairs[p0].referenceIdx + (long long)(i - p0) * stride0 &&
+                      (long long)q.queryIdx - q.referenceIdx == qoff0;
             const long long a0 = std::min(q.referenceIdx, q.queryIdx);
             const long long a1 = std::max((long long)q.referenceIdx + q.referenceSize, (long long)q.queryIdx + q.querySize);
             lo = std::min(lo, a0); hi = std::max(hi, a1);
@@ -1570,7 +1583,7 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
         }
         dpx_batch* b = nullptr;
         const bool fast = c > 0 && minr == maxr && minq == maxq;
-        int s = fast ? batch_known_copy(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, maxr, maxq, &b)
+        int s = fast ? batch_known_copy(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, maxr, maxq, regular ? stride0 : 0, &b)
                      : batch_begin(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, p1 - p0, &b);
         if (s) return s;
         inflight[lane] = b; chunk_batch[c] = b; chunk_fast[c] = fast;

@@ -131,6 +131,15 @@ __global__ void __launch_bounds__(256) pairs_from_newlines_kernel(const int* __r
     pairs[k] = p;
 }
 
+// seqPair index of a fixed-length file rebuilt on the device: pair k = first + k * stride (same sizes, same query offset)
+__global__ void __launch_bounds__(256) regular_pairs_kernel(dpx_seq_pair* __restrict__ pairs, int n, const dpx_seq_pair first, int stride) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    dpx_seq_pair p = first;
+    p.referenceIdx += k * stride; p.queryIdx += k * stride;
+    pairs[k] = p;
+}
+
 struct PackLut { uint8_t code[256]; };
 
 // byte -> code (0..7) for every byte of the blob, same indexing as the blob: alphabets of 5..8 symbols

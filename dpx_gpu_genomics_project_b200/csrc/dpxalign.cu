@@ -1077,6 +1077,7 @@ static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaS
         case 2: return long_launch_m<2>(ctx, mode, a, st);
         case 4: return long_launch_m<4>(ctx, mode, a, st);
         case 8: return long_launch_m<8>(ctx, mode, a, st);
+        case 32: return long_launch_m<32>(ctx, mode, a, st);
         default: return long_launch_m<16>(ctx, mode, a, st);
     }
 }
@@ -1086,6 +1087,7 @@ static int long_capacity_k(dpx_ctx* ctx, int K, int mode, int* warps) {
         case 2: return long_capacity_m<2>(ctx, mode, warps);
         case 4: return long_capacity_m<4>(ctx, mode, warps);
         case 8: return long_capacity_m<8>(ctx, mode, warps);
+        case 32: return long_capacity_m<32>(ctx, mode, warps);
         default: return long_capacity_m<16>(ctx, mode, warps);
     }
 }
@@ -1114,15 +1116,20 @@ static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
 
 static long long pow2_at_least(long long v) { long long p = 64; while (p < v) p <<= 1; return p; }
 
-// K: columns per lane.  A warp's row step costs about 43 + 14 K cycles whether it is measured as latency (one warp per SM
-// sub-partition) or as issue slots (several), so a chain of nw = R / 32K warps advances one row every
-// (43 + 14 K) * max(1, nw / (4 * SMs)) cycles (fit of tools/long_sweep.py on B200).  Take the K that minimises it; ties go to the
-// wider lane (fewer shuffles per cell).
-static int long_pick_k(dpx_ctx* ctx, long long R_local) {
+// K: columns per lane.  Measured on B200 (tools/long_sweep.py): with at most one warp per SM sub-partition a row step costs
+// L(K) = 172 / 296 / 344 cycles for K = 8 / 16 / 32 (a dependent chain of 2 DPX ops per cell plus the shuffle / ring overhead of
+// the step); with w warps per sub-partition it stretches by 1 + 0.64 (w - 1) (1 + 1.43 (w - 1) at K = 32, whose 127 registers
+// leave less room to overlap).  The chain advances one row per step, so take the K that minimises the step time; ties go to the
+// wider lane (fewer warps = shorter pipeline fill).  Narrower lanes (K = 4, 2) only pay for references of a few thousand bases,
+// where they are what spreads the work over more than a handful of warps.
+static int long_pick_k(dpx_ctx* ctx, long long R_local, bool allow32 = false) {
     int best_k = 16; double best = 1e300;
-    for (int K : {16, 8, 4, 2}) {
-        const double nw = (double)((R_local + 32LL * K - 1) / (32LL * K));
-        const double cost = (43.0 + 14.0 * K) * std::max(1.0, nw / (4.0 * ctx->sm_count));
+    if (R_local < 4096) return R_local < 1024 ? 2 : 4;
+    for (int K : {32, 16, 8}) {
+        if (K == 32 && !allow32) continue;            // 32 columns per lane: score-table kernels only, keys h * 32 + column must fit int32
+        const double L = K == 32 ? 344.0 : K == 16 ? 296.0 : 172.0;
+        const double w = (double)((R_local + 32LL * K - 1) / (32LL * K)) / (4.0 * ctx->sm_count);
+        const double cost = L * (w <= 1.0 ? 1.0 : 1.0 + (K == 32 ? 1.43 : 0.64) * (w - 1.0));
         if (cost < best * 0.999) { best = cost; best_k = K; }
     }
     return best_k;
@@ -1131,11 +1138,11 @@ static int long_pick_k(dpx_ctx* ctx, long long R_local) {
 static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
                             int32_t* score, int64_t* end_row, int64_t* end_col) {
     cudaStream_t st = ctx->stream;
-    int K = long_pick_k(ctx, (long long)R);
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }   // tests
-    int capacity = 0;
     uint8_t code[256];
     const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
+    int K = long_pick_k(ctx, (long long)R, table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || k == 32) K = k; }   // tests
+    int capacity = 0;
     const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
     { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
     if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
@@ -1657,9 +1664,6 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
     dpx_stripe* s = new dpx_stripe();
     s->ctx = ctx; s->params = *params; s->R_local = R_local; s->col_offset = col_offset; s->Q = Q; s->index = stripe_index; s->n = n_stripes;
     auto fail = [&](int st) { dpx_stripe_free(s); return st; };
-    // lane width: the whole stripe must be one co-resident pass
-    int K = long_pick_k(ctx, (long long)R_local), cap = 0;
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16) K = k; }
     // The code map must be identical on every rank, so it is fixed instead of data-derived: digits '0'..'3' and A/C/G/T
     // (either case) map to 0..3; any other byte in this rank's data switches this stripe to the byte-compare kernel, which
     // is still exact because all ranks then compare (query byte, reference byte) pairs -- but the QUERY must be coded the
@@ -1674,9 +1678,19 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
     for (size_t i = 0; i < R_local && table; ++i) { const uint8_t c = (uint8_t)ref_stripe[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
     if (digits && letters) table = false;         // '0' and 'A' would collide
     s->mode = ((long double)params->match * (long double)Q < 8.0e6L && params->match > 0 ? 1 : 0) | (table ? 2 : 0);
+    // lane width: the whole stripe must be one co-resident pass
+    // The right edge a stripe exports is the last column of its last warp, so every stripe but the last must be made of WHOLE
+    // warps: its width has to be a multiple of 32 K.
+    const bool last = stripe_index == n_stripes - 1;
+    auto whole = [&](int k) { return last || R_local % (32ull * (unsigned)k) == 0; };
+    const bool allow32 = table && (long double)params->match * (long double)Q < 6.0e7L && whole(32);
+    int K = long_pick_k(ctx, (long long)R_local, allow32), cap = 0;
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && allow32)) K = k; }
+    while (K > 2 && !whole(K)) K /= 2;
+    if (!whole(K)) { ctx->err = "a stripe that is not the last one must be a multiple of 64 columns wide"; return fail(DPX_ERR_INVALID); }
     for (;;) {
         if (long_capacity_k(ctx, K, s->mode, &cap)) return fail(DPX_ERR_CUDA);
-        if ((long long)((R_local + 32ull * K - 1) / (32ull * K)) <= cap || K == 16) break;
+        if ((long long)((R_local + 32ull * K - 1) / (32ull * K)) <= cap || K == (allow32 ? 32 : 16) || !whole(2 * K)) break;
         K *= 2;
     }
     s->K = K; s->nw = (int)((R_local + 32ull * K - 1) / (32ull * K));

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
     const int Q = (int)a.Q;
     const long long cfirst = a.col0 + (long long)w * (32 * K) + (long long)lane * K;    // local 0-based
     const int g = a.gap, ma = a.match, mi = a.mismatch;
-    const uint32_t sixteen = a.sixteen;
+    constexpr int KPB = K > 16 ? 5 : 4, KP = 1 << KPB;           // column codes of the per-lane keys: h * KP + (KP-1-k)
+    const uint32_t sixteen = a.sixteen * (K > 16 ? 2u : 1u);       // KP as run-time data (IMAD on the FMA pipe)
     const unsigned imask = cin.ring ? (unsigned)(cin.size - 1) : 0u, omask = cout.ring ? (unsigned)(cout.size - 1) : 0u;
     const bool has_in = cin.ring != nullptr, has_out = cout.ring != nullptr;
 
@@ -200,11 +201,11 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
                         const int t2 = __viaddmax_s32(diag, sc, Hc[k]);                                          \
                         const int h = __viaddmax_s32_relu(left, g, t2);                                          \
                         diag = Hc[k]; Hc[k] = h + g; left = h;                                                   \
-                        const int key = (int)fma_u32((uint32_t)h, sixteen, (uint32_t)(15 - k));   /* FMA pipe */ \
+                        const int key = (int)fma_u32((uint32_t)h, sixteen, (uint32_t)(KP - 1 - k)); /* FMA pipe */ \
                         if (k & 1) m1 = __vimax3_s32(m1, m0, key); else m0 = key;                                \
                     }                                                                                            \
                     if (K & 1) m1 = max(m1, m0);                                                                 \
-                    if ((m1 >> 4) > bestS[0]) { bestS[0] = m1 >> 4; bestR[0] = i; bestC = 15 - (m1 & 15); }      \
+                    if ((m1 >> KPB) > bestS[0]) { bestS[0] = m1 >> KPB; bestR[0] = i; bestC = KP - 1 - (m1 & (KP - 1)); } \
                 } else {                                                                                         \
                     leftprev = leftH;                                                                            \
                     _Pragma("unroll")                                                                            \

@@ -17,8 +17,9 @@ from . import _lib
 from .api import DpxError, Engine
 
 
-def stripe_bounds(R: int, n: int, align: int = 512) -> list[int]:
-    """Column boundaries of n stripes over R columns: equal widths rounded to `align` (whole warps), last stripe takes the rest."""
+def stripe_bounds(R: int, n: int, align: int = 1024) -> list[int]:
+    """Column boundaries of n stripes over R columns: equal widths rounded to `align` (whole warps at up to 32 columns per lane;
+    the library narrows the lanes of a stripe whose width is not a multiple of 32 K), last stripe takes the rest."""
     if n <= 1:
         return [0, R]
     w = -(-R // n)

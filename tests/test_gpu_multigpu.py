@@ -64,8 +64,16 @@ def _worker(rank, world, port, out_path):
     res1, _ = job.run()
     res2, ms = job.run()          # second run exercises reset()
     job.free()
+    # every lane width the stripes can take (the exported right edge must be the stripe's last REAL column)
+    wide = []
+    for k in ("32", "16", "8", "2"):
+        os.environ["DPX_LONG_K"] = k
+        job = longpair.StripedLongPair(eng, api.make_params(api.LSW), ref, qry, rank, world, dist)
+        wide.append(job.run()[0])
+        job.free()
+    del os.environ["DPX_LONG_K"]
     if rank == 0:
-        np.savez(out_path, s=s, e=e, long1=np.array(res1), long2=np.array(res2))
+        np.savez(out_path, s=s, e=e, long1=np.array(res1), long2=np.array(res2), wide=np.array(wide))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -82,3 +90,4 @@ def test_two_gpu_modes_match_oracle(tmp_path):
     ref, qry = _long_inputs()
     want = ol.lsw_score_only(ol.params(ol.LSW), ref, qry)
     assert tuple(got["long1"]) == want and tuple(got["long2"]) == want
+    assert all(tuple(w) == want for w in got["wide"])

@@ -70,13 +70,13 @@ def test_two_rank_gloo_run_reassembles_pair_order(tmp_path):
 # ---- mode B host logic (column stripes of one long pair) ---------------------------------------------------------
 def test_stripe_bounds_cover_the_reference_in_whole_warp_blocks():
     from dpx_gpu_genomics_project_b200.longpair import stripe_bounds
-    for R in (1, 511, 512, 513, 40000, 1_000_000, 999_999):
+    for R in (1, 511, 512, 513, 1023, 1025, 40000, 1_000_000, 999_999):
         for n in (1, 2, 3, 4, 8):
             b = stripe_bounds(R, n)
             assert b[0] == 0 and b[-1] == R and len(b) == n + 1
             assert all(b[i] <= b[i + 1] for i in range(n))
-            # every stripe that is followed by a non-empty stripe ends on a multiple of 512 columns (whole warps at K <= 16)
-            assert all(b[i + 1] % 512 == 0 for i in range(n - 1) if b[i + 2] > b[i + 1])
+            # every stripe that is followed by a non-empty stripe ends on a multiple of 1024 columns (whole warps at K <= 32)
+            assert all(b[i + 1] % 1024 == 0 for i in range(n - 1) if b[i + 2] > b[i + 1])
 
 
 def test_stripe_result_reduction_follows_the_reference_end_cell_rule():

@@ -14,7 +14,7 @@
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #include "common.cuh"
 #include "dpx_ops.cuh"
@@ -1305,7 +1305,7 @@ int dpx_batch_upload_image(dpx_ctx* ctx, const char* image, size_t n_bytes, dpx_
         if (n_lines % 3 != 0) return fail(DPX_ERR_FORMAT);                // parseInput.cpp:38-41
         if (!pool_alloc(ctx, &d_nl, (size_t)n_lines + 2)) return fail(DPX_ERR_NOMEM);
         size_t tmp_bytes = 0;
-        cub::CountingInputIterator<int> idx(0);
+        thrust::counting_iterator<int> idx(0);
         cub::DeviceSelect::If(nullptr, tmp_bytes, idx, d_nl, d_count, (int)n_bytes, IsNewline{b->d_blob_alloc}, st);
         tmp = ctx->pool.alloc(tmp_bytes);
         if (!tmp) return fail(DPX_ERR_NOMEM);

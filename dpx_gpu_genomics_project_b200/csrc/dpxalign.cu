@@ -616,6 +616,7 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long code = aff ? 3 : 1;
     const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
     if (tm < 0 || tm > 127 || tx < 0 || tx > 127) return false;     // table bytes are sign-extended by the selector
+    if (b->max_r > 12000) return false;                          // the per-warp column table (2 B per column, 4 warps per block) must leave 2 blocks per SM
     const int K = 8;
     const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
     // lowest value any stored quantity can take (gaps-only path bounds H from below; Smith-Waterman: H >= 0) and the highest score

@@ -145,3 +145,19 @@ def test_five_to_eight_symbol_alphabets_use_the_wide_tables(eng, algo, alphabet)
 def test_nine_symbols_fall_back_to_the_byte_compare_kernel(eng):
     blob, pairs = _ragged(32, 60, 1, 100, b"012345678")
     _check(eng, api.LNW, blob, pairs, KERNEL_WAVEFRONT, **WEIGHTS[api.LNW][0])
+
+
+def test_very_long_references_fall_back(eng):
+    """The per-warp column table of the pair-wavefront kernels lives in shared memory: beyond 12 kbp the wavefront kernel runs."""
+    rng = synth.Rng(77)
+    r = synth.random_seq(rng, 12500); q = synth.mutate(rng, r[:300], 0.03, 0.01, 0.01)
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes([(r, q), (q, r[:500])]))
+    _check(eng, api.LNW, blob, pairs, KERNEL_WAVEFRONT, **WEIGHTS[api.LNW][0])
+
+
+def test_long_references_inside_the_limit(eng):
+    rng = synth.Rng(78)
+    r = synth.random_seq(rng, 11000); q = synth.mutate(rng, r[:400], 0.03, 0.01, 0.01)
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes([(r, q), (q, r[:600]), (r[:5000], r[100:4800])]))
+    for algo in (api.LNW, api.ANW, api.LSW):
+        _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])

@@ -498,756 +498,9 @@ static int batch_create(dpx_ctx* ctx, cudaStream_t st, int lane, const char* seq
 }
 #undef CUB_
 
-template <int ALGO, bool TB, int K>
-static int query_wf(dpx_ctx* ctx, int slots_wanted, int* blocks_out) {
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_fill_kernel<ALGO, TB, K>, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-    int blocks = std::min(ctx->sm_count * per_sm, (slots_wanted + 3) / 4);
-    *blocks_out = std::max(blocks, 1);
-    return DPX_OK;
-}
+#include "host_run.cuh"
 
-template <int ALGO, bool TB>
-static int dispatch_wf_k(dpx_ctx* ctx, cudaStream_t st, int K, const WfArgs& a, int blocks, bool query_only, int slots, int* blocks_out) {
-    if (K == 4) { if (query_only) return query_wf<ALGO, TB, 4>(ctx, slots, blocks_out); wf_fill_kernel<ALGO, TB, 4><<<blocks, 128, 0, st>>>(a); }
-    else        { if (query_only) return query_wf<ALGO, TB, 8>(ctx, slots, blocks_out); wf_fill_kernel<ALGO, TB, 8><<<blocks, 128, 0, st>>>(a); }
-    return DPX_OK;
-}
-
-static int dispatch_wf(dpx_ctx* ctx, cudaStream_t st, int algo, bool tb, int K, const WfArgs& a, int blocks, bool query_only, int slots, int* blocks_out) {
-    switch (algo) {
-        case DPX_ALGO_LNW: return tb ? dispatch_wf_k<DPX_ALGO_LNW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_LNW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
-        case DPX_ALGO_ANW: return tb ? dispatch_wf_k<DPX_ALGO_ANW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_ANW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
-        case DPX_ALGO_LSW: return tb ? dispatch_wf_k<DPX_ALGO_LSW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_LSW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
-        case DPX_ALGO_BSW: return tb ? dispatch_wf_k<DPX_ALGO_BSW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_BSW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
-    }
-    return DPX_ERR_INVALID;
-}
-
-template <int G, int K>
-static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xormode) {
-    const int gpb = 128 / G;
-    a.bnd_stride = b->max_r + G + 2;
-    a.rsel_stride = (b->max_r + 2 * G + 18 + 1) & ~1;          // the table is written 16 entries (one packed word) at a time
-    const size_t smem = (size_t)gpb * ((size_t)a.bnd_stride * 4 + (size_t)a.rsel_stride * 2);
-    auto launch = [&](auto kern) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-        if (per_sm < 1) { ctx->err = "short-read kernel does not fit on an SM"; return DPX_ERR_RANGE; }
-        const int warps_needed = (a.n_slots + (32 / G) - 1) / (32 / G);
-        int blocks = std::min(ctx->sm_count * per_sm, (warps_needed + 3) / 4);
-        if (blocks < 1) blocks = 1;
-        kern<<<blocks, 128, smem, b->stream>>>(a);
-        CU(cudaGetLastError());
-        return DPX_OK;
-    };
-    if (track) return xormode ? launch(sr_lsw_kernel<G, K, true, true>) : launch(sr_lsw_kernel<G, K, true, false>);
-    return xormode ? launch(sr_lsw_kernel<G, K, false, true>) : launch(sr_lsw_kernel<G, K, false, false>);
-}
-
-// Eligibility of the packed int16x2 short-read kernel (shortread.cuh).
-static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, bool* xormode, int* kbits_out) {
-    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || !b->packed2) return false;
-    const int m = p->match, x = p->mismatch, g = p->gap_open;
-    if (!(m > 0 && x < 0 && g < 0)) return false;                 // pads must stay strictly below real cells
-    if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
-    if (b->max_r > 4096 || b->max_q > 65535) return false;
-    const int B = std::max(2, -g);
-    // position bits: (Hmax + B) << k < 32768; one of the k bits marks the upper row of a row pair, the other
-    // k-1 count steps inside blocks of 2^(k-1) steps; at most 256 blocks per pass
-    const long long top = (long long)m * std::min(b->max_r, b->max_q) + B;
-    int k = 0;
-    while (k < 8 && (top << (k + 1)) < 32768) ++k;
-    if (k < 3) return false;                  // below that the fold every 2^(k-1) steps costs more than it saves
-    if (((long long)b->max_r + 16) >> (k - 1) >= 255) return false;
-    *B_out = B; *xormode = (x - g < 0); *kbits_out = k;
-    return true;
-}
-
-static int ensure_order(dpx_batch* b) {
-    dpx_ctx* ctx = b->ctx;
-    if (b->uniform || b->d_order) return DPX_OK;
-    const int n = (int)b->n_pairs;
-    unsigned long long *k_in = nullptr, *k_out = nullptr; int32_t* v_in = nullptr;
-    if (!pool_alloc(ctx, &k_in, n) || !pool_alloc(ctx, &k_out, n) || !pool_alloc(ctx, &v_in, n) || !pool_alloc(ctx, &b->d_order, n)) return DPX_ERR_NOMEM;
-    sched_keys_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_pairs, n, k_in, v_in);
-    size_t tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, b->d_order, n, 0, 64, b->stream);
-    void* tmp = ctx->pool.alloc(tmp_bytes);
-    if (!tmp) return DPX_ERR_NOMEM;
-    CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, b->d_order, n, 0, 64, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
-    ctx->pool.release(tmp); ctx->pool.release(k_in); ctx->pool.release(k_out); ctx->pool.release(v_in);
-    return DPX_OK;
-}
-
-static int ensure_str_off(dpx_batch* b) {
-    dpx_ctx* ctx = b->ctx;
-    if (b->d_str_off) return DPX_OK;
-    const int n = (int)b->n_pairs;
-    if (!pool_alloc(ctx, &b->d_str_off, n + 1) || !pool_alloc(ctx, &b->d_str_start, n)) return DPX_ERR_NOMEM;
-    size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b->d_str_len, b->d_str_off, n, b->stream);
-    void* tmp = ctx->pool.alloc(tmp_bytes);
-    if (!tmp) return DPX_ERR_NOMEM;
-    CU(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, b->d_str_len, b->d_str_off, n, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
-    ctx->pool.release(tmp);
-    if (!pool_alloc(ctx, &b->d_strings, (size_t)b->info.str_bytes + 1)) return DPX_ERR_NOMEM;
-    return DPX_OK;
-}
-
-
-// ---- packed two-pair Needleman-Wunsch path (pairwf.cuh): plan = every constant of the 4*X + BIAS + code arithmetic ----
-struct PwPlan { int K; bool packed, wide; uint32_t lut_lo, lut_hi, ext2, addc, addc3, zero2; int b0, b1, bstep, dec_sub, dec_add; };
-
-static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
-    const bool sw = p->algo == DPX_ALGO_LSW;
-    const bool wide = !b->packed2 && b->d_codes != nullptr;       // 5..8 symbols: int32, both table registers for one pair
-    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || (!b->packed2 && !wide) || getenv("DPX_NO_PAIRWF")) return false;
-    if (sw && !(p->flags & DPX_OUT_STRINGS)) return false;      // score / end cell alone: the short-read kernel (or the int32 wavefront)
-    const bool aff = p->algo == DPX_ALGO_ANW;
-    const long long m = p->match, x = p->mismatch, go = p->gap_open, ge = aff ? p->gap_extend : 0;
-    const long long open = aff ? go + ge : go;                   // cost of the first gap column: "goe" (Gotoh) or g (linear)
-    if (open >= 0 || ge > 0 || go > 0) return false;             // the add constant must be negative (always-carry rule)
-    if (sw && !(m > 0 && x < 0)) return false;                   // pads must stay strictly below the maximum
-    const long long code = aff ? 3 : 1;
-    const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
-    if (tm < 0 || tm > 127 || tx < 0 || tx > 127) return false;     // table bytes are sign-extended by the selector
-    if (b->max_r > 12000) return false;                          // the per-warp column table (2 B per column, 4 warps per block) must leave 2 blocks per SM
-    const int K = 8;
-    const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
-    // lowest value any stored quantity can take (gaps-only path bounds H from below; Smith-Waterman: H >= 0) and the highest score
-    const long long lo = sw ? go - 2
-                       : aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
-                             : (Qp + Rp + 1) * go + std::min<long long>(x, 0) - 2;
-    const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
-    const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
-    const long long B = -4 * lo + margin;
-    const bool packed = !wide && 4 * hi + B + 16 <= 32767 && !getenv("DPX_PAIRWF_INT32");     // else one pair per warp in int32
-    if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
-    pl->K = K; pl->packed = packed; pl->wide = wide;
-    pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
-    auto pk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; };
-    // add constants: packed halves need the always-carry compensation (high half pre-decremented), int32 takes the value itself
-    auto addk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) | ((uint32_t)((v - 1) & 0xffff) << 16) : (uint32_t)v; };
-    pl->ext2 = aff ? pk(4 * ge) : pk(1);
-    const long long c = aff ? 4 * open : 4 * open - 2;           // (h' | 3) + c -> code 3 (Gotoh) / code 1 (linear)
-    pl->addc = addk(c);
-    pl->addc3 = addk(c + 3);
-    pl->zero2 = pk(B + 3);
-    pl->b0 = (int)(4 * open + B + code);
-    pl->b1 = aff ? (int)(4 * (go + open) + B + code) : pl->b0;
-    pl->bstep = sw ? 0 : (int)(4 * (aff ? ge : go));             // Smith-Waterman borders are 0 everywhere
-    pl->dec_sub = (int)(sw ? B : B + code); pl->dec_add = (int)(sw ? 0 : -open);
-    return true;
-}
-
-template <int ALGO, bool TB, bool PACKED, bool GBND, bool WIDE = false>
-static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
-    auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND, WIDE>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
-    if (per_sm < 1) { ctx->err = "pair-wavefront kernel does not fit on an SM"; return DPX_ERR_RANGE; }
-    const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, (n_slots + 3) / 4));
-    kern<<<blocks, 128, smem, st>>>(a);
-    CU(cudaGetLastError());
-    return DPX_OK;
-}
-template <int ALGO, bool TB>
-static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots, bool packed) {
-    if (a.codes) return a.bnd_global ? launch_pairwf_w<ALGO, TB, false, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false, true>(ctx, st, a, smem, n_slots);
-    if (a.bnd_global) return packed ? launch_pairwf_w<ALGO, TB, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, true>(ctx, st, a, smem, n_slots);
-    return packed ? launch_pairwf_w<ALGO, TB, true, false>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false>(ctx, st, a, smem, n_slots);
-}
-
-
-// ---- banded Smith-Waterman with the band mapped onto one warp (band.cuh) ---------------------------------------------
-struct BandPlan { uint32_t lut_lo, lut_hi; int gadd, zerog, kb; };
-
-static bool band_eligible(const dpx_batch* b, const dpx_params* p, int band, BandPlan* pl) {
-    if (p->algo != DPX_ALGO_BSW || !b->packed2 || getenv("DPX_NO_BANDKERNEL")) return false;
-    const long long m = p->match, x = p->mismatch, g = p->gap_open;
-    if (!(m > 0 && x < 0 && g < 0) || band < 0 || band > 96) return false;
-    const long long tm = 4 * (m - g) - 1, tx = 4 * (x - g) - 1;
-    if (tm < -128 || tm > 127 || tx < -128 || tx > 127 || g < -(1 << 20)) return false;   // int8 table entries
-    const long long hcmax = 4 * m * (long long)std::min(b->max_q, b->max_r) + 3;
-    int nb = 0; while ((hcmax >> nb) != 0) ++nb;
-    const int kb = std::min(16, 32 - nb);
-    if (kb < 4) return false;
-    uint8_t tab[8];
-    for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)tx;
-    tab[3] = (uint8_t)tm;
-    pl->lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
-    pl->lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
-    pl->gadd = (int)(4 * g - 2); pl->zerog = (int)(4 * g + 1); pl->kb = kb;
-    return true;
-}
-
-template <int M, bool EXTRA>
-static int launch_band(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, bool tb) {
-    auto go = [&](auto kern) -> int {
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
-        const int blocks = std::max(1, std::min(ctx->sm_count * std::max(per_sm, 1), (a.count + 3) / 4));
-        kern<<<blocks, 128, 0, st>>>(a);
-        CU(cudaGetLastError());
-        return DPX_OK;
-    };
-    return tb ? go(band_sw_kernel<M, EXTRA, true>) : go(band_sw_kernel<M, EXTRA, false>);
-}
-
-static int launch_band_any(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, bool tb) {
-    const BandGeom g = BandGeom::make(a.W);
-    switch (g.M * 2 + g.extra) {
-        case 2: return launch_band<1, false>(ctx, st, a, tb);
-        case 3: return launch_band<1, true>(ctx, st, a, tb);
-        case 4: return launch_band<2, false>(ctx, st, a, tb);
-        case 5: return launch_band<2, true>(ctx, st, a, tb);
-        case 6: return launch_band<3, false>(ctx, st, a, tb);
-        default: return launch_band<3, true>(ctx, st, a, tb);
-    }
-}
-
-static int batch_run(dpx_batch* b, const dpx_params* p) {
-    dpx_ctx* ctx = b->ctx;
-    cudaStream_t st = b->stream;
-    if (p->algo < DPX_ALGO_LNW || p->algo > DPX_ALGO_BSW) return DPX_ERR_INVALID;
-    if (p->algo == DPX_ALGO_BSW && p->band < 0) return DPX_ERR_INVALID;
-    const size_t n = b->n_pairs;
-    b->params = *p; b->ran = true;
-    b->stats = dpx_run_stats{};
-    for (auto e : b->ev) cudaEventDestroy(e);
-    for (auto e : b->ev_sync) cudaEventDestroy(e);
-    b->ev.clear(); b->ev_kind.clear(); b->ev_sync.clear();
-    const bool want_strings = (p->flags & DPX_OUT_STRINGS) != 0;
-    const int algo = p->algo;
-    const int CB = (algo == DPX_ALGO_ANW) ? 4 : 2;
-    const int K = (b->max_q <= 128) ? 4 : 8;
-    int band = -1;
-    if (algo == DPX_ALGO_BSW) band = std::min(p->band, std::max(b->max_q, b->max_r));
-    b->stats.cells = b->info.cells;
-    b->stats.kernel_id = DPX_KERNEL_WAVEFRONT_S32;
-    if (n == 0) { CU(cudaEventRecord(b->ev_begin, st)); CU(cudaEventRecord(b->ev_end, st)); return DPX_OK; }
-    unsigned int* counters = ctx->counters + 64 * b->lane;   // 64 counters per lane
-
-    // one-time (per batch) preparation, outside the timed first-kernel -> last-byte window
-    { int s = ensure_order(b); if (s) return s; }
-    if (want_strings) { int s = ensure_str_off(b); if (s) return s; }
-    if (algo == DPX_ALGO_BSW) {
-        if (!b->d_band_cells && !pool_alloc(ctx, &b->d_band_cells, 1)) return DPX_ERR_NOMEM;
-        CU(cudaMemsetAsync(b->d_band_cells, 0, sizeof(unsigned long long), st));
-        band_cells_kernel<<<std::min<int>((int)((n + 7) / 8), ctx->sm_count * 8), 256, 0, st>>>(b->d_pairs, (int)n, band, b->d_band_cells);
-    }
-    CU(cudaEventRecord(b->ev_begin, st));
-
-    auto add_event_pair = [&](int kind, cudaEvent_t* s, cudaEvent_t* e) -> int {
-        CU(cudaEventCreate(s)); CU(cudaEventCreate(e));
-        b->ev.push_back(*s); b->ev.push_back(*e); b->ev_kind.push_back(kind);
-        return DPX_OK;
-    };
-
-    // ---- short-read path: packed int16x2 DPX kernel (score / end cell only) -------------------------
-    {
-        int B = 0, kbits = 0; bool xormode = false;
-        if (short_eligible(b, p, &B, &xormode, &kbits)) {
-            const int g = p->gap_open;
-            SrArgs sa{};
-            sa.packed = b->d_packed; sa.pk_off = b->d_pk_off; sa.pk_stride = b->pk_stride;
-            sa.pairs = b->d_pairs; sa.order = b->d_order;
-            sa.n_pairs = (int)n; sa.n_slots = (int)((n + 1) / 2);
-            const int ms = p->match - g, xs = p->mismatch - g;
-            uint8_t tab[8];
-            for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)(int8_t)xs;
-            tab[xormode ? 0 : 3] = (uint8_t)(int8_t)ms;
-            sa.lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
-            sa.lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
-            sa.ms_byte = (uint32_t)(ms & 0xff); sa.xs_byte = (uint32_t)(xs & 0xff);
-            auto pk = [](int v) { return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16); };
-            sa.one = 1u; sa.kbits = kbits; sa.kmul = 1u << kbits; sa.B = B; sa.B2 = pk(B); sa.Bg2 = pk(B + g);
-            sa.G2 = (uint32_t)(g & 0xffff) | ((uint32_t)((g - 1) & 0xffff) << 16);
-            sa.scores = b->d_scores; sa.end_rc = b->d_end_rc;
-            sa.counter = counters;
-            CU(cudaMemsetAsync(sa.counter, 0, sizeof(unsigned int), st));
-            const bool track = (p->flags & DPX_OUT_END_COORDS) != 0;
-            cudaEvent_t s, e;
-            { int r = add_event_pair(0, &s, &e); if (r) return r; }
-            CU(cudaEventRecord(s, st));
-            int r;
-            if (b->max_q <= 64) r = run_short<8, 8>(ctx, b, sa, track, xormode);
-            else                r = run_short<8, 19>(ctx, b, sa, track, xormode);
-            if (r) return r;
-            CU(cudaEventRecord(e, st));
-            b->stats.kernel_launches = 1;
-            b->stats.kernel_id = DPX_KERNEL_SHORT_S16X2;
-            CU(cudaEventRecord(b->ev_end, st));
-            return DPX_OK;
-        }
-    }
-
-    // ---- NW / Gotoh: packed two-pair wavefront with directions in the low score bits (pairwf.cuh) ------------
-    {
-        PwPlan pl;
-        if (pairwf_eligible(b, p, &pl)) {
-            const bool aff = algo == DPX_ALGO_ANW;
-            const PwGeom geo = PwGeom::make(pl.K, aff ? 4 : 2);
-            const unsigned long long tbs = want_strings ? geo.words(b->max_q, b->max_r) : 0;
-            // Traceback runs are cut into chunks over TWO slab buffers: the backtrack of chunk c runs on a second stream while
-            // the fill kernel of chunk c+1 writes the other buffer (the walk is latency-bound and leaves the issue slots to the fill).
-            size_t per_chunk = n; int nbuf = 1;
-            if (want_strings) {
-                const size_t ppw = pl.packed ? 2 : 1;                                    // pairs per warp
-                const size_t slots_total = (n + ppw - 1) / ppw;
-                const size_t max_slots = std::max<size_t>(1, (ctx->tb_budget_bytes / 2 / 4) / std::max<unsigned long long>(tbs, 1));
-                size_t nchunks = (slots_total + max_slots - 1) / max_slots;
-                if (!getenv("DPX_SERIAL_CHUNKS"))                                               // (set by bench.py to time the fill kernel alone)
-                    nchunks = std::max<size_t>(nchunks, std::min<size_t>(8, n / 16384));        // >= 16k pairs per chunk: whole waves of warps
-                const size_t slots = (slots_total + nchunks - 1) / nchunks;
-                per_chunk = ppw * slots; nbuf = (nchunks > 1 && !getenv("DPX_SERIAL_CHUNKS")) ? 2 : 1;
-                const size_t need = (size_t)nbuf * slots * (size_t)tbs;
-                if (b->d_tb && b->tb_words < need) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
-                if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, need)) return DPX_ERR_NOMEM; b->tb_words = need; }
-                b->stats.traceback_bytes = (uint64_t)slots_total * tbs * 4;
-            }
-            // streams of the chunk pipeline: fills alternate between the batch stream and a second one (the tail of one fill
-            // overlaps the head of the next), walks run on a third
-            cudaStream_t bt_st = nbuf > 1 ? ctx->aux_stream[0] : st;
-            cudaStream_t fill2_st = nbuf > 1 ? ctx->aux_stream[1] : st;
-            auto sync_event = [&](cudaEvent_t* ev) -> int { CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming)); b->ev_sync.push_back(*ev); return DPX_OK; };
-            std::vector<cudaEvent_t> bt_done, fill_done;
-            if (nbuf > 1) {
-                cudaEvent_t start;
-                { int r2 = sync_event(&start); if (r2) return r2; }
-                CU(cudaEventRecord(start, st));
-                CU(cudaStreamWaitEvent(fill2_st, start, 0));
-            }
-            PwArgs a{};
-            a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
-            a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu; a.zero2 = pl.zero2;
-            a.one = 1u; a.two = 2u; a.four = 4u; a.eight = 8u; a.sixteen = 16u;
-            a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
-            a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
-            a.bnd_stride = b->max_r + 36; a.rsel_stride = (b->max_r + 68) & ~1;
-            a.codes = pl.wide ? b->d_codes : nullptr;
-            size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
-            if (smem > 44 * 1024) {
-                // long references: the boundary rows would leave fewer than 5 blocks per SM; keep them in a per-warp global buffer
-                const size_t warps = (size_t)ctx->sm_count * 16 * 4, need = warps * (size_t)a.bnd_stride * (aff ? 2 : 1);
-                if (ctx->boundary_ints[b->lane] < need) {
-                    if (ctx->boundary[b->lane]) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->boundary[b->lane]); ctx->boundary[b->lane] = nullptr; ctx->boundary_ints[b->lane] = 0; }
-                    CU(cudaMalloc(&ctx->boundary[b->lane], need * sizeof(int32_t))); ctx->boundary_ints[b->lane] = need;
-                }
-                a.bnd_global = reinterpret_cast<uint32_t*>(ctx->boundary[b->lane]);
-                smem = (size_t)4 * a.rsel_stride * 2;
-            }
-            b->stats.kernel_id = pl.packed ? DPX_KERNEL_PAIR_S16X2 : DPX_KERNEL_PAIR_S32;
-            int c = 0;
-            for (size_t first = 0; first < n; first += per_chunk, ++c) {
-                a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
-                a.counter = counters + (c % 64);
-                a.tb = want_strings ? b->d_tb + (size_t)(c % nbuf) * (per_chunk / (pl.packed ? 2 : 1)) * (size_t)tbs : nullptr;
-                cudaStream_t fst = (c & 1) ? fill2_st : st;
-                if (nbuf > 1 && c >= nbuf) CU(cudaStreamWaitEvent(fst, bt_done[c - nbuf], 0));     // the buffer's previous walk is over
-                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), fst));
-                cudaEvent_t s, e;
-                { int r = add_event_pair(0, &s, &e); if (r) return r; }
-                CU(cudaEventRecord(s, fst));
-                const int n_slots = pl.packed ? (a.count + 1) / 2 : a.count;
-                int r;
-                if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, fst, a, smem, n_slots, pl.packed);
-                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots, pl.packed);
-                else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, fst, a, smem, n_slots, pl.packed);
-                if (r) return r;
-                CU(cudaEventRecord(e, fst));
-                b->stats.kernel_launches++;
-                if (want_strings) {
-                    if (nbuf > 1) {
-                        cudaEvent_t filled;
-                        { int r2 = sync_event(&filled); if (r2) return r2; }
-                        CU(cudaEventRecord(filled, fst));
-                        CU(cudaStreamWaitEvent(bt_st, filled, 0));
-                        fill_done.push_back(filled);
-                    }
-                    PwBtArgs t{};
-                    t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.K = pl.K;
-                    t.tb = a.tb; t.tb_stride = tbs; t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
-                    t.scores = b->d_scores; t.end_rc = b->d_end_rc;
-                    { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
-                    CU(cudaEventRecord(s, bt_st));
-                    const int bt_blocks = (a.count + 127) / 128;
-                    if (pl.packed) {
-                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
-                    } else {
-                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
-                    }
-                    CU(cudaGetLastError());
-                    CU(cudaEventRecord(e, bt_st));
-                    b->stats.kernel_launches++;
-                    if (nbuf > 1) {
-                        cudaEvent_t walked;
-                        { int r2 = sync_event(&walked); if (r2) return r2; }
-                        CU(cudaEventRecord(walked, bt_st));
-                        bt_done.push_back(walked);
-                    }
-                }
-            }
-            for (size_t k = 0; k < bt_done.size(); ++k) CU(cudaStreamWaitEvent(st, bt_done[k], 0));     // the batch stream ends after every walk
-            CU(cudaEventRecord(b->ev_end, st));
-            return DPX_OK;
-        }
-    }
-
-    // ---- banded SW: the band mapped onto one warp (band.cuh) ----------------------------------------------------
-    {
-        BandPlan pl;
-        if (band_eligible(b, p, band, &pl)) {
-            const BandGeom geo = BandGeom::make(band);
-            const int qs_len = geo.qs_len(b->max_q, b->max_r), rs_len = geo.rs_len(b->max_q, b->max_r);
-            if (b->band_prep_w != band) {
-                if (b->d_band_qs) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_band_qs); ctx->pool.release(b->d_band_rs); b->d_band_qs = b->d_band_rs = nullptr; }
-                if (!pool_alloc(ctx, &b->d_band_qs, n * (size_t)qs_len) || !pool_alloc(ctx, &b->d_band_rs, n * (size_t)rs_len)) return DPX_ERR_NOMEM;
-                band_prep_kernel<<<std::min<int>((int)((n + 7) / 8), ctx->sm_count * 8), 256, 0, st>>>(
-                    b->d_packed, b->d_pk_off, b->pk_stride, b->d_pairs, (int)n, geo.offq(), geo.offr(), qs_len, rs_len, b->d_band_qs, b->d_band_rs);
-                CU(cudaGetLastError());
-                b->band_prep_w = band;
-                CU(cudaEventRecord(b->ev_begin, st));       // stream layout is per-batch preparation, like the 2-bit pack
-            }
-            const unsigned long long tbs = want_strings ? geo.words(b->max_q, b->max_r) : 0;
-            size_t per_chunk = n;
-            if (want_strings) {
-                per_chunk = std::max<size_t>(1, std::min<size_t>(n, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tbs, 1)));
-                if (b->d_tb && b->tb_words < per_chunk * (size_t)tbs) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
-                if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tbs)) return DPX_ERR_NOMEM; b->tb_words = per_chunk * (size_t)tbs; }
-                b->stats.traceback_bytes = (uint64_t)n * tbs * 4;
-            }
-            BandArgs a{};
-            a.pairs = b->d_pairs; a.order = b->d_order; a.qs = b->d_band_qs; a.rs = b->d_band_rs; a.qs_len = qs_len; a.rs_len = rs_len;
-            a.W = band; a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.gadd = pl.gadd; a.zerog = pl.zerog; a.kb = pl.kb; a.kmul = 1u << pl.kb;
-            a.one = 1u; a.four = 4u; a.sixteen = 16u; a.minus1 = 0xffffffffu; a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
-            b->stats.kernel_id = DPX_KERNEL_BAND_S32;
-            int c = 0;
-            for (size_t first = 0; first < n; first += per_chunk, ++c) {
-                a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
-                a.counter = counters + (c % 64);
-                CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-                cudaEvent_t s, e;
-                { int r = add_event_pair(0, &s, &e); if (r) return r; }
-                CU(cudaEventRecord(s, st));
-                { int r = launch_band_any(ctx, st, a, want_strings); if (r) return r; }
-                CU(cudaEventRecord(e, st));
-                b->stats.kernel_launches++;
-                if (want_strings) {
-                    BandBtArgs t{};
-                    t.blob = b->d_blob; t.blob_lo = b->d_blob_alloc; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count; t.W = band;
-                    t.scores = b->d_scores; t.end_rc = b->d_end_rc; t.tb = b->d_tb; t.tb_stride = tbs;
-                    t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
-                    { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
-                    CU(cudaEventRecord(s, st));
-                    const size_t bt_smem = (size_t)BAND_BT_SMEM_WORDS * sizeof(uint32_t);
-                    CU(cudaFuncSetAttribute(band_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
-                    band_bt_kernel<<<(a.count + 31) / 32, 32, bt_smem, st>>>(t);
-                    CU(cudaGetLastError());
-                    CU(cudaEventRecord(e, st));
-                    b->stats.kernel_launches++;
-                }
-            }
-            CU(cudaEventRecord(b->ev_end, st));
-            return DPX_OK;
-        }
-    }
-
-    // ---- general path: warp-per-pair wavefront (+ traceback and GPU backtrack) ----------------------------
-    const unsigned long long tb_stride = want_strings ? WfGeom::make(K, CB, b->max_q, b->max_r, band).words() : 0;
-    size_t per_chunk = n;
-    if (want_strings) {
-        per_chunk = std::max<size_t>(1, std::min<size_t>(n, (ctx->tb_budget_bytes / 4) / std::max<unsigned long long>(tb_stride, 1)));
-        if (b->d_tb && b->tb_words < per_chunk * (size_t)tb_stride) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
-        if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, per_chunk * (size_t)tb_stride)) return DPX_ERR_NOMEM; b->tb_words = per_chunk * (size_t)tb_stride; }
-        b->stats.traceback_bytes = (uint64_t)n * tb_stride * 4;
-    }
-
-    WfArgs a{};
-    a.blob = b->d_blob; a.pairs = b->d_pairs; a.order = b->d_order;
-    a.match = p->match; a.mismatch = p->mismatch; a.go = p->gap_open; a.ge = p->gap_extend; a.band = band;
-    a.scores = b->d_scores; a.end_rc = b->d_end_rc;
-    a.tb = want_strings ? b->d_tb : nullptr; a.tb_stride = tb_stride;
-    a.rmax_p1 = b->max_r + 1;
-    a.boundary_stride = 2LL * (b->max_r + 1);
-    int blocks = 0;
-    { int r = dispatch_wf(ctx, st, algo, want_strings, K, a, 0, true, (int)std::min<size_t>(n, 1u << 30), &blocks); if (r) return r; }
-    const size_t need = (size_t)blocks * 4 * (size_t)a.boundary_stride;
-    if (ctx->boundary_ints[b->lane] < need) {
-        if (ctx->boundary[b->lane]) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->boundary[b->lane]); ctx->boundary[b->lane] = nullptr; ctx->boundary_ints[b->lane] = 0; }
-        CU(cudaMalloc(&ctx->boundary[b->lane], need * sizeof(int32_t))); ctx->boundary_ints[b->lane] = need;
-    }
-    a.boundary = ctx->boundary[b->lane];
-
-    int c = 0;
-    for (size_t first = 0; first < n; first += per_chunk, ++c) {
-        a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
-        a.counter = counters + (c % 64);
-        CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), st));
-        cudaEvent_t s, e;
-        { int r = add_event_pair(0, &s, &e); if (r) return r; }
-        CU(cudaEventRecord(s, st));
-        dispatch_wf(ctx, st, algo, want_strings, K, a, blocks, false, 0, nullptr);
-        CU(cudaGetLastError());
-        CU(cudaEventRecord(e, st));
-        b->stats.kernel_launches++;
-        if (want_strings) {
-            BtArgs t{};
-            t.blob = b->d_blob; t.pairs = b->d_pairs; t.order = a.order; t.first = a.first; t.count = a.count;
-            t.K = K; t.band = band; t.scores = b->d_scores; t.end_rc = b->d_end_rc; t.tb = b->d_tb; t.tb_stride = tb_stride;
-            t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
-            { int r = add_event_pair(1, &s, &e); if (r) return r; }
-            CU(cudaEventRecord(s, st));
-            const int bt_blocks = (a.count + 127) / 128;
-            switch (algo) {
-                case DPX_ALGO_LNW: bt_walk_kernel<DPX_ALGO_LNW><<<bt_blocks, 128, 0, st>>>(t); break;
-                case DPX_ALGO_ANW: bt_walk_kernel<DPX_ALGO_ANW><<<bt_blocks, 128, 0, st>>>(t); break;
-                case DPX_ALGO_LSW: bt_walk_kernel<DPX_ALGO_LSW><<<bt_blocks, 128, 0, st>>>(t); break;
-                case DPX_ALGO_BSW: bt_walk_kernel<DPX_ALGO_BSW><<<bt_blocks, 128, 0, st>>>(t); break;
-            }
-            CU(cudaGetLastError());
-            CU(cudaEventRecord(e, st));
-            b->stats.kernel_launches++;
-        }
-    }
-    CU(cudaEventRecord(b->ev_end, st));
-    return DPX_OK;
-}
-
-// D2H of scores / end cells into caller memory at their final place; asynchronous.
-static int batch_fetch_async(dpx_batch* b, int32_t* scores, int32_t* end_rc) {
-    dpx_ctx* ctx = b->ctx;
-    const size_t n = b->n_pairs;
-    if (scores && n) CU(cudaMemcpyAsync(scores, b->d_scores, n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
-    if (end_rc && n) CU(cudaMemcpyAsync(end_rc, b->d_end_rc, 2 * n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
-    return DPX_OK;
-}
-
-// ---- one long pair on one GPU: systolic array of warps over column blocks (longpair.cuh) ------------------------
-struct LongPlan { int K; int capacity_warps; };
-
-// mode bits: 1 = PACK (the travelling H and the query base share one 32-bit shuffle word; needs H < 2^23),
-//            2 = TABLE (2-bit coded sequences, per-column score table; needs <= 4 symbols and int8 scores)
-template <int K, bool PACK, bool TABLE>
-static int long_capacity(dpx_ctx* ctx, int* warps) {
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK, TABLE>, 128, 0));
-    *warps = per_sm * ctx->sm_count * 4;
-    return DPX_OK;
-}
-
-template <int K, bool PACK, bool TABLE>
-static int long_launch(dpx_ctx* ctx, const LongArgs& a, cudaStream_t st) {
-    const int blocks = (a.nwarps + 3) / 4;
-    void* kargs[] = {(void*)&a};
-    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK, TABLE>, dim3(blocks), dim3(128), kargs, 0, st));
-    return DPX_OK;
-}
-
-template <int K>
-static int long_launch_m(dpx_ctx* ctx, int mode, const LongArgs& a, cudaStream_t st) {
-    switch (mode & 3) {
-        case 0: return long_launch<K, false, false>(ctx, a, st);
-        case 1: return long_launch<K, true, false>(ctx, a, st);
-        case 2: return long_launch<K, false, true>(ctx, a, st);
-        default: return long_launch<K, true, true>(ctx, a, st);
-    }
-}
-template <int K>
-static int long_capacity_m(dpx_ctx* ctx, int mode, int* warps) {
-    switch (mode & 3) {
-        case 0: return long_capacity<K, false, false>(ctx, warps);
-        case 1: return long_capacity<K, true, false>(ctx, warps);
-        case 2: return long_capacity<K, false, true>(ctx, warps);
-        default: return long_capacity<K, true, true>(ctx, warps);
-    }
-}
-
-static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaStream_t st) {
-    switch (K) {
-        case 2: return long_launch_m<2>(ctx, mode, a, st);
-        case 4: return long_launch_m<4>(ctx, mode, a, st);
-        case 8: return long_launch_m<8>(ctx, mode, a, st);
-        case 32: return long_launch_m<32>(ctx, mode, a, st);
-        default: return long_launch_m<16>(ctx, mode, a, st);
-    }
-}
-
-static int long_capacity_k(dpx_ctx* ctx, int K, int mode, int* warps) {
-    switch (K) {
-        case 2: return long_capacity_m<2>(ctx, mode, warps);
-        case 4: return long_capacity_m<4>(ctx, mode, warps);
-        case 8: return long_capacity_m<8>(ctx, mode, warps);
-        case 32: return long_capacity_m<32>(ctx, mode, warps);
-        default: return long_capacity_m<16>(ctx, mode, warps);
-    }
-}
-
-// Byte -> 2-bit code map over both sequences of a long pair; returns the number of distinct symbols (codes are only
-// meaningful when it is <= 4).  Host pass over a few MB, off the kernel's path.
-static int long_alphabet(const char* ref, size_t R, const char* qry, size_t Q, uint8_t code[256]) {
-    bool present[256] = {false};
-    for (size_t i = 0; i < R; ++i) present[(uint8_t)ref[i]] = true;
-    for (size_t i = 0; i < Q; ++i) present[(uint8_t)qry[i]] = true;
-    int n = 0;
-    for (int c = 0; c < 256; ++c) { code[c] = 0; if (present[c]) code[c] = (uint8_t)(n++ & 3); }
-    return n;
-}
-
-static bool long_table_ok(const dpx_params* p, size_t R, size_t Q) {
-    const int ms = p->match - p->gap_open, xs = p->mismatch - p->gap_open;
-    // int8 table entries; the row-maximum keys are h*16 + column, so h must stay below 2^27
-    return ms >= -128 && ms <= 127 && xs >= -128 && xs <= 127 && p->match > 0 &&
-           (long double)p->match * (long double)std::min(R, Q) < 1.3e8L;
-}
-
-static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
-    return (long double)p->match * (long double)std::min(R, Q) < 8.0e6L && p->match > 0;
-}
-
-static long long pow2_at_least(long long v) { long long p = 64; while (p < v) p <<= 1; return p; }
-
-// K: columns per lane.  Measured on B200 (tools/long_sweep.py): with at most one warp per SM sub-partition a row step costs
-// L(K) = 172 / 296 / 344 cycles for K = 8 / 16 / 32 (a dependent chain of 2 DPX ops per cell plus the shuffle / ring overhead of
-// the step); with w warps per sub-partition it stretches by 1 + 0.64 (w - 1) (1 + 1.43 (w - 1) at K = 32, whose 127 registers
-// leave less room to overlap).  The chain advances one row per step, so take the K that minimises the step time; ties go to the
-// wider lane (fewer warps = shorter pipeline fill).  Narrower lanes (K = 4, 2) only pay for references of a few thousand bases,
-// where they are what spreads the work over more than a handful of warps.
-static int long_pick_k(dpx_ctx* ctx, long long R_local, bool allow32 = false) {
-    int best_k = 16; double best = 1e300;
-    if (R_local < 4096) return R_local < 1024 ? 2 : 4;
-    for (int K : {32, 16, 8}) {
-        if (K == 32 && !allow32) continue;            // 32 columns per lane: score-table kernels only, keys h * 32 + column must fit int32
-        const double L = K == 32 ? 344.0 : K == 16 ? 296.0 : 172.0;
-        const double w = (double)((R_local + 32LL * K - 1) / (32LL * K)) / (4.0 * ctx->sm_count);
-        const double cost = L * (w <= 1.0 ? 1.0 : 1.0 + (K == 32 ? 1.43 : 0.64) * (w - 1.0));
-        if (cost < best * 0.999) { best = cost; best_k = K; }
-    }
-    return best_k;
-}
-
-static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
-                            int32_t* score, int64_t* end_row, int64_t* end_col) {
-    cudaStream_t st = ctx->stream;
-    uint8_t code[256];
-    const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
-    int K = long_pick_k(ctx, (long long)R, table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || k == 32) K = k; }   // tests
-    int capacity = 0;
-    const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
-    { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
-    if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
-    if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
-    const long long CW = 32LL * K;
-    const long long nw_total = ((long long)R + CW - 1) / CW;
-    const long long passes = (nw_total + capacity - 1) / capacity;
-    const long long nw_pass = (nw_total + passes - 1) / passes;
-    const long long RING = 2048;
-
-    uint8_t *d_ref = nullptr, *d_qry = nullptr;
-    unsigned long long *d_rings = nullptr, *d_full[2] = {nullptr, nullptr}; int32_t* d_bs = nullptr;
-    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
-    LongChan* d_chans = nullptr; int* d_err = nullptr;
-    auto cleanup = [&]() {
-        cudaStreamSynchronize(st);
-        DevPool& P = ctx->pool;
-        P.release(d_ref); P.release(d_qry); P.release(d_rings); P.release(d_full[0]); P.release(d_full[1]); P.release(d_bs);
-        P.release(d_cnt); P.release(d_br); P.release(d_bc); P.release(d_chans); P.release(d_err);
-    };
-#define LCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
-    bool ok = pool_alloc(ctx, &d_ref, R + 16) && pool_alloc(ctx, &d_qry, Q + 16) && pool_alloc(ctx, &d_rings, (size_t)(nw_pass * RING)) &&
-              pool_alloc(ctx, &d_cnt, (size_t)(2 * (nw_pass + 2))) && pool_alloc(ctx, &d_bs, (size_t)nw_pass) &&
-              pool_alloc(ctx, &d_br, (size_t)nw_pass) && pool_alloc(ctx, &d_bc, (size_t)nw_pass) &&
-              pool_alloc(ctx, &d_chans, (size_t)(nw_pass + 1)) && pool_alloc(ctx, &d_err, 1);
-    const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
-    if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
-    if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
-    std::vector<uint8_t> cref, cqry;
-    if (table) {
-        cref.resize(R); cqry.resize(Q);
-        for (size_t i = 0; i < R; ++i) cref[i] = code[(uint8_t)ref[i]];
-        for (size_t i = 0; i < Q; ++i) cqry[i] = code[(uint8_t)qry[i]];
-    }
-    LCU(cudaMemcpyAsync(d_ref, table ? (const char*)cref.data() : ref, R, cudaMemcpyHostToDevice, st));
-    LCU(cudaMemcpyAsync(d_qry, table ? (const char*)cqry.data() : qry, Q, cudaMemcpyHostToDevice, st));
-    LCU(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-    LCU(cudaStreamSynchronize(st));
-
-    int32_t best = 0; long long brow = 0, bcol = 0;
-    std::vector<LongChan> chans((size_t)nw_pass + 1);
-    std::vector<int32_t> h_bs((size_t)nw_pass); std::vector<long long> h_br((size_t)nw_pass), h_bc((size_t)nw_pass);
-    for (long long ps = 0; ps < passes; ++ps) {
-        const long long w0 = ps * nw_pass, nw = std::min(nw_pass, nw_total - w0);
-        if (nw <= 0) break;
-        // credit counters and ring tags start from zero (a tag of 0 never equals a row >= 1)
-        LCU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)(2 * (nw_pass + 2)), st));
-        LCU(cudaMemsetAsync(d_rings, 0, sizeof(unsigned long long) * (size_t)(nw_pass * RING), st));
-        if (ps + 1 < passes) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
-        long long* cred = d_cnt;
-        for (long long c = 0; c <= nw; ++c) {
-            LongChan ch{};
-            if (c == 0) {
-                if (ps > 0) { ch.ring = d_full[(ps - 1) & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
-            } else if (c == nw) {
-                if (ps + 1 < passes) { ch.ring = d_full[ps & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
-            } else {
-                ch.ring = d_rings + (c - 1) * RING; ch.size = RING; ch.credit = cred + c;
-            }
-            chans[(size_t)c] = ch;
-        }
-        LCU(cudaMemcpyAsync(d_chans, chans.data(), sizeof(LongChan) * (size_t)(nw + 1), cudaMemcpyHostToDevice, st));
-        LongArgs a{};
-        a.ref = d_ref; a.qry = d_qry; a.Q = (long long)Q; a.R_local = (long long)R; a.col0 = w0 * CW; a.col_offset = 0;
-        a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open; a.nwarps = (int)nw; a.chans = d_chans;
-        a.best_score = d_bs; a.best_row = d_br; a.best_col = d_bc; a.error_flag = d_err; a.system_scope = 0;
-        a.tab_match = p->match - p->gap_open; a.tab_mismatch = p->mismatch - p->gap_open; a.sixteen = 16u;
-        { int s = long_launch_k(ctx, K, mode, a, st); if (s) { cleanup(); return s; } }
-        LCU(cudaMemcpyAsync(h_bs.data(), d_bs, sizeof(int32_t) * (size_t)nw, cudaMemcpyDeviceToHost, st));
-        LCU(cudaMemcpyAsync(h_br.data(), d_br, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
-        LCU(cudaMemcpyAsync(h_bc.data(), d_bc, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
-        int err = 0;
-        LCU(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
-        LCU(cudaStreamSynchronize(st));
-        if (err) { ctx->err = "long-pair pipeline watchdog fired"; cleanup(); return DPX_ERR_CUDA; }
-        for (long long w = 0; w < nw; ++w) {
-            const int32_t s = h_bs[(size_t)w]; const long long r = h_br[(size_t)w], c = h_bc[(size_t)w];
-            if (s > best || (s == best && s > 0 && (r < brow || (r == brow && c < bcol)))) { best = s; brow = r; bcol = c; }
-        }
-    }
-#undef LCU
-    cleanup();
-    *score = best; if (end_row) *end_row = brow; if (end_col) *end_col = bcol;
-    return DPX_OK;
-}
-
-// ---- multi-GPU mode B: one column stripe of a long pair per GPU -------------------------------------------------
-struct dpx_stripe {
-    dpx_ctx* ctx = nullptr;
-    dpx_params params{};
-    size_t R_local = 0, col_offset = 0, Q = 0;
-    int index = 0, n = 1, K = 8, nw = 0; int mode = 0;
-    static constexpr long long XRING = 65536, RING = 2048;
-    // exchange buffer (own memory, exported over CUDA IPC): [1] out credit (written by the next stripe), inbox ring of
-    // tagged 8-byte entries at byte 128 (written by the previous stripe)
-    char* xbuf = nullptr;
-    char* prev_x = nullptr; char* next_x = nullptr;          // neighbours' exchange buffers (peer mappings)
-    uint8_t *d_ref = nullptr, *d_qry = nullptr;
-    unsigned long long* d_rings = nullptr; int32_t* d_bs = nullptr;
-    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
-    LongChan* d_chans = nullptr; int* d_err = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    bool launched = false;
-};
+#include "host_long.cuh"
 
 extern "C" {
 
@@ -1656,180 +909,6 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     return status;
 }
 
-int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_stripe, size_t R_local, size_t col_offset,
-                      const char* qry, size_t Q, int stripe_index, int n_stripes, dpx_stripe** out) {
-    if (!ctx || !params || !out || !ref_stripe || !qry || R_local == 0 || Q == 0 || n_stripes < 1 || stripe_index < 0 || stripe_index >= n_stripes) return DPX_ERR_INVALID;
-    if (params->algo != DPX_ALGO_LSW) return DPX_ERR_UNSUPPORTED;
-    if (Q > 0x7ffffff0u || (long double)params->match * (long double)Q > 2.0e9L) return DPX_ERR_RANGE;
-    CU(cudaSetDevice(ctx->device));
-    dpx_stripe* s = new dpx_stripe();
-    s->ctx = ctx; s->params = *params; s->R_local = R_local; s->col_offset = col_offset; s->Q = Q; s->index = stripe_index; s->n = n_stripes;
-    auto fail = [&](int st) { dpx_stripe_free(s); return st; };
-    // The code map must be identical on every rank, so it is fixed instead of data-derived: digits '0'..'3' and A/C/G/T
-    // (either case) map to 0..3; any other byte in this rank's data switches this stripe to the byte-compare kernel, which
-    // is still exact because all ranks then compare (query byte, reference byte) pairs -- but the QUERY must be coded the
-    // same way everywhere, so TABLE is only used when the whole query and this stripe's reference are inside the map.
-    static const auto fixed_code = [](uint8_t c) -> int {
-        switch (c) { case '0': case 'A': case 'a': return 0; case '1': case 'C': case 'c': return 1;
-                     case '2': case 'G': case 'g': return 2; case '3': case 'T': case 't': return 3; default: return -1; }
-    };
-    bool table = long_table_ok(params, Q, Q) && !getenv("DPX_LONG_NOTABLE");
-    bool digits = false, letters = false;
-    for (size_t i = 0; i < Q && table; ++i) { const uint8_t c = (uint8_t)qry[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
-    for (size_t i = 0; i < R_local && table; ++i) { const uint8_t c = (uint8_t)ref_stripe[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
-    if (digits && letters) table = false;         // '0' and 'A' would collide
-    s->mode = ((long double)params->match * (long double)Q < 8.0e6L && params->match > 0 ? 1 : 0) | (table ? 2 : 0);
-    // lane width: the whole stripe must be one co-resident pass
-    // The right edge a stripe exports is the last column of its last warp, so every stripe but the last must be made of WHOLE
-    // warps: its width has to be a multiple of 32 K.
-    const bool last = stripe_index == n_stripes - 1;
-    auto whole = [&](int k) { return last || R_local % (32ull * (unsigned)k) == 0; };
-    const bool allow32 = table && (long double)params->match * (long double)Q < 6.0e7L && whole(32);
-    int K = long_pick_k(ctx, (long long)R_local, allow32), cap = 0;
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && allow32)) K = k; }
-    while (K > 2 && !whole(K)) K /= 2;
-    if (!whole(K)) { ctx->err = "a stripe that is not the last one must be a multiple of 64 columns wide"; return fail(DPX_ERR_INVALID); }
-    for (;;) {
-        if (long_capacity_k(ctx, K, s->mode, &cap)) return fail(DPX_ERR_CUDA);
-        if ((long long)((R_local + 32ull * K - 1) / (32ull * K)) <= cap || K == (allow32 ? 32 : 16) || !whole(2 * K)) break;
-        K *= 2;
-    }
-    s->K = K; s->nw = (int)((R_local + 32ull * K - 1) / (32ull * K));
-    if (s->nw > cap) { ctx->err = "stripe too wide for one co-resident pass"; return fail(DPX_ERR_RANGE); }
-    const size_t nw = (size_t)s->nw;
-    bool ok = cudaMalloc(&s->xbuf, 128 + sizeof(unsigned long long) * (size_t)dpx_stripe::XRING) == cudaSuccess &&
-              cudaMalloc(&s->d_ref, R_local + 16) == cudaSuccess && cudaMalloc(&s->d_qry, Q + 16) == cudaSuccess &&
-              cudaMalloc(&s->d_rings, sizeof(unsigned long long) * nw * (size_t)dpx_stripe::RING) == cudaSuccess &&
-              cudaMalloc(&s->d_cnt, sizeof(long long) * 2 * (nw + 2)) == cudaSuccess &&
-              cudaMalloc(&s->d_bs, sizeof(int32_t) * nw) == cudaSuccess && cudaMalloc(&s->d_br, sizeof(long long) * nw) == cudaSuccess &&
-              cudaMalloc(&s->d_bc, sizeof(long long) * nw) == cudaSuccess && cudaMalloc(&s->d_chans, sizeof(LongChan) * (nw + 1)) == cudaSuccess &&
-              cudaMalloc(&s->d_err, sizeof(int)) == cudaSuccess &&
-              cudaEventCreate(&s->e0) == cudaSuccess && cudaEventCreate(&s->e1) == cudaSuccess;
-    if (!ok) { cudaGetLastError(); return fail(DPX_ERR_NOMEM); }
-    std::vector<uint8_t> cref, cqry;
-    if (table) {
-        cref.resize(R_local); cqry.resize(Q);
-        for (size_t i = 0; i < R_local; ++i) cref[i] = (uint8_t)fixed_code((uint8_t)ref_stripe[i]);
-        for (size_t i = 0; i < Q; ++i) cqry[i] = (uint8_t)fixed_code((uint8_t)qry[i]);
-    }
-    if (cudaMemcpy(s->d_ref, table ? (const char*)cref.data() : ref_stripe, R_local, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(s->d_qry, table ? (const char*)cqry.data() : qry, Q, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemset(s->xbuf, 0, 128) != cudaSuccess) return fail(DPX_ERR_CUDA);
-    *out = s;
-    return DPX_OK;
-}
-
-int dpx_stripe_export(dpx_stripe* s, void* handle) {
-    if (!s || !handle) return DPX_ERR_INVALID;
-    dpx_ctx* ctx = s->ctx;
-    static_assert(sizeof(cudaIpcMemHandle_t) == DPX_IPC_HANDLE_BYTES, "IPC handle size");
-    CU(cudaSetDevice(ctx->device));
-    cudaIpcMemHandle_t h;
-    CU(cudaIpcGetMemHandle(&h, s->xbuf));
-    memcpy(handle, &h, sizeof(h));
-    return DPX_OK;
-}
-
-int dpx_stripe_connect(dpx_stripe* s, const void* prev_handle, const void* next_handle) {
-    if (!s) return DPX_ERR_INVALID;
-    dpx_ctx* ctx = s->ctx;
-    CU(cudaSetDevice(ctx->device));
-    if (prev_handle && s->index > 0) {
-        cudaIpcMemHandle_t h; memcpy(&h, prev_handle, sizeof(h));
-        CU(cudaIpcOpenMemHandle((void**)&s->prev_x, h, cudaIpcMemLazyEnablePeerAccess));
-    }
-    if (next_handle && s->index + 1 < s->n) {
-        cudaIpcMemHandle_t h; memcpy(&h, next_handle, sizeof(h));
-        CU(cudaIpcOpenMemHandle((void**)&s->next_x, h, cudaIpcMemLazyEnablePeerAccess));
-    }
-    if ((s->index > 0 && !s->prev_x) || (s->index + 1 < s->n && !s->next_x)) return DPX_ERR_INVALID;
-    // channels: [0] = inbox (own memory; credit goes back to prev), [1..nw-1] local rings, [nw] = next stripe's inbox (peer)
-    const long long nw = s->nw;
-    std::vector<LongChan> ch((size_t)nw + 1);
-    long long* cred = s->d_cnt;
-    for (long long c = 0; c <= nw; ++c) {
-        LongChan x{};
-        if (c == 0) {
-            if (s->index > 0) { x.ring = (unsigned long long*)(s->xbuf + 128); x.size = dpx_stripe::XRING; x.credit = (long long*)(s->prev_x + 8); }
-        } else if (c == nw) {
-            if (s->index + 1 < s->n) { x.ring = (unsigned long long*)(s->next_x + 128); x.size = dpx_stripe::XRING; x.credit = (long long*)(s->xbuf + 8); }
-        } else { x.ring = s->d_rings + (c - 1) * dpx_stripe::RING; x.size = dpx_stripe::RING; x.credit = cred + c; }
-        ch[(size_t)c] = x;
-    }
-    CU(cudaMemcpy(s->d_chans, ch.data(), sizeof(LongChan) * (size_t)(nw + 1), cudaMemcpyHostToDevice));
-    return DPX_OK;
-}
-
-int dpx_stripe_reset(dpx_stripe* s) {
-    if (!s) return DPX_ERR_INVALID;
-    dpx_ctx* ctx = s->ctx;
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaMemset(s->xbuf, 0, 128 + sizeof(unsigned long long) * (size_t)dpx_stripe::XRING));     // credit + inbox tags
-    CU(cudaMemset(s->d_cnt, 0, sizeof(long long) * 2 * ((size_t)s->nw + 2)));
-    CU(cudaMemset(s->d_rings, 0, sizeof(unsigned long long) * (size_t)s->nw * (size_t)dpx_stripe::RING));
-    CU(cudaMemset(s->d_err, 0, sizeof(int)));
-    CU(cudaDeviceSynchronize());
-    return DPX_OK;
-}
-
-int dpx_stripe_run(dpx_stripe* s) {
-    if (!s) return DPX_ERR_INVALID;
-    dpx_ctx* ctx = s->ctx;
-    CU(cudaSetDevice(ctx->device));
-    LongArgs a{};
-    a.ref = s->d_ref; a.qry = s->d_qry; a.Q = (long long)s->Q; a.R_local = (long long)s->R_local; a.col0 = 0; a.col_offset = (long long)s->col_offset;
-    a.match = s->params.match; a.mismatch = s->params.mismatch; a.gap = s->params.gap_open; a.nwarps = s->nw; a.chans = s->d_chans;
-    a.best_score = s->d_bs; a.best_row = s->d_br; a.best_col = s->d_bc; a.error_flag = s->d_err; a.system_scope = s->n > 1;
-    a.tab_match = s->params.match - s->params.gap_open; a.tab_mismatch = s->params.mismatch - s->params.gap_open; a.sixteen = 16u;
-    CU(cudaEventRecord(s->e0, ctx->stream));
-    { int st = long_launch_k(ctx, s->K, s->mode, a, ctx->stream); if (st) return st; }
-    CU(cudaEventRecord(s->e1, ctx->stream));
-    s->launched = true;
-    return DPX_OK;
-}
-
-int dpx_stripe_result(dpx_stripe* s, int32_t* score, int64_t* end_row, int64_t* end_col, double* kernel_ms) {
-    if (!s || !s->launched || !score) return DPX_ERR_INVALID;
-    dpx_ctx* ctx = s->ctx;
-    CU(cudaSetDevice(ctx->device));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const size_t nw = (size_t)s->nw;
-    std::vector<int32_t> bs(nw); std::vector<long long> br(nw), bc(nw); int err = 0;
-    CU(cudaMemcpy(bs.data(), s->d_bs, sizeof(int32_t) * nw, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(br.data(), s->d_br, sizeof(long long) * nw, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(bc.data(), s->d_bc, sizeof(long long) * nw, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(&err, s->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (err) { ctx->err = "stripe pipeline watchdog fired (a neighbour never produced / consumed)"; return DPX_ERR_CUDA; }
-    int32_t best = 0; long long r0 = 0, c0 = 0;
-    for (size_t w = 0; w < nw; ++w)
-        if (bs[w] > best || (bs[w] == best && best > 0 && (br[w] < r0 || (br[w] == r0 && bc[w] < c0)))) { best = bs[w]; r0 = br[w]; c0 = bc[w]; }
-    *score = best; if (end_row) *end_row = r0; if (end_col) *end_col = c0;
-    if (kernel_ms) { float ms = 0; CU(cudaEventElapsedTime(&ms, s->e0, s->e1)); *kernel_ms = ms; }
-    return DPX_OK;
-}
-
-void dpx_stripe_free(dpx_stripe* s) {
-    if (!s) return;
-    cudaSetDevice(s->ctx->device);
-    cudaDeviceSynchronize();
-    if (s->prev_x) cudaIpcCloseMemHandle(s->prev_x);
-    if (s->next_x) cudaIpcCloseMemHandle(s->next_x);
-    cudaFree(s->xbuf); cudaFree(s->d_ref); cudaFree(s->d_qry); cudaFree(s->d_rings); cudaFree(s->d_cnt); cudaFree(s->d_bs);
-    cudaFree(s->d_br); cudaFree(s->d_bc); cudaFree(s->d_chans); cudaFree(s->d_err);
-    if (s->e0) cudaEventDestroy(s->e0);
-    if (s->e1) cudaEventDestroy(s->e1);
-    delete s;
-}
-
-int dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params, const char* ref, size_t R, const char* qry, size_t Q,
-                        int32_t* score, int64_t* end_row, int64_t* end_col) {
-    if (!ctx || !params || !score || (!ref && R) || (!qry && Q)) return DPX_ERR_INVALID;
-    if (params->algo != DPX_ALGO_LSW) return DPX_ERR_UNSUPPORTED;
-    CU(cudaSetDevice(ctx->device));
-    *score = 0; if (end_row) *end_row = 0; if (end_col) *end_col = 0;
-    if (R == 0 || Q == 0) return DPX_OK;
-    if ((long double)params->match * (long double)std::min(R, Q) > 2.0e9L || Q > 0x7ffffff0u || R > 0x7ffffff0u) return DPX_ERR_RANGE;     // int32 scores / rows
-    return long_pair_single(ctx, params, ref, R, qry, Q, score, end_row, end_col);
-}
+#include "host_long_abi.cuh"
 
 }  // extern "C"

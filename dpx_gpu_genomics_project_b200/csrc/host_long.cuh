@@ -1,0 +1,221 @@
+// host_long.cuh — host side of the long-pair path (csrc/longpair.cuh): kernel dispatch over (K, PACK, TABLE), the lane-width
+// model, the single-GPU driver and the per-GPU stripe object of multi-GPU mode B.  Included by dpxalign.cu after the context,
+// pool and CU() definitions; not a stand-alone header.
+#pragma once
+
+// ---- one long pair on one GPU: systolic array of warps over column blocks (longpair.cuh) ------------------------
+struct LongPlan { int K; int capacity_warps; };
+
+// mode bits: 1 = PACK (the travelling H and the query base share one 32-bit shuffle word; needs H < 2^23),
+//            2 = TABLE (2-bit coded sequences, per-column score table; needs <= 4 symbols and int8 scores)
+template <int K, bool PACK, bool TABLE>
+static int long_capacity(dpx_ctx* ctx, int* warps) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK, TABLE>, 128, 0));
+    *warps = per_sm * ctx->sm_count * 4;
+    return DPX_OK;
+}
+
+template <int K, bool PACK, bool TABLE>
+static int long_launch(dpx_ctx* ctx, const LongArgs& a, cudaStream_t st) {
+    const int blocks = (a.nwarps + 3) / 4;
+    void* kargs[] = {(void*)&a};
+    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK, TABLE>, dim3(blocks), dim3(128), kargs, 0, st));
+    return DPX_OK;
+}
+
+template <int K>
+static int long_launch_m(dpx_ctx* ctx, int mode, const LongArgs& a, cudaStream_t st) {
+    switch (mode & 3) {
+        case 0: return long_launch<K, false, false>(ctx, a, st);
+        case 1: return long_launch<K, true, false>(ctx, a, st);
+        case 2: return long_launch<K, false, true>(ctx, a, st);
+        default: return long_launch<K, true, true>(ctx, a, st);
+    }
+}
+template <int K>
+static int long_capacity_m(dpx_ctx* ctx, int mode, int* warps) {
+    switch (mode & 3) {
+        case 0: return long_capacity<K, false, false>(ctx, warps);
+        case 1: return long_capacity<K, true, false>(ctx, warps);
+        case 2: return long_capacity<K, false, true>(ctx, warps);
+        default: return long_capacity<K, true, true>(ctx, warps);
+    }
+}
+
+static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaStream_t st) {
+    switch (K) {
+        case 2: return long_launch_m<2>(ctx, mode, a, st);
+        case 4: return long_launch_m<4>(ctx, mode, a, st);
+        case 8: return long_launch_m<8>(ctx, mode, a, st);
+        case 32: return long_launch_m<32>(ctx, mode, a, st);
+        default: return long_launch_m<16>(ctx, mode, a, st);
+    }
+}
+
+static int long_capacity_k(dpx_ctx* ctx, int K, int mode, int* warps) {
+    switch (K) {
+        case 2: return long_capacity_m<2>(ctx, mode, warps);
+        case 4: return long_capacity_m<4>(ctx, mode, warps);
+        case 8: return long_capacity_m<8>(ctx, mode, warps);
+        case 32: return long_capacity_m<32>(ctx, mode, warps);
+        default: return long_capacity_m<16>(ctx, mode, warps);
+    }
+}
+
+// Byte -> 2-bit code map over both sequences of a long pair; returns the number of distinct symbols (codes are only
+// meaningful when it is <= 4).  Host pass over a few MB, off the kernel's path.
+static int long_alphabet(const char* ref, size_t R, const char* qry, size_t Q, uint8_t code[256]) {
+    bool present[256] = {false};
+    for (size_t i = 0; i < R; ++i) present[(uint8_t)ref[i]] = true;
+    for (size_t i = 0; i < Q; ++i) present[(uint8_t)qry[i]] = true;
+    int n = 0;
+    for (int c = 0; c < 256; ++c) { code[c] = 0; if (present[c]) code[c] = (uint8_t)(n++ & 3); }
+    return n;
+}
+
+static bool long_table_ok(const dpx_params* p, size_t R, size_t Q) {
+    const int ms = p->match - p->gap_open, xs = p->mismatch - p->gap_open;
+    // int8 table entries; the row-maximum keys are h*16 + column, so h must stay below 2^27
+    return ms >= -128 && ms <= 127 && xs >= -128 && xs <= 127 && p->match > 0 &&
+           (long double)p->match * (long double)std::min(R, Q) < 1.3e8L;
+}
+
+static bool long_can_pack(const dpx_params* p, size_t R, size_t Q) {
+    return (long double)p->match * (long double)std::min(R, Q) < 8.0e6L && p->match > 0;
+}
+
+static long long pow2_at_least(long long v) { long long p = 64; while (p < v) p <<= 1; return p; }
+
+// K: columns per lane.  Measured on B200 (tools/long_sweep.py): with at most one warp per SM sub-partition a row step costs
+// L(K) = 172 / 296 / 344 cycles for K = 8 / 16 / 32 (a dependent chain of 2 DPX ops per cell plus the shuffle / ring overhead of
+// the step); with w warps per sub-partition it stretches by 1 + 0.64 (w - 1) (1 + 1.43 (w - 1) at K = 32, whose 127 registers
+// leave less room to overlap).  The chain advances one row per step, so take the K that minimises the step time; ties go to the
+// wider lane (fewer warps = shorter pipeline fill).  Narrower lanes (K = 4, 2) only pay for references of a few thousand bases,
+// where they are what spreads the work over more than a handful of warps.
+static int long_pick_k(dpx_ctx* ctx, long long R_local, bool allow32 = false) {
+    int best_k = 16; double best = 1e300;
+    if (R_local < 4096) return R_local < 1024 ? 2 : 4;
+    for (int K : {32, 16, 8}) {
+        if (K == 32 && !allow32) continue;            // 32 columns per lane: score-table kernels only, keys h * 32 + column must fit int32
+        const double L = K == 32 ? 344.0 : K == 16 ? 296.0 : 172.0;
+        const double w = (double)((R_local + 32LL * K - 1) / (32LL * K)) / (4.0 * ctx->sm_count);
+        const double cost = L * (w <= 1.0 ? 1.0 : 1.0 + (K == 32 ? 1.43 : 0.64) * (w - 1.0));
+        if (cost < best * 0.999) { best = cost; best_k = K; }
+    }
+    return best_k;
+}
+
+static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
+                            int32_t* score, int64_t* end_row, int64_t* end_col) {
+    cudaStream_t st = ctx->stream;
+    uint8_t code[256];
+    const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
+    int K = long_pick_k(ctx, (long long)R, table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || k == 32) K = k; }   // tests
+    int capacity = 0;
+    const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
+    { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
+    if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
+    if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
+    const long long CW = 32LL * K;
+    const long long nw_total = ((long long)R + CW - 1) / CW;
+    const long long passes = (nw_total + capacity - 1) / capacity;
+    const long long nw_pass = (nw_total + passes - 1) / passes;
+    const long long RING = 2048;
+
+    uint8_t *d_ref = nullptr, *d_qry = nullptr;
+    unsigned long long *d_rings = nullptr, *d_full[2] = {nullptr, nullptr}; int32_t* d_bs = nullptr;
+    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
+    LongChan* d_chans = nullptr; int* d_err = nullptr;
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        DevPool& P = ctx->pool;
+        P.release(d_ref); P.release(d_qry); P.release(d_rings); P.release(d_full[0]); P.release(d_full[1]); P.release(d_bs);
+        P.release(d_cnt); P.release(d_br); P.release(d_bc); P.release(d_chans); P.release(d_err);
+    };
+#define LCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
+    bool ok = pool_alloc(ctx, &d_ref, R + 16) && pool_alloc(ctx, &d_qry, Q + 16) && pool_alloc(ctx, &d_rings, (size_t)(nw_pass * RING)) &&
+              pool_alloc(ctx, &d_cnt, (size_t)(2 * (nw_pass + 2))) && pool_alloc(ctx, &d_bs, (size_t)nw_pass) &&
+              pool_alloc(ctx, &d_br, (size_t)nw_pass) && pool_alloc(ctx, &d_bc, (size_t)nw_pass) &&
+              pool_alloc(ctx, &d_chans, (size_t)(nw_pass + 1)) && pool_alloc(ctx, &d_err, 1);
+    const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
+    if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
+    if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
+    std::vector<uint8_t> cref, cqry;
+    if (table) {
+        cref.resize(R); cqry.resize(Q);
+        for (size_t i = 0; i < R; ++i) cref[i] = code[(uint8_t)ref[i]];
+        for (size_t i = 0; i < Q; ++i) cqry[i] = code[(uint8_t)qry[i]];
+    }
+    LCU(cudaMemcpyAsync(d_ref, table ? (const char*)cref.data() : ref, R, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemcpyAsync(d_qry, table ? (const char*)cqry.data() : qry, Q, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    LCU(cudaStreamSynchronize(st));
+
+    int32_t best = 0; long long brow = 0, bcol = 0;
+    std::vector<LongChan> chans((size_t)nw_pass + 1);
+    std::vector<int32_t> h_bs((size_t)nw_pass); std::vector<long long> h_br((size_t)nw_pass), h_bc((size_t)nw_pass);
+    for (long long ps = 0; ps < passes; ++ps) {
+        const long long w0 = ps * nw_pass, nw = std::min(nw_pass, nw_total - w0);
+        if (nw <= 0) break;
+        // credit counters and ring tags start from zero (a tag of 0 never equals a row >= 1)
+        LCU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)(2 * (nw_pass + 2)), st));
+        LCU(cudaMemsetAsync(d_rings, 0, sizeof(unsigned long long) * (size_t)(nw_pass * RING), st));
+        if (ps + 1 < passes) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
+        long long* cred = d_cnt;
+        for (long long c = 0; c <= nw; ++c) {
+            LongChan ch{};
+            if (c == 0) {
+                if (ps > 0) { ch.ring = d_full[(ps - 1) & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
+            } else if (c == nw) {
+                if (ps + 1 < passes) { ch.ring = d_full[ps & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
+            } else {
+                ch.ring = d_rings + (c - 1) * RING; ch.size = RING; ch.credit = cred + c;
+            }
+            chans[(size_t)c] = ch;
+        }
+        LCU(cudaMemcpyAsync(d_chans, chans.data(), sizeof(LongChan) * (size_t)(nw + 1), cudaMemcpyHostToDevice, st));
+        LongArgs a{};
+        a.ref = d_ref; a.qry = d_qry; a.Q = (long long)Q; a.R_local = (long long)R; a.col0 = w0 * CW; a.col_offset = 0;
+        a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open; a.nwarps = (int)nw; a.chans = d_chans;
+        a.best_score = d_bs; a.best_row = d_br; a.best_col = d_bc; a.error_flag = d_err; a.system_scope = 0;
+        a.tab_match = p->match - p->gap_open; a.tab_mismatch = p->mismatch - p->gap_open; a.sixteen = 16u;
+        { int s = long_launch_k(ctx, K, mode, a, st); if (s) { cleanup(); return s; } }
+        LCU(cudaMemcpyAsync(h_bs.data(), d_bs, sizeof(int32_t) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(h_br.data(), d_br, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(h_bc.data(), d_bc, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
+        int err = 0;
+        LCU(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        if (err) { ctx->err = "long-pair pipeline watchdog fired"; cleanup(); return DPX_ERR_CUDA; }
+        for (long long w = 0; w < nw; ++w) {
+            const int32_t s = h_bs[(size_t)w]; const long long r = h_br[(size_t)w], c = h_bc[(size_t)w];
+            if (s > best || (s == best && s > 0 && (r < brow || (r == brow && c < bcol)))) { best = s; brow = r; bcol = c; }
+        }
+    }
+#undef LCU
+    cleanup();
+    *score = best; if (end_row) *end_row = brow; if (end_col) *end_col = bcol;
+    return DPX_OK;
+}
+
+// ---- multi-GPU mode B: one column stripe of a long pair per GPU -------------------------------------------------
+struct dpx_stripe {
+    dpx_ctx* ctx = nullptr;
+    dpx_params params{};
+    size_t R_local = 0, col_offset = 0, Q = 0;
+    int index = 0, n = 1, K = 8, nw = 0; int mode = 0;
+    static constexpr long long XRING = 65536, RING = 2048;
+    // exchange buffer (own memory, exported over CUDA IPC): [1] out credit (written by the next stripe), inbox ring of
+    // tagged 8-byte entries at byte 128 (written by the previous stripe)
+    char* xbuf = nullptr;
+    char* prev_x = nullptr; char* next_x = nullptr;          // neighbours' exchange buffers (peer mappings)
+    uint8_t *d_ref = nullptr, *d_qry = nullptr;
+    unsigned long long* d_rings = nullptr; int32_t* d_bs = nullptr;
+    long long *d_cnt = nullptr, *d_br = nullptr, *d_bc = nullptr;
+    LongChan* d_chans = nullptr; int* d_err = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool launched = false;
+};
+

@@ -59,6 +59,8 @@ static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, 
     if (!(m > 0 && x < 0 && g < 0)) return false;                 // pads must stay strictly below real cells
     if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
     if (b->max_r > 4096 || b->max_q > 65535) return false;
+    // 16 pair groups per block, each with a boundary row (4 B per column) and a column table (2 B): must fit one block's shared memory
+    if ((size_t)16 * ((size_t)(b->max_r + 10) * 4 + (size_t)(b->max_r + 36) * 2) > (size_t)227 * 1024) return false;
     const int B = std::max(2, -g);
     // position bits: (Hmax + B) << k < 32768; one of the k bits marks the upper row of a row pair, the other
     // k-1 count steps inside blocks of 2^(k-1) steps; at most 256 blocks per pass

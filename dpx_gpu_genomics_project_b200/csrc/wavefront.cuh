@@ -104,6 +104,9 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
             {
                 const int i = i_first - 1;
                 diag0 = (ALGO == DPX_ALGO_LNW) ? i * g : IS_ANW ? (i == 0 ? 0 : a.go + i * ge) : 0;
+                // banded: the window of a later stripe starts at column jstart > 1, and the cell above-left of its first cell,
+                // (s*rows, s*rows - band), sits exactly on the band's edge: it is a real cell of the previous stripe's last row
+                if (BANDED && lane == 0 && s > 0 && jstart > 1) diag0 = bH[jstart - 1];
             }
             int bestH[K], bestJ[K];
             #pragma unroll

@@ -91,6 +91,29 @@ def test_banded_vs_oracle(eng, band):
     gpu_vs_oracle(eng, api.BSW, blob, pairs, match=3, mismatch=-1, gap_open=-2, band=band)
 
 
+@pytest.mark.parametrize("band", [0, 1, 5, 40])
+def test_banded_multi_stripe_queries_on_the_byte_kernel(eng, band):
+    """Queries of several stripes on the general wavefront kernel (8 symbols keep the band kernel out): the cell above-left of a
+    later stripe's first cell lies on the band's edge and belongs to the previous stripe's last row (found by tools/fuzz_gpu.py)."""
+    blob, pairs = random_pairs(0xED9E + band, 40, 700, alphabets=(b"ACGTNacg",))
+    gpu_vs_oracle(eng, api.BSW, blob, pairs, match=2, mismatch=-5, gap_open=-5, band=band)
+
+
+def test_long_reference_short_query_smith_waterman_scores(eng):
+    """A 3 kbp reference with short queries passes the short-read kernel's score-range test but not its shared-memory budget:
+    the batch must fall through to the next kernel instead of failing the launch (found by tools/fuzz_gpu.py)."""
+    rng = synth.Rng(99)
+    r = synth.random_seq(rng, 3100)
+    pp = [(r, r[500:900]), (r[:2600], synth.mutate(rng, r[100:400], 0.05, 0.02, 0.02)), (r[:2500], b"")]
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    for flags in (api.OUT_SCORE, api.OUT_SCORE | api.OUT_END_COORDS):
+        res = eng.align_batch(api.make_params(api.LSW, match=1, mismatch=-2, gap_open=-3, flags=flags), blob, pairs)
+        s, e, _ = ol.align_batch(ol.params(api.LSW, match=1, mismatch=-2, gap_open=-3), blob, pairs, strings=False)
+        assert (res.scores == s).all()
+        if flags & api.OUT_END_COORDS:
+            assert (res.end_row_col == e).all()
+
+
 def test_banded_full_band_equals_lsw_golden(eng):
     p = api.parse_input(os.path.join(GOLD, "shapes.in.txt"))
     res = eng.align_batch(api.make_params(api.BSW, band=600, flags=ALL), p.sequences, p.pairs)

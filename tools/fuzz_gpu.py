@@ -1,0 +1,94 @@
+"""Randomised differential test of the whole library against the CPU oracle (test infrastructure): random alphabets, lengths,
+weights, algorithms, bands and output selections; every result (scores, end cells, strings, formatted text) must be bit-exact.
+usage: python tools/fuzz_gpu.py [seconds] [seed]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+
+import oracle_lib as ol  # noqa: E402
+from dpx_gpu_genomics_project_b200 import api, synth  # noqa: E402
+
+ALPHABETS = [b"0", b"01", b"012", b"0123", b"ACGT", b"01234", b"ACGTN", b"ACGTNacg", b"012345678"]
+
+
+def make_batch(rng, seed):
+    r = synth.Rng(seed)
+    alpha = ALPHABETS[int(rng.integers(len(ALPHABETS)))]
+    shape = int(rng.integers(6))
+    n = int(rng.integers(1, 60))
+    lo, hi = [(0, 40), (1, 150), (100, 320), (200, 700), (900, 1400), (2500, 3300)][shape]
+    if shape >= 4:
+        n = int(rng.integers(1, 6))
+    pp = []
+    for k in range(n):
+        R = int(rng.integers(lo, hi + 1))
+        ref = synth.random_seq(r, R, alpha)
+        mode = int(rng.integers(4))
+        if mode == 0:
+            q = synth.random_seq(r, int(rng.integers(lo, hi + 1)), alpha)
+        elif mode == 1:
+            q = synth.mutate(r, ref, 0.05, 0.02, 0.02, alpha)
+        elif mode == 2:
+            q = synth.mutate(r, ref, 0.2, 0.1, 0.1, alpha)
+        else:
+            a = int(rng.integers(0, max(1, R // 2))); q = ref[a:a + int(rng.integers(0, R + 1))]
+        pp.append((ref, q))
+    return ol.parse_image(synth.pairs_to_file_bytes(pp)), alpha, (lo, hi), n
+
+
+def main():
+    seconds = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 12345
+    rng = np.random.default_rng(seed)
+    eng = api.Engine(0)
+    t_end = time.time() + seconds
+    cases = 0
+    kernels = {}
+    failures = []
+    while time.time() < t_end:
+        (blob, pairs), alpha, span, n = make_batch(rng, int(rng.integers(1 << 30)))
+        algo = int(rng.integers(4))
+        m = int(rng.integers(1, 7)); x = -int(rng.integers(0, 6)); g = -int(rng.integers(1, 8))
+        w = dict(match=m, mismatch=x, gap_open=g)
+        if algo == api.ANW:
+            w["gap_open"] = -int(rng.integers(0, 8)); w["gap_extend"] = -int(rng.integers(0, 4))
+            if w["gap_open"] == 0 and w["gap_extend"] == 0:
+                w["gap_extend"] = -1
+        if algo == api.BSW:
+            w["band"] = int(rng.choice([0, 1, 5, 16, 31, 32, 33, 64, 65, 96, 97, 150]))
+        flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if rng.integers(3) else 0)
+        strings = bool(flags & api.OUT_STRINGS)
+        tag = f"case {cases} seed {seed} algo {algo} w {w} flags {flags} alpha {alpha} span {span} n {n}"
+        try:
+            b = eng.upload(blob, pairs)
+            b.run(api.make_params(algo, flags=flags, **w)); b.sync()
+            kid = b.stats()["kernel_id"]
+            kernels[kid] = kernels.get(kid, 0) + 1
+            tag += f" kernel {kid}"
+            res = b.fetch()
+            b.free()
+            s, e, t = ol.align_batch(ol.params(algo, **w), blob, pairs, strings=strings, threads=16)
+            assert (res.scores == s).all(), f"scores, first bad {np.flatnonzero(res.scores != s)[:5]}"
+            assert (res.end_row_col == e).all(), "end cells"
+            if strings:
+                assert res.strings == t, "strings"
+                if rng.integers(4) == 0:
+                    assert eng.align_batch_text(api.make_params(algo, flags=flags, **w), blob, pairs) == ol.format_text(s, t), "text"
+        except (AssertionError, api.DpxError) as ex:       # keep going: one run should list every distinct failure
+            failures.append(f"{type(ex).__name__}: {ex} :: {tag}")
+            print("FAIL", failures[-1], flush=True)
+            if len(failures) >= 10:
+                break
+        cases += 1
+    if failures:
+        print(f"fuzz FAILED: {len(failures)} of {cases} batches")
+        sys.exit(1)
+    print(f"fuzz ok: {cases} batches in {seconds:.0f} s, kernel ids used {dict(sorted(kernels.items()))}")
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,10 @@ def lib() -> C.CDLL:
     L.dpx_align_long_pair.restype = C.c_int
     L.dpx_align_long_pair.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                       i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dpx_align_long_pair_strings.restype = C.c_int
+    L.dpx_align_long_pair_strings.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
+                                              i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
+                                              C.POINTER(vp), C.POINTER(C.c_size_t), C.POINTER(C.c_double)]
     L.dpx_stripe_create.restype = C.c_int
     L.dpx_stripe_create.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_size_t, C.c_char_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(vp)]
     L.dpx_stripe_export.restype = C.c_int; L.dpx_stripe_export.argtypes = [vp, vp]

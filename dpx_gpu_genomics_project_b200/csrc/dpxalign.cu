@@ -23,6 +23,7 @@
 #include "backtrack.cuh"
 #include "shortread.cuh"
 #include "longpair.cuh"
+#include "longtrace.cuh"
 #include "pairwf.cuh"
 #include "band.cuh"
 

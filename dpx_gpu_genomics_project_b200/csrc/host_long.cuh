@@ -106,13 +106,24 @@ static int long_pick_k(dpx_ctx* ctx, long long R_local, bool allow32 = false) {
     return best_k;
 }
 
+// Checkpoint mode of the forward pass (longtrace.cuh): every channel between two warps is a full-length array, so the right
+// edge of every column block, H[i][(c + 1) * CW] for all rows i, is still there when the kernel has finished.
+struct LongCkpt {
+    unsigned long long* base = nullptr;   // entry (c, i) at base[c * stride + i]: {row tag : 32 | H : 32}
+    long long stride = 0;                 // entries per channel (a power of two > Q)
+    long long n = 0;                      // channels = column blocks - 1
+    int CW = 0;                           // columns per block
+    void free() { if (base) cudaFree(base); base = nullptr; }
+};
+
 static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
-                            int32_t* score, int64_t* end_row, int64_t* end_col) {
+                            int32_t* score, int64_t* end_row, int64_t* end_col, LongCkpt* ck = nullptr) {
     cudaStream_t st = ctx->stream;
     uint8_t code[256];
     const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
-    int K = long_pick_k(ctx, (long long)R, table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || k == 32) K = k; }   // tests
+    // checkpoint mode: the column blocks are the tiles of the traceback, whose directions must fit shared memory: at most 512 wide
+    int K = long_pick_k(ctx, (long long)R, !ck && table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && !ck)) K = k; }   // tests
     int capacity = 0;
     const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
     { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
@@ -140,8 +151,20 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
               pool_alloc(ctx, &d_br, (size_t)nw_pass) && pool_alloc(ctx, &d_bc, (size_t)nw_pass) &&
               pool_alloc(ctx, &d_chans, (size_t)(nw_pass + 1)) && pool_alloc(ctx, &d_err, 1);
     const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
-    if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
+    if (ok && passes > 1 && !ck) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
     if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
+    if (ck) {
+        ck->CW = (int)CW; ck->n = nw_total - 1; ck->stride = FULLSZ; ck->base = nullptr;
+        if (ck->n > 0) {
+            const size_t bytes = sizeof(unsigned long long) * (size_t)ck->n * (size_t)FULLSZ;
+            if (cudaMalloc(&ck->base, bytes) != cudaSuccess) {
+                cudaGetLastError(); ck->base = nullptr; cleanup();
+                ctx->err = "long-pair traceback: " + std::to_string(bytes >> 20) + " MiB of checkpoints do not fit in device memory";
+                return DPX_ERR_NOMEM;
+            }
+            LCU(cudaMemsetAsync(ck->base, 0, bytes, st));             // a tag of 0 never equals a row >= 1
+        }
+    }
     std::vector<uint8_t> cref, cqry;
     if (table) {
         cref.resize(R); cqry.resize(Q);
@@ -162,11 +185,14 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
         // credit counters and ring tags start from zero (a tag of 0 never equals a row >= 1)
         LCU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)(2 * (nw_pass + 2)), st));
         LCU(cudaMemsetAsync(d_rings, 0, sizeof(unsigned long long) * (size_t)(nw_pass * RING), st));
-        if (ps + 1 < passes) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
+        if (ps + 1 < passes && !ck) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
         long long* cred = d_cnt;
         for (long long c = 0; c <= nw; ++c) {
             LongChan ch{};
-            if (c == 0) {
+            if (ck) {
+                const long long gc = w0 + c;                             // channel gc carries the right edge of column block gc - 1
+                if (gc > 0 && gc < nw_total) { ch.ring = ck->base + (gc - 1) * FULLSZ; ch.size = FULLSZ; ch.credit = nullptr; }
+            } else if (c == 0) {
                 if (ps > 0) { ch.ring = d_full[(ps - 1) & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
             } else if (c == nw) {
                 if (ps + 1 < passes) { ch.ring = d_full[ps & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
@@ -197,6 +223,96 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
 #undef LCU
     cleanup();
     *score = best; if (end_row) *end_row = brow; if (end_col) *end_col = bcol;
+    return DPX_OK;
+}
+
+// ---- alignment strings of one long pair: checkpointed forward passes + tile-by-tile walk (longtrace.cuh) ----------------
+// lines: library-allocated (dpx_free) blob of three NUL-terminated lines REF, REL, QRY, each `len` characters, at offsets
+// 0, len + 1, 2 (len + 1) — the three lines LinearSmithWaterman::print_results writes (c++/LinearSmithWaterman.cpp:259-285).
+struct LongTraceStats { double fwd_ms = 0, fwd_t_ms = 0, walk_ms = 0; long long tiles = 0; int TH = 0, TW = 0; };
+
+static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
+                             int32_t* score, int64_t* end_row, int64_t* end_col, int64_t* start_row, int64_t* start_col,
+                             char** lines, size_t* len, LongTraceStats* stats) {
+    cudaStream_t st = ctx->stream;
+    LongCkpt colck, rowck;
+    uint8_t *d_ref = nullptr, *d_qry = nullptr, *d_out = nullptr; long long* d_res = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        cudaStreamSynchronize(st);
+        colck.free(); rowck.free();
+        ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+    };
+#define TCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
+    TCU(cudaEventCreate(&ev[0])); TCU(cudaEventCreate(&ev[1]));
+    auto timed = [&](double* ms, auto&& fn) -> int {
+        cudaEventRecord(ev[0], st);
+        const int r = fn();
+        cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]);
+        float f = 0; cudaEventElapsedTime(&f, ev[0], ev[1]); *ms = f;
+        return r;
+    };
+    LongTraceStats ls;
+    int32_t sc = 0; int64_t ie = 0, je = 0;
+    // forward pass, column checkpoints: H[i][c * TW] for every row
+    { int r = timed(&ls.fwd_ms, [&] { return long_pair_single(ctx, p, ref, R, qry, Q, &sc, &ie, &je, &colck); }); if (r) { cleanup(); return r; } }
+    *score = sc; if (end_row) *end_row = ie; if (end_col) *end_col = je;
+    if (start_row) *start_row = ie; if (start_col) *start_col = je;
+    *len = 0;
+    if (sc <= 0) {                                               // nothing aligns: three empty lines (:253-257)
+        char* blob = (char*)g_host.take(4);
+        if (!blob) { cleanup(); return DPX_ERR_NOMEM; }
+        blob[0] = blob[1] = blob[2] = 0; *lines = blob;
+        cleanup();
+        if (stats) *stats = ls;
+        return DPX_OK;
+    }
+    // the same pass on the transposed prefix problem, row checkpoints: H[r * TH][j] for every column up to the end cell
+    int32_t sc_t = 0; int64_t ie_t = 0, je_t = 0;
+    { int r = timed(&ls.fwd_t_ms, [&] { return long_pair_single(ctx, p, qry, (size_t)ie, ref, (size_t)je, &sc_t, &ie_t, &je_t, &rowck); }); if (r) { cleanup(); return r; } }
+    if (sc_t != sc) { ctx->err = "long-pair traceback: the transposed pass disagrees on the score"; cleanup(); return DPX_ERR_CUDA; }
+    const int TW = colck.CW, TH = rowck.CW;
+    const long long cap = (long long)ie + (long long)je;
+    if (!pool_alloc(ctx, &d_ref, (size_t)je + 16) || !pool_alloc(ctx, &d_qry, (size_t)ie + 16) || !pool_alloc(ctx, &d_out, (size_t)(3 * cap) + 16) ||
+        !pool_alloc(ctx, &d_res, 4)) { cleanup(); return DPX_ERR_NOMEM; }
+    TCU(cudaMemcpyAsync(d_ref, ref, (size_t)je, cudaMemcpyHostToDevice, st));
+    TCU(cudaMemcpyAsync(d_qry, qry, (size_t)ie, cudaMemcpyHostToDevice, st));
+    LongBtArgs a{};
+    a.ref = d_ref; a.qry = d_qry; a.ie = ie; a.je = je; a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open;
+    a.TH = TH; a.TW = TW; a.colck = colck.base; a.col_stride = colck.stride; a.rowck = rowck.base; a.row_stride = rowck.stride;
+    a.out = d_out; a.cap = cap; a.result = d_res;
+    const size_t smem = long_bt_smem(TH, TW);
+    const int nt = std::max(32, (TW + 31) & ~31);
+    if (nt > 512 || smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
+    TCU(cudaFuncSetAttribute(long_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long res[4] = {0, 0, 0, 0};
+    {
+        cudaEventRecord(ev[0], st);
+        long_bt_kernel<<<1, nt, smem, st>>>(a);
+        TCU(cudaGetLastError());
+        cudaEventRecord(ev[1], st);
+        TCU(cudaMemcpyAsync(res, d_res, sizeof(res), cudaMemcpyDeviceToHost, st));
+        TCU(cudaStreamSynchronize(st));
+        float f = 0; cudaEventElapsedTime(&f, ev[0], ev[1]); ls.walk_ms = f;
+    }
+    const long long L = res[0];
+    ls.tiles = res[3]; ls.TH = TH; ls.TW = TW;
+    if (L <= 0 || L > cap) { ctx->err = "long-pair traceback: walk returned an impossible length"; cleanup(); return DPX_ERR_CUDA; }
+    char* blob = (char*)g_host.take((size_t)(3 * (L + 1)));
+    if (!blob) { cleanup(); return DPX_ERR_NOMEM; }
+    for (int k = 0; k < 3; ++k) {
+        if (cudaMemcpyAsync(blob + (size_t)k * (size_t)(L + 1), d_out + (size_t)k * (size_t)cap + (size_t)(cap - L), (size_t)L, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+            dpx_free(blob); ctx->err = "long-pair traceback: download failed"; cleanup(); return DPX_ERR_CUDA;
+        }
+        blob[(size_t)k * (size_t)(L + 1) + (size_t)L] = 0;
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { dpx_free(blob); ctx->err = "long-pair traceback: download failed"; cleanup(); return DPX_ERR_CUDA; }
+#undef TCU
+    *lines = blob; *len = (size_t)L;
+    if (start_row) *start_row = res[1]; if (start_col) *start_col = res[2];
+    if (stats) *stats = ls;
+    cleanup();
     return DPX_OK;
 }
 

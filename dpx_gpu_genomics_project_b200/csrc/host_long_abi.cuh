@@ -178,3 +178,24 @@ int dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params, const char* ref,
     return long_pair_single(ctx, params, ref, R, qry, Q, score, end_row, end_col);
 }
 
+int dpx_align_long_pair_strings(dpx_ctx* ctx, const dpx_params* params, const char* ref, size_t R, const char* qry, size_t Q,
+                                int32_t* score, int64_t* end_row, int64_t* end_col, int64_t* start_row, int64_t* start_col,
+                                char** lines, size_t* line_len, double* stage_ms) {
+    if (!ctx || !params || !score || !lines || !line_len || (!ref && R) || (!qry && Q)) return DPX_ERR_INVALID;
+    if (params->algo != DPX_ALGO_LSW) return DPX_ERR_UNSUPPORTED;
+    CU(cudaSetDevice(ctx->device));
+    *score = 0; *lines = nullptr; *line_len = 0;
+    if (end_row) *end_row = 0; if (end_col) *end_col = 0; if (start_row) *start_row = 0; if (start_col) *start_col = 0;
+    if (stage_ms) for (int k = 0; k < 6; ++k) stage_ms[k] = 0;
+    if (R == 0 || Q == 0) {
+        char* blob = (char*)g_host.take(4);
+        if (!blob) return DPX_ERR_NOMEM;
+        blob[0] = blob[1] = blob[2] = 0; *lines = blob;
+        return DPX_OK;
+    }
+    if ((long double)params->match * (long double)std::min(R, Q) > 2.0e9L || Q > 0x7ffffff0u || R > 0x7ffffff0u) return DPX_ERR_RANGE;
+    LongTraceStats ls;
+    const int r = long_pair_strings(ctx, params, ref, R, qry, Q, score, end_row, end_col, start_row, start_col, lines, line_len, &ls);
+    if (r == DPX_OK && stage_ms) { stage_ms[0] = ls.fwd_ms; stage_ms[1] = ls.fwd_t_ms; stage_ms[2] = ls.walk_ms; stage_ms[3] = (double)ls.tiles; stage_ms[4] = ls.TH; stage_ms[5] = ls.TW; }
+    return r;
+}

@@ -1,0 +1,128 @@
+// longtrace.cuh — alignment strings of ONE very long LinearSmithWaterman pair from CHECKPOINTS instead of a traceback matrix.
+//
+// A 1 Mbp x 1 Mbp direction matrix is 250 GB even at 2 bits per cell (the reference's 8 B per cell: 8 TB,
+// c++/LinearSmithWaterman.cpp:32-45), so the forward kernel (longpair.cuh) keeps none.  What it can keep for free is the
+// right edge of every warp's column block: in checkpoint mode each channel between two warps is a full-length array instead
+// of a ring, i.e. H[i][c * TW] for every row i and every block boundary c * TW.  The same kernel run on the TRANSPOSED problem
+// (the Smith-Waterman matrix of (qry, ref) is the transpose of that of (ref, qry): the recurrence :70-114 is symmetric in up
+// and left) leaves H[r * TH][j] for every column j.  Together they are the top row and the left column of every TH x TW tile.
+//
+// The walk (c++/LinearSmithWaterman.cpp:160-226 restated) then needs the directions of one tile at a time: starting from the
+// end cell, re-fill the tile that holds the current cell from its two borders with the reference's direction rule
+// (UP if up == H, else LEFT if left == H, else DIAG; STOP iff H == 0, :104-108 and :222), follow the directions to the tile's
+// edge, move to the neighbouring tile.  At most Q / TH + R / TW + 1 tiles are ever filled: 2 * 10^9 cells for the 10^12-cell
+// matrix.  Every H the walk looks at is the forward pass's own value, so the strings are those the reference's full-matrix
+// walk would print (tests: bit-exact against the oracle's full-matrix backtrack up to 30 kbp, tile-size invariance).
+//
+// One persistent block does all of it: thread t owns column t of the tile and sweeps its rows with a skew of t (anti-diagonal
+// wavefront, one __syncthreads per step, neighbours through a double-buffered shared row); directions are packed 16 rows per
+// word into shared memory; thread 0 walks them and writes the three lines from the back of their buffers.
+#pragma once
+#include "common.cuh"
+
+namespace dpx {
+
+struct LongBtArgs {
+    const uint8_t* ref;                  // raw reference bytes (compared for equality, as the reference does)
+    const uint8_t* qry;
+    long long ie, je;                    // end cell (1-based matrix row / column)
+    int match, mismatch, gap;
+    int TH, TW;                          // tile height = row-checkpoint spacing, tile width = column-checkpoint spacing
+    const unsigned long long* colck;     // colck[c * col_stride + i]: low 32 bits = H[i][(c + 1) * TW]  (tagged ring entries of longpair.cuh)
+    long long col_stride;
+    const unsigned long long* rowck;     // rowck[r * row_stride + j]: low 32 bits = H[(r + 1) * TH][j]
+    long long row_stride;
+    uint8_t* out;                        // three lines of `cap` bytes each (REF, REL, QRY), written from the back
+    long long cap;
+    long long* result;                   // [0] length of the lines, [1] start row, [2] start column (cell where the walk stopped), [3] tiles filled
+};
+
+// shared memory: int hbuf[2][TWp] | int left[TH + 1] | uint32 dirs[ceil(TH / 16)][TWp] | uint8 sq[TH] | uint8 sr[TWp]
+DPX_HD size_t long_bt_smem(int TH, int TW) {
+    const size_t TWp = (size_t)((TW + 31) & ~31);
+    return 2 * TWp * 4 + (size_t)(TH + 1) * 4 + (size_t)((TH + 15) / 16) * TWp * 4 + (size_t)((TH + 3) & ~3) + TWp;
+}
+
+__global__ void __launch_bounds__(512) long_bt_kernel(const LongBtArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, NT = blockDim.x;
+    const int TH = a.TH, TW = a.TW, TWp = (TW + 31) & ~31;
+    int* hbuf = reinterpret_cast<int*>(smem_raw);
+    int* sleft = hbuf + 2 * TWp;
+    uint32_t* sdirs = reinterpret_cast<uint32_t*>(sleft + TH + 1);
+    uint8_t* sq = reinterpret_cast<uint8_t*>(sdirs + (size_t)((TH + 15) / 16) * TWp);
+    uint8_t* sr = sq + ((TH + 3) & ~3);
+    __shared__ long long s_i, s_j, s_n, s_tiles;
+    __shared__ int s_done;
+    const int g = a.gap;
+
+    if (tid == 0) { s_i = a.ie; s_j = a.je; s_n = 0; s_tiles = 0; s_done = (a.ie <= 0 || a.je <= 0); }
+    __syncthreads();
+
+    while (!s_done) {
+        const long long i = s_i, j = s_j;
+        const long long tr = (i - 1) / TH, tc = (j - 1) / TW;
+        const long long r0 = tr * TH, c0 = tc * TW;
+        const int h = (int)(i - r0), w = (int)(j - c0);                // the part of the tile at or above-left of the current cell
+        // ---- borders and sequence slices of the tile ------------------------------------------------------------------------
+        for (int k = tid; k < h; k += NT) sq[k] = a.qry[r0 + k];
+        for (int k = tid; k <= h; k += NT)
+            sleft[k] = tc > 0 ? (int)(unsigned)a.colck[(tc - 1) * a.col_stride + r0 + k] : 0;        // H[r0 + k][c0]
+        const bool active = tid < w;
+        uint32_t rcv = 0x100u;
+        int up = 0, diag = 0;
+        if (active) {
+            rcv = a.ref[c0 + tid];
+            sr[tid] = (uint8_t)rcv;
+            if (tr > 0) {
+                up = (int)(unsigned)a.rowck[(tr - 1) * a.row_stride + c0 + 1 + tid];               // H[r0][c0 + 1 + tid]
+                diag = (int)(unsigned)a.rowck[(tr - 1) * a.row_stride + c0 + tid];                 // H[r0][c0 + tid]
+            }
+        }
+        __syncthreads();
+        // ---- skewed sweep: at step s thread t fills tile row s - t of its column -----------------------------------------------
+        uint32_t acc = 0;
+        const int nsteps = h + w - 1;
+        for (int s = 0; s < nsteps; ++s) {
+            const int r = s - tid;
+            if (active && r >= 0 && r < h) {
+                const int left = tid == 0 ? sleft[r + 1] : hbuf[((s - 1) & 1) * TWp + tid - 1];
+                const int ug = up + g, lg = left + g;
+                const int dg = diag + ((uint32_t)sq[r] == rcv ? a.match : a.mismatch);
+                const int v = __vimax3_s32_relu(ug, lg, dg);
+                const uint32_t code = v == 0 ? C_STOP : (ug == v ? C_UP : (lg == v ? C_LEFT : C_DIAG));
+                acc |= code << (2 * (r & 15));
+                if ((r & 15) == 15 || r == h - 1) { sdirs[(r >> 4) * TWp + tid] = acc; acc = 0; }
+                hbuf[(s & 1) * TWp + tid] = v;
+                diag = left; up = v;
+            }
+            __syncthreads();
+        }
+        // ---- walk inside the tile -----------------------------------------------------------------------------------------------
+        if (tid == 0) {
+            int ra = h, cb = w;
+            long long n = s_n;
+            bool stopped = false;
+            uint8_t* o0 = a.out + (a.cap - 1), *o1 = o0 + a.cap, *o2 = o1 + a.cap;
+            while (ra > 0 && cb > 0) {
+                const uint32_t d = (sdirs[((ra - 1) >> 4) * TWp + (cb - 1)] >> (2 * ((ra - 1) & 15))) & 3u;
+                if (d == C_STOP) { stopped = true; break; }
+                const uint8_t qi = sq[ra - 1], rj = sr[cb - 1];
+                const bool dg = d == C_DIAG, upm = d == C_UP;
+                o0[-n] = upm ? (uint8_t)'_' : rj;                                      // REF line: '_' where the query base has no partner
+                o1[-n] = dg ? (qi == rj ? (uint8_t)'*' : (uint8_t)'|') : (uint8_t)' ';
+                o2[-n] = (dg || upm) ? qi : (uint8_t)'_';
+                ra -= (dg || upm) ? 1 : 0;
+                cb -= (dg || !upm) ? 1 : 0;
+                ++n;
+            }
+            s_n = n; s_i = r0 + ra; s_j = c0 + cb; s_tiles += 1;
+            // on a tile edge the cell (s_i, s_j) belongs to the next tile, whose fill says through its STOP code whether H is 0 there
+            s_done = stopped || s_i == 0 || s_j == 0;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { a.result[0] = s_n; a.result[1] = s_i; a.result[2] = s_j; a.result[3] = s_tiles; }
+}
+
+}  // namespace dpx

@@ -186,6 +186,19 @@ int         dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params,
                                 const char* ref, size_t R, const char* qry, size_t Q,
                                 int32_t* score, int64_t* end_row, int64_t* end_col);
 
+/* ---- one very long pair WITH its alignment: the three lines LinearSmithWaterman::print_results
+ * writes (c++/LinearSmithWaterman.cpp:259-285) for a pair whose direction matrix could never be stored.  Two checkpointed
+ * forward passes (the pair and its transpose) keep H on a grid of rows and columns; the walk of :160-226 then re-fills one
+ * tile at a time (csrc/longtrace.cuh).  Needs 16 B * R * Q / 512 of device memory for the checkpoints (33 GB at 1 Mbp x 1 Mbp).
+ *   lines      : library-allocated (dpx_free): REF, REL, QRY, each *line_len characters + NUL, back to back
+ *   start_row/start_col : the cell where the walk stopped (H == 0); the alignment covers rows start_row+1 .. end_row
+ *   stage_ms   : optional double[6]: forward pass, transposed forward pass, tile walk (ms), tiles filled, tile height, tile width */
+int         dpx_align_long_pair_strings(dpx_ctx* ctx, const dpx_params* params,
+                                        const char* ref, size_t R, const char* qry, size_t Q,
+                                        int32_t* score, int64_t* end_row, int64_t* end_col,
+                                        int64_t* start_row, int64_t* start_col,
+                                        char** lines, size_t* line_len, double* stage_ms);
+
 /* ---- one very long pair across SEVERAL GPUs (multi-GPU mode B): column stripes, one per GPU,
  * pipelined along the anti-diagonal; the right edge of stripe g streams into stripe g+1's inbox by NVLink P2P
  * stores.  One process per GPU: each rank creates its stripe, the ranks exchange the 64-byte IPC handles

@@ -8,39 +8,70 @@ struct LongPlan { int K; int capacity_warps; };
 
 // mode bits: 1 = PACK (the travelling H and the query base share one 32-bit shuffle word; needs H < 2^23),
 //            2 = TABLE (2-bit coded sequences, per-column score table; needs <= 4 symbols and int8 scores)
-template <int K, bool PACK, bool TABLE>
+// mode bit 4 = CK: the checkpoint instantiation (row dumps compiled in; longtrace.cuh)
+template <int K, bool PACK, bool TABLE, bool CK>
 static int long_capacity(dpx_ctx* ctx, int* warps) {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK, TABLE>, 128, 0));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, long_sw_kernel<K, PACK, TABLE, CK>, 128, 0));
     *warps = per_sm * ctx->sm_count * 4;
     return DPX_OK;
 }
 
-template <int K, bool PACK, bool TABLE>
+template <int K, bool PACK, bool TABLE, bool CK>
 static int long_launch(dpx_ctx* ctx, const LongArgs& a, cudaStream_t st) {
     const int blocks = (a.nwarps + 3) / 4;
     void* kargs[] = {(void*)&a};
-    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK, TABLE>, dim3(blocks), dim3(128), kargs, 0, st));
+    CU(cudaLaunchCooperativeKernel((void*)long_sw_kernel<K, PACK, TABLE, CK>, dim3(blocks), dim3(128), kargs, 0, st));
     return DPX_OK;
 }
 
 template <int K>
 static int long_launch_m(dpx_ctx* ctx, int mode, const LongArgs& a, cudaStream_t st) {
-    switch (mode & 3) {
-        case 0: return long_launch<K, false, false>(ctx, a, st);
-        case 1: return long_launch<K, true, false>(ctx, a, st);
-        case 2: return long_launch<K, false, true>(ctx, a, st);
-        default: return long_launch<K, true, true>(ctx, a, st);
+    switch (mode & 7) {
+        case 0: return long_launch<K, false, false, false>(ctx, a, st);
+        case 1: return long_launch<K, true, false, false>(ctx, a, st);
+        case 2: return long_launch<K, false, true, false>(ctx, a, st);
+        case 3: return long_launch<K, true, true, false>(ctx, a, st);
+        case 4: return long_launch<K, false, false, true>(ctx, a, st);
+        case 5: return long_launch<K, true, false, true>(ctx, a, st);
+        case 6: return long_launch<K, false, true, true>(ctx, a, st);
+        default: return long_launch<K, true, true, true>(ctx, a, st);
     }
 }
 template <int K>
 static int long_capacity_m(dpx_ctx* ctx, int mode, int* warps) {
-    switch (mode & 3) {
-        case 0: return long_capacity<K, false, false>(ctx, warps);
-        case 1: return long_capacity<K, true, false>(ctx, warps);
-        case 2: return long_capacity<K, false, true>(ctx, warps);
-        default: return long_capacity<K, true, true>(ctx, warps);
+    switch (mode & 7) {
+        case 0: return long_capacity<K, false, false, false>(ctx, warps);
+        case 1: return long_capacity<K, true, false, false>(ctx, warps);
+        case 2: return long_capacity<K, false, true, false>(ctx, warps);
+        case 3: return long_capacity<K, true, true, false>(ctx, warps);
+        case 4: return long_capacity<K, false, false, true>(ctx, warps);
+        case 5: return long_capacity<K, true, false, true>(ctx, warps);
+        case 6: return long_capacity<K, false, true, true>(ctx, warps);
+        default: return long_capacity<K, true, true, true>(ctx, warps);
     }
+}
+
+// K = 32 exists for the score-table kernels only (mode bit 2); the byte-compare kernels stop at 16 columns per lane
+template <int K>
+static int long_launch_t(dpx_ctx* ctx, int mode, const LongArgs& a, cudaStream_t st) {
+    switch (mode & 7) {
+        case 2: return long_launch<K, false, true, false>(ctx, a, st);
+        case 3: return long_launch<K, true, true, false>(ctx, a, st);
+        case 6: return long_launch<K, false, true, true>(ctx, a, st);
+        case 7: return long_launch<K, true, true, true>(ctx, a, st);
+    }
+    ctx->err = "32 columns per lane need the score-table kernel"; return DPX_ERR_INVALID;
+}
+template <int K>
+static int long_capacity_t(dpx_ctx* ctx, int mode, int* warps) {
+    switch (mode & 7) {
+        case 2: return long_capacity<K, false, true, false>(ctx, warps);
+        case 3: return long_capacity<K, true, true, false>(ctx, warps);
+        case 6: return long_capacity<K, false, true, true>(ctx, warps);
+        case 7: return long_capacity<K, true, true, true>(ctx, warps);
+    }
+    ctx->err = "32 columns per lane need the score-table kernel"; return DPX_ERR_INVALID;
 }
 
 static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaStream_t st) {
@@ -48,7 +79,7 @@ static int long_launch_k(dpx_ctx* ctx, int K, int mode, const LongArgs& a, cudaS
         case 2: return long_launch_m<2>(ctx, mode, a, st);
         case 4: return long_launch_m<4>(ctx, mode, a, st);
         case 8: return long_launch_m<8>(ctx, mode, a, st);
-        case 32: return long_launch_m<32>(ctx, mode, a, st);
+        case 32: return long_launch_t<32>(ctx, mode, a, st);
         default: return long_launch_m<16>(ctx, mode, a, st);
     }
 }
@@ -58,7 +89,7 @@ static int long_capacity_k(dpx_ctx* ctx, int K, int mode, int* warps) {
         case 2: return long_capacity_m<2>(ctx, mode, warps);
         case 4: return long_capacity_m<4>(ctx, mode, warps);
         case 8: return long_capacity_m<8>(ctx, mode, warps);
-        case 32: return long_capacity_m<32>(ctx, mode, warps);
+        case 32: return long_capacity_t<32>(ctx, mode, warps);
         default: return long_capacity_m<16>(ctx, mode, warps);
     }
 }
@@ -106,14 +137,18 @@ static int long_pick_k(dpx_ctx* ctx, long long R_local, bool allow32 = false) {
     return best_k;
 }
 
-// Checkpoint mode of the forward pass (longtrace.cuh): every channel between two warps is a full-length array, so the right
-// edge of every column block, H[i][(c + 1) * CW] for all rows i, is still there when the kernel has finished.
+// Checkpoint mode of the forward pass (longtrace.cuh): every warp also stores the column it reads from its left neighbour, so
+// the left edge of every column block, H[i][c * CW] for all rows i, is still there when the kernel has finished; and every lane
+// stores its columns of every TH-th row.  Together: the top row and the left column of every TH x CW tile of the matrix.
 struct LongCkpt {
-    unsigned long long* base = nullptr;   // entry (c, i) at base[c * stride + i]: {row tag : 32 | H : 32}
-    long long stride = 0;                 // entries per channel (a power of two > Q)
-    long long n = 0;                      // channels = column blocks - 1
-    int CW = 0;                           // columns per block
-    void free() { if (base) cudaFree(base); base = nullptr; }
+    int32_t* base = nullptr;              // H[i][(c + 1) * CW] at base[c * stride + i], i = 1..Q
+    long long stride = 0;                 // entries per column boundary (>= Q + 1)
+    long long n = 0;                      // column boundaries = column blocks - 1
+    int CW = 0;                           // columns per block = tile width
+    int32_t* rbase = nullptr;             // H[(m + 1) * TH][j] at rbase[m * rstride + j - 1], j = 1..R
+    long long rstride = 0, rn = 0;        // entries per checkpoint row, checkpoint rows = floor(Q / TH)
+    int TH = 0;                           // tile height (a power of two)
+    void free() { if (base) cudaFree(base); if (rbase) cudaFree(rbase); base = rbase = nullptr; }
 };
 
 static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
@@ -121,11 +156,11 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
     cudaStream_t st = ctx->stream;
     uint8_t code[256];
     const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
-    // checkpoint mode: the column blocks are the tiles of the traceback, whose directions must fit shared memory: at most 512 wide
-    int K = long_pick_k(ctx, (long long)R, !ck && table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L);
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && !ck)) K = k; }   // tests
+    const bool allow32 = table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L;
+    int K = long_pick_k(ctx, (long long)R, allow32);
+    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && allow32)) K = k; }   // tests
     int capacity = 0;
-    const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0);
+    const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0) | (ck ? 4 : 0);
     { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
     if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
     if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
@@ -151,18 +186,16 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
               pool_alloc(ctx, &d_br, (size_t)nw_pass) && pool_alloc(ctx, &d_bc, (size_t)nw_pass) &&
               pool_alloc(ctx, &d_chans, (size_t)(nw_pass + 1)) && pool_alloc(ctx, &d_err, 1);
     const long long FULLSZ = pow2_at_least((long long)Q + 2);      // ring sizes are powers of two; this one never wraps
-    if (ok && passes > 1 && !ck) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
+    if (ok && passes > 1) ok = pool_alloc(ctx, &d_full[0], (size_t)FULLSZ) && pool_alloc(ctx, &d_full[1], (size_t)FULLSZ);
     if (!ok) { cleanup(); return DPX_ERR_NOMEM; }
     if (ck) {
-        ck->CW = (int)CW; ck->n = nw_total - 1; ck->stride = FULLSZ; ck->base = nullptr;
-        if (ck->n > 0) {
-            const size_t bytes = sizeof(unsigned long long) * (size_t)ck->n * (size_t)FULLSZ;
-            if (cudaMalloc(&ck->base, bytes) != cudaSuccess) {
-                cudaGetLastError(); ck->base = nullptr; cleanup();
-                ctx->err = "long-pair traceback: " + std::to_string(bytes >> 20) + " MiB of checkpoints do not fit in device memory";
-                return DPX_ERR_NOMEM;
-            }
-            LCU(cudaMemsetAsync(ck->base, 0, bytes, st));             // a tag of 0 never equals a row >= 1
+        ck->CW = (int)CW; ck->n = nw_total - 1; ck->stride = ((long long)Q + 1 + 31) & ~31LL; ck->base = nullptr;
+        ck->TH = (int)std::min<long long>(CW, 512); ck->rn = (long long)Q / ck->TH; ck->rstride = ((long long)R + 3) & ~3LL; ck->rbase = nullptr;
+        const size_t bytes = sizeof(int32_t) * (size_t)ck->n * (size_t)ck->stride, rbytes = sizeof(int32_t) * (size_t)ck->rn * (size_t)ck->rstride;
+        if ((bytes && cudaMalloc(&ck->base, bytes) != cudaSuccess) || (rbytes && cudaMalloc(&ck->rbase, rbytes) != cudaSuccess)) {
+            cudaGetLastError(); cleanup();
+            ctx->err = "long-pair traceback: " + std::to_string((bytes + rbytes) >> 20) + " MiB of checkpoints do not fit in device memory";
+            return DPX_ERR_NOMEM;
         }
     }
     std::vector<uint8_t> cref, cqry;
@@ -185,14 +218,11 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
         // credit counters and ring tags start from zero (a tag of 0 never equals a row >= 1)
         LCU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * (size_t)(2 * (nw_pass + 2)), st));
         LCU(cudaMemsetAsync(d_rings, 0, sizeof(unsigned long long) * (size_t)(nw_pass * RING), st));
-        if (ps + 1 < passes && !ck) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
+        if (ps + 1 < passes) LCU(cudaMemsetAsync(d_full[ps & 1], 0, sizeof(unsigned long long) * (size_t)FULLSZ, st));
         long long* cred = d_cnt;
         for (long long c = 0; c <= nw; ++c) {
             LongChan ch{};
-            if (ck) {
-                const long long gc = w0 + c;                             // channel gc carries the right edge of column block gc - 1
-                if (gc > 0 && gc < nw_total) { ch.ring = ck->base + (gc - 1) * FULLSZ; ch.size = FULLSZ; ch.credit = nullptr; }
-            } else if (c == 0) {
+            if (c == 0) {
                 if (ps > 0) { ch.ring = d_full[(ps - 1) & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
             } else if (c == nw) {
                 if (ps + 1 < passes) { ch.ring = d_full[ps & 1]; ch.size = FULLSZ; ch.credit = nullptr; }
@@ -207,6 +237,11 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
         a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open; a.nwarps = (int)nw; a.chans = d_chans;
         a.best_score = d_bs; a.best_row = d_br; a.best_col = d_bc; a.error_flag = d_err; a.system_scope = 0;
         a.tab_match = p->match - p->gap_open; a.tab_mismatch = p->mismatch - p->gap_open; a.sixteen = 16u;
+        if (ck) {
+            a.ck_base = ck->base; a.ck_stride = ck->stride; a.ck_first = w0;
+            a.rk_base = ck->rbase; a.rk_stride = ck->rstride; a.rk_shift = 0;
+            while ((1 << a.rk_shift) < ck->TH) ++a.rk_shift;
+        }
         { int s = long_launch_k(ctx, K, mode, a, st); if (s) { cleanup(); return s; } }
         LCU(cudaMemcpyAsync(h_bs.data(), d_bs, sizeof(int32_t) * (size_t)nw, cudaMemcpyDeviceToHost, st));
         LCU(cudaMemcpyAsync(h_br.data(), d_br, sizeof(long long) * (size_t)nw, cudaMemcpyDeviceToHost, st));
@@ -235,12 +270,12 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
                              int32_t* score, int64_t* end_row, int64_t* end_col, int64_t* start_row, int64_t* start_col,
                              char** lines, size_t* len, LongTraceStats* stats) {
     cudaStream_t st = ctx->stream;
-    LongCkpt colck, rowck;
+    LongCkpt colck;
     uint8_t *d_ref = nullptr, *d_qry = nullptr, *d_out = nullptr; long long* d_res = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     auto cleanup = [&]() {
         cudaStreamSynchronize(st);
-        colck.free(); rowck.free();
+        colck.free();
         ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
     };
@@ -255,8 +290,10 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     };
     LongTraceStats ls;
     int32_t sc = 0; int64_t ie = 0, je = 0;
-    // forward pass, column checkpoints: H[i][c * TW] for every row
-    { int r = timed(&ls.fwd_ms, [&] { return long_pair_single(ctx, p, ref, R, qry, Q, &sc, &ie, &je, &colck); }); if (r) { cleanup(); return r; } }
+    // forward pass with checkpoints: H on every TW-th column and every TH-th row
+    LongCkpt ck;
+    { int r = timed(&ls.fwd_ms, [&] { return long_pair_single(ctx, p, ref, R, qry, Q, &sc, &ie, &je, &ck); }); if (r) { ck.free(); cleanup(); return r; } }
+    colck = ck;                                                  // owned by cleanup() from here on
     *score = sc; if (end_row) *end_row = ie; if (end_col) *end_col = je;
     if (start_row) *start_row = ie; if (start_col) *start_col = je;
     *len = 0;
@@ -268,11 +305,7 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
         if (stats) *stats = ls;
         return DPX_OK;
     }
-    // the same pass on the transposed prefix problem, row checkpoints: H[r * TH][j] for every column up to the end cell
-    int32_t sc_t = 0; int64_t ie_t = 0, je_t = 0;
-    { int r = timed(&ls.fwd_t_ms, [&] { return long_pair_single(ctx, p, qry, (size_t)ie, ref, (size_t)je, &sc_t, &ie_t, &je_t, &rowck); }); if (r) { cleanup(); return r; } }
-    if (sc_t != sc) { ctx->err = "long-pair traceback: the transposed pass disagrees on the score"; cleanup(); return DPX_ERR_CUDA; }
-    const int TW = colck.CW, TH = rowck.CW;
+    const int TW = colck.CW, TH = colck.TH;
     const long long cap = (long long)ie + (long long)je;
     if (!pool_alloc(ctx, &d_ref, (size_t)je + 16) || !pool_alloc(ctx, &d_qry, (size_t)ie + 16) || !pool_alloc(ctx, &d_out, (size_t)(3 * cap) + 16) ||
         !pool_alloc(ctx, &d_res, 4)) { cleanup(); return DPX_ERR_NOMEM; }
@@ -280,11 +313,12 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     TCU(cudaMemcpyAsync(d_qry, qry, (size_t)ie, cudaMemcpyHostToDevice, st));
     LongBtArgs a{};
     a.ref = d_ref; a.qry = d_qry; a.ie = ie; a.je = je; a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open;
-    a.TH = TH; a.TW = TW; a.colck = colck.base; a.col_stride = colck.stride; a.rowck = rowck.base; a.row_stride = rowck.stride;
+    a.TH = TH; a.TW = TW; a.colck = colck.base; a.col_stride = colck.stride;
+    a.rowck = colck.rbase - 1; a.row_stride = colck.rstride;      // 0-based columns: rowck[r * stride + j] is column j >= 1
     a.out = d_out; a.cap = cap; a.result = d_res;
     const size_t smem = long_bt_smem(TH, TW);
-    const int nt = std::max(32, (TW + 31) & ~31);
-    if (nt > 512 || smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
+    const int nt = std::max(32, ((TW + LONG_BT_CPT - 1) / LONG_BT_CPT + 31) & ~31);
+    if (nt > 256 || smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
     TCU(cudaFuncSetAttribute(long_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long res[4] = {0, 0, 0, 0};
     {

@@ -48,6 +48,15 @@ struct LongArgs {
     // TABLE kernels: ref / qry hold 2-bit codes (one per byte) and scores come from a per-column byte table
     int tab_match, tab_mismatch;   // match - gap, mismatch - gap (both fit int8)
     uint32_t sixteen;              // 16, passed as data so that h*16 + (15-k) stays one IMAD on the FMA pipe
+    // checkpoint mode (longtrace.cuh): every warp also leaves the column it READS, H[i][left edge of its block], in
+    // ck_base[(ck_first + w - 1) * ck_stride + i] — 32 rows per coalesced store, straight from the block prologue's registers
+    int32_t* ck_base;              // null: no checkpoints
+    long long ck_stride;
+    long long ck_first;            // global index of this launch's warp 0
+    // ... and (CK kernels) every lane leaves its K columns of the rows i = m * 2^rk_shift: H[i][j] at rk_base[(m - 1) * rk_stride + j - 1]
+    int32_t* rk_base;
+    long long rk_stride;
+    int rk_shift;
 };
 
 __device__ __forceinline__ uint32_t prmt_b32l(uint32_t a, uint32_t b, uint32_t sel) {
@@ -89,7 +98,7 @@ constexpr int LONG_WATCHDOG = 1 << 22;   // polls before a stuck channel raises 
 //     h  = max(left + gap, t, 0)  (VIADDMNMX.RELU)  hg = h + gap                                 (IMAD)
 // and the end cell is tracked per LANE (a max3 tree per row step, a rare branch when the lane's maximum grows).
 // !TABLE: byte compare + per-column tracking, for alphabets with more than four symbols.
-template <int K, bool PACK, bool TABLE>
+template <int K, bool PACK, bool TABLE, bool CK = false>
 __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -129,6 +138,7 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
     long long credit = 0;
     bool dead = false;
     const int nsteps = Q + 31;
+    const int rk_mask = CK ? (1 << a.rk_shift) - 1 : 0;
 
     // software prefetch of the first block
     uint32_t qnext = (lane < Q) ? (uint32_t)__ldcg(a.qry + lane) : 0u;
@@ -149,6 +159,7 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
             }
             if (dead) break;
             rin = (int)(unsigned)e;
+            if (a.ck_base != nullptr && row <= Q) a.ck_base[(a.ck_first + w - 1) * a.ck_stride + row] = rin;
             if (cin.credit && lane == 0) st_volatile_s64(cin.credit, (sb + 32 < Q) ? sb + 32 : Q);   // those rows now live in registers
         }
         {
@@ -217,6 +228,11 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
                     }                                                                                            \
                 }                                                                                                \
                 lastH = left;                                                                                    \
+                if (CK && (i & rk_mask) == 0) {                     /* a checkpoint row: once per 2^rk_shift rows */ \
+                    int32_t* dst = a.rk_base + ((long long)(i >> a.rk_shift) - 1) * a.rk_stride + a.col_offset + cfirst; \
+                    _Pragma("unroll")                                                                            \
+                    for (int k = 0; k < K; ++k) if (cv[k]) dst[k] = TABLE ? Hc[k] - g : Hc[k];                   \
+                }                                                                                                \
                 if (has_out && lane == 31)                                                                       \
                     st_volatile_u64(cout.ring + ((unsigned)i & omask), ((unsigned long long)(unsigned)i << 32) | (unsigned)left); \
             }                                                                                                    \

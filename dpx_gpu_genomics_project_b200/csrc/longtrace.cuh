@@ -1,11 +1,11 @@
 // longtrace.cuh — alignment strings of ONE very long LinearSmithWaterman pair from CHECKPOINTS instead of a traceback matrix.
 //
 // A 1 Mbp x 1 Mbp direction matrix is 250 GB even at 2 bits per cell (the reference's 8 B per cell: 8 TB,
-// c++/LinearSmithWaterman.cpp:32-45), so the forward kernel (longpair.cuh) keeps none.  What it can keep for free is the
-// right edge of every warp's column block: in checkpoint mode each channel between two warps is a full-length array instead
-// of a ring, i.e. H[i][c * TW] for every row i and every block boundary c * TW.  The same kernel run on the TRANSPOSED problem
-// (the Smith-Waterman matrix of (qry, ref) is the transpose of that of (ref, qry): the recurrence :70-114 is symmetric in up
-// and left) leaves H[r * TH][j] for every column j.  Together they are the top row and the left column of every TH x TW tile.
+// c++/LinearSmithWaterman.cpp:32-45), so the forward kernel (longpair.cuh) keeps none.  In checkpoint mode it keeps a GRID of
+// H instead: every warp stores the column it reads from its left neighbour (32 rows per coalesced store), i.e. H[i][c * TW]
+// for every row i and every block boundary c * TW, and every lane stores its columns of every TH-th row, H[r * TH][j]
+// (4 B * R * Q * (1 / TW + 1 / TH): 12 GB at 1 Mbp x 1 Mbp with 512 x 1024 tiles).  Together they are the top row and the
+// left column of every TH x TW tile of the matrix.
 //
 // The walk (c++/LinearSmithWaterman.cpp:160-226 restated) then needs the directions of one tile at a time: starting from the
 // end cell, re-fill the tile that holds the current cell from its two borders with the reference's direction rule
@@ -14,9 +14,9 @@
 // matrix.  Every H the walk looks at is the forward pass's own value, so the strings are those the reference's full-matrix
 // walk would print (tests: bit-exact against the oracle's full-matrix backtrack up to 30 kbp, tile-size invariance).
 //
-// One persistent block does all of it: thread t owns column t of the tile and sweeps its rows with a skew of t (anti-diagonal
-// wavefront, one __syncthreads per step, neighbours through a double-buffered shared row); directions are packed 16 rows per
-// word into shared memory; thread 0 walks them and writes the three lines from the back of their buffers.
+// One persistent block does all of it: thread t owns four columns of the tile and sweeps their rows with a skew of t
+// (anti-diagonal wavefront, one __syncthreads per step, neighbours through a double-buffered shared row); directions are packed
+// 16 rows per word into shared memory; thread 0 walks them and writes the three lines from the back of their buffers.
 #pragma once
 #include "common.cuh"
 
@@ -28,22 +28,25 @@ struct LongBtArgs {
     long long ie, je;                    // end cell (1-based matrix row / column)
     int match, mismatch, gap;
     int TH, TW;                          // tile height = row-checkpoint spacing, tile width = column-checkpoint spacing
-    const unsigned long long* colck;     // colck[c * col_stride + i]: low 32 bits = H[i][(c + 1) * TW]  (tagged ring entries of longpair.cuh)
+    const int32_t* colck;                // colck[c * col_stride + i] = H[i][(c + 1) * TW], rows 1..Q (checkpoint dumps of longpair.cuh)
     long long col_stride;
-    const unsigned long long* rowck;     // rowck[r * row_stride + j]: low 32 bits = H[(r + 1) * TH][j]
+    const int32_t* rowck;                // rowck[r * row_stride + j] = H[(r + 1) * TH][j], columns 1..R (the host passes base - 1)
     long long row_stride;
     uint8_t* out;                        // three lines of `cap` bytes each (REF, REL, QRY), written from the back
     long long cap;
     long long* result;                   // [0] length of the lines, [1] start row, [2] start column (cell where the walk stopped), [3] tiles filled
 };
 
-// shared memory: int hbuf[2][TWp] | int left[TH + 1] | uint32 dirs[ceil(TH / 16)][TWp] | uint8 sq[TH] | uint8 sr[TWp]
+constexpr int LONG_BT_CPT = 4;           // tile columns per thread
+
+// shared memory: int hbuf[2][NT] | int left[TH + 1] | uint32 dirs[ceil(TH / 16)][TWp] | uint8 sq[TH] | uint8 sr[TWp]
 DPX_HD size_t long_bt_smem(int TH, int TW) {
     const size_t TWp = (size_t)((TW + 31) & ~31);
     return 2 * TWp * 4 + (size_t)(TH + 1) * 4 + (size_t)((TH + 15) / 16) * TWp * 4 + (size_t)((TH + 3) & ~3) + TWp;
 }
 
-__global__ void __launch_bounds__(512) long_bt_kernel(const LongBtArgs a) {
+__global__ void __launch_bounds__(256) long_bt_kernel(const LongBtArgs a) {
+    constexpr int CPT = LONG_BT_CPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, NT = blockDim.x;
     const int TH = a.TH, TW = a.TW, TWp = (TW + 31) & ~31;
@@ -64,37 +67,51 @@ __global__ void __launch_bounds__(512) long_bt_kernel(const LongBtArgs a) {
         const long long tr = (i - 1) / TH, tc = (j - 1) / TW;
         const long long r0 = tr * TH, c0 = tc * TW;
         const int h = (int)(i - r0), w = (int)(j - c0);                // the part of the tile at or above-left of the current cell
-        // ---- borders and sequence slices of the tile ------------------------------------------------------------------------
+        const int wt = (w + CPT - 1) / CPT;                             // threads with at least one column
+        // ---- borders and sequence slices of the tile (row 0 and column 0 of the matrix are 0 and have no checkpoint) --------
         for (int k = tid; k < h; k += NT) sq[k] = a.qry[r0 + k];
         for (int k = tid; k <= h; k += NT)
-            sleft[k] = tc > 0 ? (int)(unsigned)a.colck[(tc - 1) * a.col_stride + r0 + k] : 0;        // H[r0 + k][c0]
-        const bool active = tid < w;
-        uint32_t rcv = 0x100u;
-        int up = 0, diag = 0;
-        if (active) {
-            rcv = a.ref[c0 + tid];
-            sr[tid] = (uint8_t)rcv;
-            if (tr > 0) {
-                up = (int)(unsigned)a.rowck[(tr - 1) * a.row_stride + c0 + 1 + tid];               // H[r0][c0 + 1 + tid]
-                diag = (int)(unsigned)a.rowck[(tr - 1) * a.row_stride + c0 + tid];                 // H[r0][c0 + tid]
-            }
+            sleft[k] = (tc > 0 && r0 + k > 0) ? a.colck[(tc - 1) * a.col_stride + r0 + k] : 0;        // H[r0 + k][c0]
+        for (int k = tid; k < w; k += NT) sr[k] = a.ref[c0 + k];
+        uint32_t rcv[CPT];
+        int up[CPT];
+        int diag0 = 0;                                                  // H[r - 1][column left of this thread's first]
+        #pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const int c = tid * CPT + k;
+            rcv[k] = c < w ? (uint32_t)a.ref[c0 + c] : 0x100u;          // columns right of the current cell never match; nobody reads them
+            up[k] = (c < w && tr > 0) ? a.rowck[(tr - 1) * a.row_stride + c0 + 1 + c] : 0;          // H[r0][c0 + 1 + c]
         }
+        if (tid < wt && tr > 0 && c0 + (long long)tid * CPT > 0) diag0 = a.rowck[(tr - 1) * a.row_stride + c0 + (long long)tid * CPT];
         __syncthreads();
-        // ---- skewed sweep: at step s thread t fills tile row s - t of its column -----------------------------------------------
-        uint32_t acc = 0;
-        const int nsteps = h + w - 1;
+        // ---- skewed sweep: at step s thread t fills tile row s - t of its CPT columns ----------------------------------------
+        uint32_t acc[CPT];
+        #pragma unroll
+        for (int k = 0; k < CPT; ++k) acc[k] = 0;
+        const int nsteps = h + wt - 1;
         for (int s = 0; s < nsteps; ++s) {
             const int r = s - tid;
-            if (active && r >= 0 && r < h) {
-                const int left = tid == 0 ? sleft[r + 1] : hbuf[((s - 1) & 1) * TWp + tid - 1];
-                const int ug = up + g, lg = left + g;
-                const int dg = diag + ((uint32_t)sq[r] == rcv ? a.match : a.mismatch);
-                const int v = __vimax3_s32_relu(ug, lg, dg);
-                const uint32_t code = v == 0 ? C_STOP : (ug == v ? C_UP : (lg == v ? C_LEFT : C_DIAG));
-                acc |= code << (2 * (r & 15));
-                if ((r & 15) == 15 || r == h - 1) { sdirs[(r >> 4) * TWp + tid] = acc; acc = 0; }
-                hbuf[(s & 1) * TWp + tid] = v;
-                diag = left; up = v;
+            if (tid < wt && r >= 0 && r < h) {
+                const int left_in = tid == 0 ? sleft[r + 1] : hbuf[((s - 1) & 1) * NT + tid - 1];
+                const uint32_t qc = sq[r];
+                int left = left_in, diag = diag0;
+                const int sh = 2 * (r & 15);
+                #pragma unroll
+                for (int k = 0; k < CPT; ++k) {
+                    const int u = up[k];
+                    const int ug = u + g, lg = left + g;
+                    const int dg = diag + (qc == rcv[k] ? a.match : a.mismatch);
+                    const int v = __vimax3_s32_relu(ug, lg, dg);
+                    const uint32_t code = v == 0 ? C_STOP : (ug == v ? C_UP : (lg == v ? C_LEFT : C_DIAG));
+                    acc[k] |= code << sh;
+                    diag = u; up[k] = v; left = v;
+                }
+                diag0 = left_in;
+                hbuf[(s & 1) * NT + tid] = left;
+                if ((r & 15) == 15 || r == h - 1) {
+                    #pragma unroll
+                    for (int k = 0; k < CPT; ++k) { if (tid * CPT + k < TWp) sdirs[(r >> 4) * TWp + tid * CPT + k] = acc[k]; acc[k] = 0; }
+                }
             }
             __syncthreads();
         }

@@ -187,12 +187,12 @@ int         dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params,
                                 int32_t* score, int64_t* end_row, int64_t* end_col);
 
 /* ---- one very long pair WITH its alignment: the three lines LinearSmithWaterman::print_results
- * writes (c++/LinearSmithWaterman.cpp:259-285) for a pair whose direction matrix could never be stored.  Two checkpointed
- * forward passes (the pair and its transpose) keep H on a grid of rows and columns; the walk of :160-226 then re-fills one
- * tile at a time (csrc/longtrace.cuh).  Needs 16 B * R * Q / 512 of device memory for the checkpoints (33 GB at 1 Mbp x 1 Mbp).
+ * writes (c++/LinearSmithWaterman.cpp:259-285) for a pair whose direction matrix could never be stored.  The forward pass
+ * keeps H on a grid of rows and columns (checkpoints); the walk of :160-226 then re-fills one tile at a time from its two
+ * borders (csrc/longtrace.cuh).  Needs 4 B * R * Q * (1/512 + 1/1024) of device memory for the checkpoints (12 GB at 1 Mbp^2).
  *   lines      : library-allocated (dpx_free): REF, REL, QRY, each *line_len characters + NUL, back to back
  *   start_row/start_col : the cell where the walk stopped (H == 0); the alignment covers rows start_row+1 .. end_row
- *   stage_ms   : optional double[6]: forward pass, transposed forward pass, tile walk (ms), tiles filled, tile height, tile width */
+ *   stage_ms   : optional double[6]: forward pass (ms), walk rounds, tile fills + walk (ms), tiles walked, tile height, tile width */
 int         dpx_align_long_pair_strings(dpx_ctx* ctx, const dpx_params* params,
                                         const char* ref, size_t R, const char* qry, size_t Q,
                                         int32_t* score, int64_t* end_row, int64_t* end_col,

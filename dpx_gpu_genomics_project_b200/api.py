@@ -177,7 +177,7 @@ class Engine:
 
     def align_long_pair_strings(self, params: _lib.Params, ref: bytes, qry: bytes):
         """One long LinearSmithWaterman pair with its alignment: ((score, end_row, end_col), (start_row, start_col),
-        (REF, REL, QRY) bytes, stages) — stages = device ms of the two checkpointed forward passes and of the tile walk, tiles filled."""
+        (REF, REL, QRY) bytes, stages) — stages = device ms of the checkpointed forward pass and of the tile fills + walk, rounds, tiles walked, tile shape."""
         s = C.c_int32(); r = C.c_int64(); c = C.c_int64(); r0 = C.c_int64(); c0 = C.c_int64()
         blob = C.c_void_p(); n = C.c_size_t(); ms = (C.c_double * 6)()
         _check(self.L.dpx_align_long_pair_strings(self.ctx, C.byref(params), ref, len(ref), qry, len(qry), C.byref(s), C.byref(r), C.byref(c),
@@ -186,7 +186,7 @@ class Engine:
         raw = C.string_at(blob.value, 3 * (L + 1))
         self.L.dpx_free(blob)
         lines = tuple(raw[k * (L + 1): k * (L + 1) + L] for k in range(3))
-        return (s.value, r.value, c.value), (r0.value, c0.value), lines, dict(fwd_ms=ms[0], fwd_t_ms=ms[1], walk_ms=ms[2], tiles=int(ms[3]), tile_rows=int(ms[4]), tile_cols=int(ms[5]))
+        return (s.value, r.value, c.value), (r0.value, c0.value), lines, dict(fwd_ms=ms[0], rounds=int(ms[1]), walk_ms=ms[2], tiles=int(ms[3]), tile_rows=int(ms[4]), tile_cols=int(ms[5]))
 
 
 class Batch:

@@ -264,7 +264,7 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
 // ---- alignment strings of one long pair: checkpointed forward passes + tile-by-tile walk (longtrace.cuh) ----------------
 // lines: library-allocated (dpx_free) blob of three NUL-terminated lines REF, REL, QRY, each `len` characters, at offsets
 // 0, len + 1, 2 (len + 1) — the three lines LinearSmithWaterman::print_results writes (c++/LinearSmithWaterman.cpp:259-285).
-struct LongTraceStats { double fwd_ms = 0, fwd_t_ms = 0, walk_ms = 0; long long tiles = 0; int TH = 0, TW = 0; };
+struct LongTraceStats { double fwd_ms = 0, walk_ms = 0; long long tiles = 0, rounds = 0; int TH = 0, TW = 0; };
 
 static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref, size_t R, const char* qry, size_t Q,
                              int32_t* score, int64_t* end_row, int64_t* end_col, int64_t* start_row, int64_t* start_col,
@@ -272,11 +272,12 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     cudaStream_t st = ctx->stream;
     LongCkpt colck;
     uint8_t *d_ref = nullptr, *d_qry = nullptr, *d_out = nullptr; long long* d_res = nullptr;
+    unsigned long long* d_tiles = nullptr; uint32_t* d_slots = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     auto cleanup = [&]() {
         cudaStreamSynchronize(st);
         colck.free();
-        ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res);
+        ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res); ctx->pool.release(d_tiles); ctx->pool.release(d_slots);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
     };
 #define TCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
@@ -308,30 +309,62 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     const int TW = colck.CW, TH = colck.TH;
     const long long cap = (long long)ie + (long long)je;
     if (!pool_alloc(ctx, &d_ref, (size_t)je + 16) || !pool_alloc(ctx, &d_qry, (size_t)ie + 16) || !pool_alloc(ctx, &d_out, (size_t)(3 * cap) + 16) ||
-        !pool_alloc(ctx, &d_res, 4)) { cleanup(); return DPX_ERR_NOMEM; }
+        !pool_alloc(ctx, &d_res, 8)) { cleanup(); return DPX_ERR_NOMEM; }
     TCU(cudaMemcpyAsync(d_ref, ref, (size_t)je, cudaMemcpyHostToDevice, st));
     TCU(cudaMemcpyAsync(d_qry, qry, (size_t)ie, cudaMemcpyHostToDevice, st));
     LongBtArgs a{};
     a.ref = d_ref; a.qry = d_qry; a.ie = ie; a.je = je; a.match = p->match; a.mismatch = p->mismatch; a.gap = p->gap_open;
     a.TH = TH; a.TW = TW; a.colck = colck.base; a.col_stride = colck.stride;
     a.rowck = colck.rbase - 1; a.row_stride = colck.rstride;      // 0-based columns: rowck[r * stride + j] is column j >= 1
-    a.out = d_out; a.cap = cap; a.result = d_res;
-    const size_t smem = long_bt_smem(TH, TW);
+    a.out = d_out; a.cap = cap; a.state = d_res;
+    // ---- rounds: predict the tiles ahead of the walk, fill them all at once, walk until the walk stops or leaves them ----
     const int nt = std::max(32, ((TW + LONG_BT_CPT - 1) / LONG_BT_CPT + 31) & ~31);
-    if (nt > 256 || smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
-    TCU(cudaFuncSetAttribute(long_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    long long res[4] = {0, 0, 0, 0};
-    {
-        cudaEventRecord(ev[0], st);
-        long_bt_kernel<<<1, nt, smem, st>>>(a);
+    const size_t fill_smem = long_bt_fill_smem(TH, nt), walk_smem = long_bt_walk_smem(TH, TW), slot_words = long_bt_slot_words(TH, TW);
+    if (nt > 256 || walk_smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
+    int max_tiles = 2 * ctx->sm_count;
+    if (const char* e = getenv("DPX_LONG_BT_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 4096) max_tiles = v; }   // tests: short rounds
+    if (!pool_alloc(ctx, &d_tiles, (size_t)max_tiles) || !pool_alloc(ctx, &d_slots, slot_words * (size_t)max_tiles)) { cleanup(); return DPX_ERR_NOMEM; }
+    TCU(cudaFuncSetAttribute(long_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+    TCU(cudaFuncSetAttribute(long_tile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fill_smem, 1024)));
+    a.slots = d_slots; a.tiles = d_tiles;
+    long long state[5] = {ie, je, 0, 0, 0};                       // row, column, characters written, done, tiles walked
+    TCU(cudaMemcpyAsync(d_res, state, sizeof(state), cudaMemcpyHostToDevice, st));
+    double di = 1.0, dj = 1.0;                                    // the walk's direction, rows and columns per step of the prediction line
+    std::vector<unsigned long long> tiles;
+    const long long margin = std::max<long long>(TW / 8, 16);
+    cudaEventRecord(ev[0], st);
+    while (!state[3]) {
+        // the band: tiles under the line (i - t di, j - t dj) and `margin` columns either side of it, the current tile first
+        tiles.clear();
+        const long long i0 = state[0], j0 = state[1];
+        const double step = (double)std::min(TH, TW) / 8.0;
+        for (double t = 0; (int)tiles.size() < max_tiles; t += step) {
+            const long long ii = i0 - (long long)(t * di), jj = j0 - (long long)(t * dj);
+            if (ii < 1 || jj < 1) break;
+            for (long long dlt : {0LL, -margin, margin}) {
+                const long long jc = std::min<long long>(std::max<long long>(jj + dlt, 1), je);
+                const unsigned long long key = ((unsigned long long)((ii - 1) / TH) << 32) | (unsigned long long)((jc - 1) / TW);
+                if (std::find(tiles.begin(), tiles.end(), key) == tiles.end() && (int)tiles.size() < max_tiles) tiles.push_back(key);
+            }
+        }
+        a.ntiles = (int)tiles.size();
+        TCU(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(unsigned long long) * tiles.size(), cudaMemcpyHostToDevice, st));
+        long_tile_fill_kernel<<<a.ntiles, nt, fill_smem, st>>>(a);
+        long_walk_kernel<<<1, 256, walk_smem, st>>>(a);
         TCU(cudaGetLastError());
-        cudaEventRecord(ev[1], st);
-        TCU(cudaMemcpyAsync(res, d_res, sizeof(res), cudaMemcpyDeviceToHost, st));
+        TCU(cudaMemcpyAsync(state, d_res, sizeof(state), cudaMemcpyDeviceToHost, st));
         TCU(cudaStreamSynchronize(st));
-        float f = 0; cudaEventElapsedTime(&f, ev[0], ev[1]); ls.walk_ms = f;
+        ++ls.rounds;
+        const long long mi = i0 - state[0], mj = j0 - state[1];
+        if (mi + mj >= 64) { const double m = (double)std::max(mi, mj); di = mi / m; dj = mj / m; }
+        else { di = dj = 1.0; }
+        if (!state[3] && mi == 0 && mj == 0) { ctx->err = "long-pair traceback: the walk made no progress"; cleanup(); return DPX_ERR_CUDA; }
     }
-    const long long L = res[0];
-    ls.tiles = res[3]; ls.TH = TH; ls.TW = TW;
+    cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]);
+    { float f = 0; cudaEventElapsedTime(&f, ev[0], ev[1]); ls.walk_ms = f; }
+    const long long L = state[2];
+    const long long res[3] = {L, state[0], state[1]};
+    ls.tiles = state[4]; ls.TH = TH; ls.TW = TW;
     if (L <= 0 || L > cap) { ctx->err = "long-pair traceback: walk returned an impossible length"; cleanup(); return DPX_ERR_CUDA; }
     char* blob = (char*)g_host.take((size_t)(3 * (L + 1)));
     if (!blob) { cleanup(); return DPX_ERR_NOMEM; }

@@ -196,6 +196,6 @@ int dpx_align_long_pair_strings(dpx_ctx* ctx, const dpx_params* params, const ch
     if ((long double)params->match * (long double)std::min(R, Q) > 2.0e9L || Q > 0x7ffffff0u || R > 0x7ffffff0u) return DPX_ERR_RANGE;
     LongTraceStats ls;
     const int r = long_pair_strings(ctx, params, ref, R, qry, Q, score, end_row, end_col, start_row, start_col, lines, line_len, &ls);
-    if (r == DPX_OK && stage_ms) { stage_ms[0] = ls.fwd_ms; stage_ms[1] = ls.fwd_t_ms; stage_ms[2] = ls.walk_ms; stage_ms[3] = (double)ls.tiles; stage_ms[4] = ls.TH; stage_ms[5] = ls.TW; }
+    if (r == DPX_OK && stage_ms) { stage_ms[0] = ls.fwd_ms; stage_ms[1] = (double)ls.rounds; stage_ms[2] = ls.walk_ms; stage_ms[3] = (double)ls.tiles; stage_ms[4] = ls.TH; stage_ms[5] = ls.TW; }
     return r;
 }

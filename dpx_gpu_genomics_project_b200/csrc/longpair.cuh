@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
             if (dead) break;
         }
         const uint32_t pinbuf = PACK ? (((uint32_t)rin << 8) | qbuf) : 0u;
-        const bool steady = (sb >= 31) && (sb + 32 <= Q);          // every lane is inside the matrix for all 32 steps
+        // CK: a checkpoint row m * 2^rk_shift is crossed by the skewed lanes in the two blocks around it; those take the
+        // checked loop, which carries the dump code, so that the unrolled steady loop stays as small as the score-only kernel's
+        const bool ckblk = CK && ((sb & rk_mask) == 0 || ((sb + 32) & rk_mask) == 0);
+        const bool steady = (sb >= 31) && (sb + 32 <= Q) && !ckblk;    // every lane is inside the matrix for all 32 steps
 
 #define DPX_LONG_STEP(CHECKED)                                                                                   \
         {                                                                                                        \
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(128) long_sw_kernel(const LongArgs a) {
                     }                                                                                            \
                 }                                                                                                \
                 lastH = left;                                                                                    \
-                if (CK && (i & rk_mask) == 0) {                     /* a checkpoint row: once per 2^rk_shift rows */ \
+                if (CK && (CHECKED) && (i & rk_mask) == 0) {        /* a checkpoint row: once per 2^rk_shift rows */ \
                     int32_t* dst = a.rk_base + ((long long)(i >> a.rk_shift) - 1) * a.rk_stride + a.col_offset + cfirst; \
                     _Pragma("unroll")                                                                            \
                     for (int k = 0; k < K; ++k) if (cv[k]) dst[k] = TABLE ? Hc[k] - g : Hc[k];                   \

@@ -64,6 +64,20 @@ def test_every_tile_geometry_gives_the_same_strings(eng, k, monkeypatch):
     _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
 
 
+@pytest.mark.parametrize("tiles_per_round", ["1", "2", "5"])
+def test_mispredicted_rounds_only_cost_rounds(eng, tiles_per_round, monkeypatch):
+    """The tiles ahead of the walk are predicted and filled in bulk; DPX_LONG_BT_TILES shrinks a round to a few tiles so that the
+    walk keeps stepping onto tiles nobody predicted (and, with long gaps, off the predicted diagonal)."""
+    monkeypatch.setenv("DPX_LONG_K", "2"); monkeypatch.setenv("DPX_LONG_BT_TILES", tiles_per_round)
+    rng = synth.Rng(15)
+    r = synth.random_seq(rng, 3000)
+    q = r[:500] + r[900:1500] + synth.random_seq(rng, 400) + r[1500:]
+    st = _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
+    assert st["rounds"] >= st["tiles"] // int(tiles_per_round)
+    r, q = _pair(2500, 2600, 16)
+    _check(eng, r, q)
+
+
 def test_several_passes_with_checkpoints(eng, monkeypatch):
     monkeypatch.setenv("DPX_LONG_K", "2"); monkeypatch.setenv("DPX_LONG_CAP", "8")
     r, q = _pair(4000, 3500, 12)

@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
     L.dpx_set_stream.restype = C.c_int; L.dpx_set_stream.argtypes = [vp, vp]
     L.dpx_parse_input.restype = C.c_int
     L.dpx_parse_input.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(InputInfo)]
+    L.dpx_parse_fastx.restype = C.c_int
+    L.dpx_parse_fastx.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(InputInfo)]
     L.dpx_free.restype = None; L.dpx_free.argtypes = [vp]
     L.dpx_align_batch.restype = C.c_int
     L.dpx_align_batch.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.POINTER(vp), C.POINTER(vp)]

@@ -62,6 +62,20 @@ def parse_input(path: str) -> ParsedInput:
     return ParsedInput(seqs, pairs, {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_})
 
 
+def parse_fastx(path_refs: str, path_queries: str | None = None) -> ParsedInput:
+    """FASTA / FASTQ records as pairs (dpx_parse_fastx): one file = records alternate reference, query; two files = paired by order."""
+    L = _lib.lib()
+    pairs_p, seq_p, info = C.c_void_p(), C.c_void_p(), _lib.InputInfo()
+    _check(L.dpx_parse_fastx(path_refs.encode(), path_queries.encode() if path_queries else None, C.byref(pairs_p), C.byref(seq_p), C.byref(info)))
+    try:
+        n, nb = info.numPairs, info.numBytes
+        seqs = np.ctypeslib.as_array(C.cast(seq_p, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb].copy()
+        pairs = np.frombuffer(C.string_at(pairs_p, n * PAIR_DTYPE.itemsize), dtype=PAIR_DTYPE).copy() if n else np.zeros(0, PAIR_DTYPE)
+    finally:
+        L.dpx_free(pairs_p); L.dpx_free(seq_p)
+    return ParsedInput(seqs, pairs, {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_})
+
+
 @dataclass
 class BatchResult:
     scores: np.ndarray                    # int32[n]

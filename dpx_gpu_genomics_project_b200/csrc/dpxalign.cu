@@ -286,6 +286,8 @@ int dpx_parse_input(const char* path, dpx_seq_pair** pairs_out, char** seq_out, 
     return DPX_OK;
 }
 
+#include "host_fastx.cuh"
+
 // ---- DPX instruction evaluation -----------------------------------------------------------------
 int dpx_dpx_eval(dpx_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, const uint32_t* c, int n,
                  uint32_t* out, uint8_t* pred_hi, uint8_t* pred_lo) {

@@ -111,6 +111,11 @@ int         dpx_set_stream(dpx_ctx* ctx, void* cuda_stream);
  * dpx_free.  numCells is accumulated in 64-bit (the reference multiplies two ints, :100). */
 int         dpx_parse_input(const char* path, dpx_seq_pair** pairs, char** sequences, dpx_input_info* info);
 void        dpx_free(void* p);
+/* FASTA / FASTQ front-end: the same blob + index from '>' / '@' records (multi-line sequences joined,
+ * qualities skipped).  path_queries == NULL: the records of path_refs alternate reference, query; otherwise record k of
+ * path_refs is the reference of pair k and record k of path_queries its query (DPX_ERR_FORMAT if the counts differ).
+ * The blob is "ref\0qry\0ref\0qry\0..."; both arrays are malloc'ed (dpx_free). */
+int         dpx_parse_fastx(const char* path_refs, const char* path_queries, dpx_seq_pair** pairs, char** sequences, dpx_input_info* info);
 
 /* ---- one-call alignment: replaces the per-pair `Aligner a(ref, query, i, weights); a.align();`
  * loop of c++/main.cpp:237-252 for a whole batch.  Host buffers in, host buffers out

@@ -90,3 +90,59 @@ def test_synth_generators_are_deterministic_and_well_formed():
     # mutated queries stay similar to their reference: SW score far above the random-pair level
     s, _, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False)
     assert s.min() > 300
+
+
+def _pairs_of(p):
+    blob = p.sequences.tobytes()
+    return [(blob[int(r["referenceIdx"]): int(r["referenceIdx"]) + int(r["referenceSize"])],
+             blob[int(r["queryIdx"]): int(r["queryIdx"]) + int(r["querySize"])]) for r in p.pairs]
+
+
+def test_fasta_and_fastq_front_end(tmp_path, L):
+    """dpx_parse_fastx: multi-line FASTA, CRLF, FASTQ with '@' / '>' inside the qualities, one interleaved file or two files."""
+    from dpx_gpu_genomics_project_b200 import api, synth
+    rng = synth.Rng(3)
+    want = []
+    for k in range(7):
+        r = synth.random_seq(rng, 50 + 37 * k, b"ACGT")
+        want.append((r, synth.mutate(rng, r, 0.1, 0.05, 0.05, b"ACGT")))
+    want.append((b"", b"ACGT")); want.append((b"N", b""))
+
+    def fasta(seq, name, width=60, eol=b"\n"):
+        lines = [seq[i:i + width] for i in range(0, len(seq), width)] or [b""]
+        return b">" + name + eol + eol.join(lines) + eol
+
+    def fastq(seq, name):
+        qual = (b"@>+I" * (len(seq) // 4 + 1))[:len(seq)]
+        return b"@" + name + b"\n" + seq + b"\n+\n" + qual + b"\n"
+
+    one = tmp_path / "pairs.fa"
+    one.write_bytes(b"\n" + b"".join(fasta(r, b"ref%d some description" % k) + fasta(q, b"qry%d" % k, 13, b"\r\n") for k, (r, q) in enumerate(want)))
+    p = api.parse_fastx(str(one))
+    assert _pairs_of(p) == want
+    assert p.info["numPairs"] == len(want) and p.info["maxReferenceLength"] == max(len(r) for r, _ in want)
+    assert p.info["numCells"] == sum(len(r) * len(q) for r, q in want)
+
+    a, b = tmp_path / "refs.fq", tmp_path / "reads.fq"
+    a.write_bytes(b"".join(fastq(r, b"r%d" % k) for k, (r, _) in enumerate(want)))
+    b.write_bytes(b"".join(fastq(q, b"q%d/1" % k) for k, (_, q) in enumerate(want)))
+    assert _pairs_of(api.parse_fastx(str(a), str(b))) == want
+    # mixed: FASTA references, FASTQ reads
+    a2 = tmp_path / "refs.fa"
+    a2.write_bytes(b"".join(fasta(r, b"r%d" % k, 70) for k, (r, _) in enumerate(want)))
+    assert _pairs_of(api.parse_fastx(str(a2), str(b))) == want
+
+    bad = tmp_path / "odd.fa"
+    bad.write_bytes(fasta(b"ACGT", b"only"))
+    with pytest.raises(api.DpxError):
+        api.parse_fastx(str(bad))                          # a reference without its query
+    with pytest.raises(api.DpxError):
+        api.parse_fastx(str(a2), str(bad))                 # record counts differ
+    bad.write_bytes(b"ACGT\n")
+    with pytest.raises(api.DpxError):
+        api.parse_fastx(str(bad))                          # neither '>' nor '@'
+    bad.write_bytes(b"@r\nACGT\n+\nII\n")
+    with pytest.raises(api.DpxError):
+        api.parse_fastx(str(bad))                          # truncated qualities
+    with pytest.raises(api.DpxError):
+        api.parse_fastx(str(tmp_path / "missing.fa"))

@@ -372,3 +372,20 @@ def test_device_parser_matches_host_parser(eng, tmp_path):
     empty = tmp_path / "empty.txt"
     empty.write_bytes(b"")
     assert eng.align_file_text(api.make_params(api.LNW, flags=ALL), str(empty))[0] == b""
+
+
+def test_fasta_pairs_align_like_the_same_pairs_in_the_reference_format(eng, tmp_path):
+    """FASTA records through dpx_parse_fastx give the blob + index every entry point takes."""
+    rng = synth.Rng(41)
+    pp = []
+    for k in range(40):
+        r = synth.random_seq(rng, 80 + 5 * k, b"ACGT")
+        pp.append((r, synth.mutate(rng, r, 0.06, 0.03, 0.03, b"ACGT")))
+    fa = tmp_path / "pairs.fa"
+    fa.write_bytes(b"".join(b">r%d\n" % k + b"\n".join(r[i:i + 60] for i in range(0, len(r), 60)) + b"\n>q%d\n" % k + q + b"\n" for k, (r, q) in enumerate(pp)))
+    p = api.parse_fastx(str(fa))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    for algo in (api.LNW, api.ANW, api.LSW):
+        res = eng.align_batch(api.make_params(algo, flags=ALL), p.sequences, p.pairs)
+        s, e, t = ol.align_batch(ol.params(algo), blob, pairs)
+        assert (res.scores == s).all() and res.strings == t

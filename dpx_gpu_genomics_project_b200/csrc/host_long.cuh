@@ -272,12 +272,12 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     cudaStream_t st = ctx->stream;
     LongCkpt colck;
     uint8_t *d_ref = nullptr, *d_qry = nullptr, *d_out = nullptr; long long* d_res = nullptr;
-    unsigned long long* d_tiles = nullptr; uint32_t* d_slots = nullptr;
+    unsigned long long* d_tiles = nullptr; uint32_t *d_slots = nullptr, *d_edges = nullptr; int4* d_segs = nullptr; long long* d_seg_off = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     auto cleanup = [&]() {
         cudaStreamSynchronize(st);
         colck.free();
-        ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res); ctx->pool.release(d_tiles); ctx->pool.release(d_slots);
+        ctx->pool.release(d_ref); ctx->pool.release(d_qry); ctx->pool.release(d_out); ctx->pool.release(d_res); ctx->pool.release(d_tiles); ctx->pool.release(d_slots); ctx->pool.release(d_edges); ctx->pool.release(d_segs); ctx->pool.release(d_seg_off);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
     };
 #define TCU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); cleanup(); return DPX_ERR_CUDA; } } while (0)
@@ -323,11 +323,13 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     if (nt > 256 || walk_smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
     int max_tiles = 2 * ctx->sm_count;
     if (const char* e = getenv("DPX_LONG_BT_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 4096) max_tiles = v; }   // tests: short rounds
-    if (!pool_alloc(ctx, &d_tiles, (size_t)max_tiles) || !pool_alloc(ctx, &d_slots, slot_words * (size_t)max_tiles)) { cleanup(); return DPX_ERR_NOMEM; }
-    TCU(cudaFuncSetAttribute(long_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
+    if (!pool_alloc(ctx, &d_tiles, (size_t)max_tiles) || !pool_alloc(ctx, &d_slots, slot_words * (size_t)max_tiles) ||
+        !pool_alloc(ctx, &d_edges, long_bt_edge_words(TH, TW) * (size_t)max_tiles) || !pool_alloc(ctx, &d_segs, (size_t)max_tiles) ||
+        !pool_alloc(ctx, &d_seg_off, (size_t)max_tiles)) { cleanup(); return DPX_ERR_NOMEM; }
+    TCU(cudaFuncSetAttribute(long_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
     TCU(cudaFuncSetAttribute(long_tile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fill_smem, 1024)));
-    a.slots = d_slots; a.tiles = d_tiles;
-    long long state[5] = {ie, je, 0, 0, 0};                       // row, column, characters written, done, tiles walked
+    a.slots = d_slots; a.tiles = d_tiles; a.edges = d_edges; a.segs = d_segs; a.seg_off = d_seg_off;
+    long long state[8] = {ie, je, 0, 0, 0, 0, 0, 0};              // row, column, characters written, done, tiles walked, segments, error
     TCU(cudaMemcpyAsync(d_res, state, sizeof(state), cudaMemcpyHostToDevice, st));
     double di = 1.0, dj = 1.0;                                    // the walk's direction, rows and columns per step of the prediction line
     std::vector<unsigned long long> tiles;
@@ -350,7 +352,8 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
         a.ntiles = (int)tiles.size();
         TCU(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(unsigned long long) * tiles.size(), cudaMemcpyHostToDevice, st));
         long_tile_fill_kernel<<<a.ntiles, nt, fill_smem, st>>>(a);
-        long_walk_kernel<<<1, 256, walk_smem, st>>>(a);
+        long_chain_kernel<<<1, 32, 0, st>>>(a);
+        long_emit_kernel<<<a.ntiles, 256, walk_smem, st>>>(a);
         TCU(cudaGetLastError());
         TCU(cudaMemcpyAsync(state, d_res, sizeof(state), cudaMemcpyDeviceToHost, st));
         TCU(cudaStreamSynchronize(st));
@@ -358,6 +361,7 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
         const long long mi = i0 - state[0], mj = j0 - state[1];
         if (mi + mj >= 64) { const double m = (double)std::max(mi, mj); di = mi / m; dj = mj / m; }
         else { di = dj = 1.0; }
+        if (state[6]) { ctx->err = "long-pair traceback: transfer tables and directions disagree"; cleanup(); return DPX_ERR_CUDA; }
         if (!state[3] && mi == 0 && mj == 0) { ctx->err = "long-pair traceback: the walk made no progress"; cleanup(); return DPX_ERR_CUDA; }
     }
     cudaEventRecord(ev[1], st); cudaEventSynchronize(ev[1]);

@@ -1,12 +1,13 @@
 """CPU model of the long-pair traceback scheme (csrc/longtrace.cuh), checked against the oracle's full-matrix backtrack.
 
-The GPU keeps no traceback for a 1 Mbp x 1 Mbp matrix.  It keeps CHECKPOINTS: H on every TW-th column (the right edges of the
-forward kernel's column blocks) and on every TH-th row (the right edges of the same kernel run on the transposed problem: the
-Smith-Waterman matrix of (qry, ref) is the transpose of that of (ref, qry)).  The walk then re-fills one TH x TW tile at a time
-from its top row and left column, with the reference's direction rule (c++/LinearSmithWaterman.cpp:104-108), follows the
-directions to the tile's edge and moves on.  This file restates that scheme in numpy at toy tile sizes: it pins the checkpoint
-indexing and the tile-edge handling; the CUDA kernels are a transcription of `walk` below and are tested on the GPU against the
-same oracle (tests/test_gpu_longpair.py).  Test infrastructure only — nothing here is on the product path."""
+The GPU keeps no traceback for a 1 Mbp x 1 Mbp matrix.  It keeps CHECKPOINTS: H on every TW-th column (what each warp of the
+forward kernel reads from its left neighbour) and on every TH-th row (what each lane holds when it crosses such a row).  The walk
+then re-fills one TH x TW tile at a time from its top row and left column, with the reference's direction rule
+(c++/LinearSmithWaterman.cpp:104-108), follows the directions to the tile's edge and moves on.  This file restates that scheme in
+numpy at toy tile sizes: it pins the checkpoint indexing, the tile-edge handling and the per-tile transfer tables (exit cell and
+move count of a walk entering through the tile's last row or column) that let the GPU hop over tiles without reading directions.
+The CUDA kernels are a transcription of `walk` / `transfer` below and are tested on the GPU against the same oracle
+(tests/test_gpu_longtrace.py).  Test infrastructure only — nothing here is on the product path."""
 import numpy as np
 import pytest
 
@@ -95,3 +96,42 @@ def test_checkpointed_tile_walk_equals_full_matrix_backtrack(seed, R, Q, TH, TW,
     a, b, c, i0, j0, tiles = walk(ref, qry, m, x, g, ie, je, colck, rowck, TH, TW)
     assert (a, b, c) == t[0]
     assert tiles >= 1 and H[i0, j0] == 0
+
+
+def transfer(D):
+    """Exit cell (tile-relative, -1 = the row above / column left of the tile) and move count of the walk from every cell of a tile
+    whose directions are D[1..h][1..w] — the recurrence the fill kernel carries beside H: a cell takes over its predecessor's answer."""
+    h, w = D.shape[0] - 1, D.shape[1] - 1
+    E = {}
+    for a in range(1, h + 1):
+        for b in range(1, w + 1):
+            d = D[a, b]
+            if d == STOP:
+                E[a, b] = (a - 1, b - 1, 0, True)
+                continue
+            pa, pb = (a - 1, b - 1) if d == DIAG else (a - 1, b) if d == UP else (a, b - 1)
+            if pa == 0 or pb == 0:
+                E[a, b] = (pa - 1, pb - 1, 1, False)
+            else:
+                x, y, n, st = E[pa, pb]
+                E[a, b] = (x, y, n + 1, st)
+    return E
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_transfer_table_equals_walking_the_directions(seed):
+    rng = np.random.default_rng(seed)
+    h, w = 13, 17
+    D = rng.integers(0, 4, size=(h + 1, w + 1)).astype(np.int8)
+    D[rng.random(D.shape) < 0.7] = DIAG
+    E = transfer(D)
+    for a, b in [(h, y) for y in range(1, w + 1)] + [(x, w) for x in range(1, h + 1)]:
+        x, y, n, stopped = a, b, 0, False
+        while x > 0 and y > 0:
+            d = D[x, y]
+            if d == STOP:
+                stopped = True
+                break
+            x, y = (x - 1, y - 1) if d == DIAG else (x - 1, y) if d == UP else (x, y - 1)
+            n += 1
+        assert E[a, b] == (x - 1, y - 1, n, stopped)

@@ -78,7 +78,27 @@ def main():
                 assert res.strings == t, "strings"
                 if rng.integers(4) == 0:
                     assert eng.align_batch_text(api.make_params(algo, flags=flags, **w), blob, pairs) == ol.format_text(s, t), "text"
+            if algo == api.LSW and len(pairs) and rng.integers(3) == 0:
+                # the long-pair entry points on one pair of the batch, at a random lane width / tile geometry / round size
+                k = int(rng.integers(len(pairs))); pr = pairs[k]
+                ref = blob[int(pr["referenceIdx"]): int(pr["referenceIdx"]) + int(pr["referenceSize"])].tobytes()
+                qry = blob[int(pr["queryIdx"]): int(pr["queryIdx"]) + int(pr["querySize"])].tobytes()
+                if len(ref) and len(qry):
+                    os.environ["DPX_LONG_K"] = str(int(rng.choice([0, 2, 4, 8, 16, 32])))
+                    os.environ["DPX_LONG_BT_TILES"] = str(int(rng.choice([0, 1, 3, 40])))
+                    os.environ["DPX_LONG_CAP"] = str(int(rng.choice([0, 0, 8, 16])))
+                    tag += f" long pair {k} env K={os.environ['DPX_LONG_K']} tiles={os.environ['DPX_LONG_BT_TILES']} cap={os.environ['DPX_LONG_CAP']}"
+                    p1 = api.make_params(api.LSW, **w)
+                    s1, e1, t1 = ol.align_batch(ol.params(algo, **w), blob, pairs[k:k + 1], strings=True)
+                    want = (int(s1[0]), int(e1[0][0]), int(e1[0][1]))
+                    assert eng.align_long_pair(p1, ref, qry) == want, "long pair score / end cell"
+                    end, start, lines, st = eng.align_long_pair_strings(p1, ref, qry)
+                    assert end == want and lines == t1[0], "long pair strings"
+                    for v in ("DPX_LONG_K", "DPX_LONG_BT_TILES", "DPX_LONG_CAP"):
+                        os.environ.pop(v, None)
         except (AssertionError, api.DpxError) as ex:       # keep going: one run should list every distinct failure
+            for v in ("DPX_LONG_K", "DPX_LONG_BT_TILES", "DPX_LONG_CAP"):
+                os.environ.pop(v, None)
             failures.append(f"{type(ex).__name__}: {ex} :: {tag}")
             print("FAIL", failures[-1], flush=True)
             if len(failures) >= 10:

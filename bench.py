@@ -20,6 +20,9 @@ collective, weak scaling); value = cells of all ranks / max-over-ranks device ti
   cpu_baseline  the reference's own C++ classes (oracle/_ref/ref_align) on the host cores, bounded sample (config 4: the C
             port, because the reference's banded class is not executable).
 
+`--config 5` is BASELINE configs[4]: ONE 1 Mbp x 1 Mbp LinearSmithWaterman pair, score + end cell; with N > 1 the pair is split into
+column stripes (strong scaling, see main_long).
+
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
 """
 import argparse
@@ -59,6 +62,11 @@ WORKLOADS = {
             title="BandedSmithWaterman band 64: {pairs} pairs x (10 kbp x 10 kbp) per GPU, 2-bit traceback + alignment strings, in-band cells, "
                   "match 3 / mismatch -1 / gap -2", cpu_per_core=0.05e9, tb_bytes_per_cell=0.25),
 }
+
+
+# BASELINE config 5: ONE pair of 1 Mbp x 1 Mbp, LinearSmithWaterman score + end cell (strong scaling: column stripes over NVLink)
+LONG = dict(R=1_000_000, Q=1_000_000, seed=0x5EED0005, weights=dict(match=3, mismatch=-1, gap_open=-2), mutate=(0.01, 0.001, 0.001),
+            cpu_sample=80_000, kernel="long_sw_kernel<K=32,PACK,TABLE>", sass="long_s32:K=32,pack=True,table=True,ck=False")
 
 
 def env_int(name, default):
@@ -193,19 +201,139 @@ def cpu_sample_size(wl, n_pairs, cores, seconds=12.0):
     return int(max(min(n_pairs, 2 * cores), min(n_pairs, wl["cpu_per_core"] * cores * seconds / cells_per_pair)))
 
 
+def main_long(args):
+    """--config 5: one step = one alignment of the 1 Mbp x 1 Mbp pair.  N > 1: the reference columns are split into one stripe per
+    GPU (multi-GPU mode B, the right edge of a stripe streams to the next GPU by NVLink P2P stores): total work is fixed, so
+    scaling is "strong".  value = R*Q / max-over-ranks kernel time (CUDA events inside the library, sequences resident);
+    e2e = the host-buffer call (N = 1: dpx_align_long_pair, H2D of both sequences + kernel + D2H of the result;
+    N > 1: reset + barrier + run + gather of the per-stripe results, sequences resident since stripe creation)."""
+    import oracle_lib as ol
+    from dpx_gpu_genomics_project_b200 import synth
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    cores = os.cpu_count() or 1
+    R, Q, w = LONG["R"], LONG["Q"], LONG["weights"]
+    if args.pairs:                                            # --pairs N shrinks the pair to N x N bases (smoke runs)
+        R = Q = args.pairs
+
+    def make_pair(r_len, q_len):
+        img = synth.mutated_fixed_file_bytes(1, r_len, q_len, LONG["seed"], *LONG["mutate"])
+        return img[2:2 + r_len].tobytes(), img[3 + r_len:3 + r_len + q_len].tobytes()
+
+    config = {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp (query = reference mutated 1 % / 0.1 % / 0.1 %), score + end cell, "
+                          "match 3 / mismatch -1 / gap -2", "baseline_config": 5, "R": R, "Q": Q,
+              "sharding": f"{max(args.gpus, world)} column stripe(s), right edges streamed GPU to GPU over NVLink P2P (no NCCL on the data path)",
+              "l2": "256 MiB memset between timed steps", "seed": f"{LONG['seed']:#x}"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n = min(LONG["cpu_sample"], R)
+        ref, qry = make_pair(n, n)
+        secs = []
+        for _ in range(max(1, min(args.steps, 2))):
+            t0 = time.perf_counter(); ol.lsw_score_only(ol.params(ol.LSW, **w), ref, qry); secs.append(time.perf_counter() - t0)
+        v = n * n / float(np.mean(secs)) / 1e9
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": max(args.gpus, world), "steps": len(secs), "warmup": 0,
+            "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": 1, "kind": "port",
+                             "sample": f"a {n} x {n} bp pair of the same generator; rolling-row C port of LinearSmithWaterman (the reference's "
+                                       "full-matrix class needs 8 B per cell: 8 TB at 1 Mbp x 1 Mbp), 1 thread"},
+            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return
+
+    import torch
+    from dpx_gpu_genomics_project_b200 import api, longpair
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libdpxalign has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
+    ref, qry = make_pair(R, Q)
+    eng = api.Engine(local)
+    params = api.make_params(api.LSW, **w)
+    job = longpair.StripedLongPair(eng, params, ref, qry, rank, world, dist)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    steps = min(args.steps, 10)
+    for _ in range(args.warmup):
+        res, _ = job.run()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_steps, wall = [], []
+    for _ in range(steps):
+        flush.zero_(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, ms = job.run()                                   # barrier inside; ms = max over ranks of the stripes' kernel times
+        wall.append(time.perf_counter() - t0); ms_steps.append(ms)
+    sampler.stop_flag.set(); sampler.join(timeout=1.0)
+    e2e_s = float(np.mean(wall))
+    h2d = 0
+    if world == 1:                                            # the host-buffer call of the ABI
+        eng.align_long_pair(params, ref, qry)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            res1 = eng.align_long_pair(params, ref, qry)
+        e2e_s = (time.perf_counter() - t0) / 3
+        assert tuple(res1) == tuple(res), "one-call and striped paths disagree"
+        h2d = R + Q
+    job.free()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    ms_per_step = float(np.mean(ms_steps))
+    cells = float(R) * float(Q)
+    value = cells / (ms_per_step * 1e-3) / 1e9
+    clocks = sampler.result()
+    peaks, _ = measured_peaks()
+    f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+    roofline = {"bound": "dpx_issue", "achieved": value, "unit": "GCUPS", "kernel": LONG["kernel"], "traffic": None, "kernel_ms": ms_per_step}
+    alu_pc, issue_pc = sass_counts(LONG["sass"])
+    if alu_pc and world == 1 and R >= 600_000:                # the lane width (hence the SASS loop) is K = 32 only for one wide stripe
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * sms * f_mhz * 1e6 / 1e9
+        roofline.update({"peak": peak, "frac": value / peak,
+                         "model": {"alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "sms": sms, "sm_mhz": f_mhz, "sass_key": LONG["sass"],
+                                   "note": "a chain of 977 warps (1.65 per SM sub-partition), each row step a dependent chain: latency-bound below the issue roofline"}})
+    out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+           "clocks": clocks, "result": list(res),
+           "e2e": {"value": cells / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20 * world, "ms_per_step": e2e_s * 1e3,
+                   "api": "dpx_align_long_pair (C ABI), host sequences in, (score, row, col) out" if world == 1 else
+                          "dpx_stripe_reset + barrier + dpx_stripe_run + gather of the per-stripe results; sequences resident since dpx_stripe_create"},
+           "gpu_launches": steps * 1, "roofline": roofline}
+    if not args.no_cpu_baseline and world == 1:
+        n = min(LONG["cpu_sample"], R)
+        r2, q2 = make_pair(n, n)
+        t0 = time.perf_counter(); want = ol.lsw_score_only(ol.params(ol.LSW, **w), r2, q2); dt = time.perf_counter() - t0
+        got = eng.align_long_pair(params, r2, q2)
+        out["parity_spot_check"] = tuple(got) == tuple(want)
+        out["cpu_baseline"] = {"value": n * n / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": dt,
+                               "sample": f"a {n} x {n} bp pair of the same generator, rolling-row C port (the reference's full-matrix class cannot "
+                                         "allocate this problem), 1 thread; also the parity check of the GPU result at that size"}
+    print(json.dumps(out))
+    eng.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dpx", choices=["dpx", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json config number (SURVEY.md §8d)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS) + [5], help="BASELINE.json config number (SURVEY.md §8d)")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--score-only", action="store_true", help="config 2: omit end coordinates; configs 3/4: no traceback / strings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "dpx":
         args.warmup = 3
+    if args.config == 5:
+        return main_long(args)
     wl = dict(WORKLOADS[args.config])
     n_pairs = args.pairs or wl["pairs"]
     want_strings = wl["strings"] and not args.score_only

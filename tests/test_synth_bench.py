@@ -52,3 +52,18 @@ def test_workload_table_names_the_baseline_configs():
     assert bench.WORKLOADS[4]["weights"]["band"] == 64 and bench.WORKLOADS[4]["pairs"] == 10_000
     for wl in bench.WORKLOADS.values():
         assert bench.cpu_sample_size(wl, wl["pairs"], 16) >= 1
+
+
+def test_config5_reference_arm_prints_the_contract_line():
+    """bench.py --config 5 --impl reference (CPU only): the rolling-row port on a bounded sample, same JSON shape as the other configs."""
+    import json
+    import subprocess
+    import sys
+    bench = _bench()
+    assert (bench.LONG["R"], bench.LONG["Q"]) == (1_000_000, 1_000_000)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--config", "5", "--impl", "reference", "--pairs", "3000", "--steps", "1"],
+                         check=True, capture_output=True, timeout=300).stdout
+    line = json.loads(out.decode().strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "GCUPS" and line["scaling"] == "strong" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["baseline_config"] == 5

@@ -40,6 +40,9 @@ SPECS = [
      lambda g: dict(M=int(g[0]), extra=bool(int(g[1])), traceback=bool(int(g[2])), cells=2 * (2 * int(g[0]) + int(g[1])))),
     (r"wf_fill_kernelILi(\d+)ELb([01])ELi(\d+)E", "wavefront_s32",
      lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=int(g[2]))),
+    # long-pair chain: the steady row loop is unrolled 4 row steps of K cells (several overlapping back-edges: pick the densest loop)
+    (r"long_sw_kernelILi(\d+)ELb([01])ELb([01])ELb([01])E", "long_s32",
+     lambda g: dict(K=int(g[0]), pack=bool(int(g[1])), table=bool(int(g[2])), ck=bool(int(g[3])), cells=4 * int(g[0]), largest=True)),
 ]
 
 
@@ -55,12 +58,16 @@ def main():
             info = fn(m.groups())
             # hot loop = the innermost loop with the most DPX (VIMNMX*/VIADDMNMX*) or max instructions
             best = None
+            cand = []
             for (s, e) in loops(ins):
                 body = [t for a, t in ins if s <= a <= e]
                 dpx = sum(1 for t in body if re.match(r"(@!?U?P\d+\s+)?VI(ADD)?MNMX", t))
-                if dpx == 0:
-                    continue
-                if best is None or len(body) < len(best[0]):
+                if dpx:
+                    cand.append((s, e, body, dpx))
+            if info.get("largest"):                           # the unrolled steady loop = the loop with the highest DPX density
+                cand = [max(cand, key=lambda c: c[3] / len(c[2]))] if cand else []
+            for (s, e, body, dpx) in cand:
+                if best is None or (len(body) > len(best[0]) if info.get("largest") else len(body) < len(best[0])):
                     best = (body, dpx)
             if best is None:
                 continue
@@ -69,7 +76,7 @@ def main():
             by_pipe = collections.Counter()
             for op, c in hist.items():
                 by_pipe[pipe(op)] += c
-            cells = info.pop("cells")
+            cells = info.pop("cells"); info.pop("largest", None)
             key = label + ":" + ",".join(f"{k}={v}" for k, v in info.items())
             res[key] = dict(mangled=name, loop_instructions=len(body), cells_per_trip=cells, dpx_instructions=dpx,
                             alu_pipe=by_pipe["alu"], fma_pipe=by_pipe["fma"], other=by_pipe["other"],

@@ -50,6 +50,36 @@ def main():
     kernels = {}
     failures = []
     while time.time() < t_end:
+        if rng.integers(120) == 0:
+            # a big batch: the chunked one-call pipeline (>= 64k pairs, score / end cell) or the two-slab traceback pipeline (>= 32k pairs, strings)
+            n = int(rng.integers(33_000, 140_000))
+            seed_b = int(rng.integers(1 << 30))
+            if rng.integers(2):
+                blob, pairs = synth.ragged_mutated_blob_pairs(n, 8, int(rng.integers(20, 70)), seed_b, 0.05, 0.02, 0.02)
+            else:
+                L = int(rng.integers(10, 60)); blob, pairs = synth.uniform_blob_pairs(n, L, int(rng.integers(10, 60)), seed_b)
+            algo = int(rng.integers(4))
+            w = dict(match=3, mismatch=-1, gap_open=-2)
+            if algo == api.ANW:
+                w.update(gap_open=-3, gap_extend=-1)
+            if algo == api.BSW:
+                w["band"] = int(rng.choice([3, 16, 40]))
+            strings = bool(rng.integers(2))
+            flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if strings else 0)
+            tag = f"case {cases} seed {seed} BIG n {n} algo {algo} w {w} strings {strings}"
+            try:
+                res = eng.align_batch(api.make_params(algo, flags=flags, **w), blob, pairs)
+                s, e, t = ol.align_batch(ol.params(algo, **w), blob, pairs, strings=strings, threads=16)
+                assert (res.scores == s).all(), f"scores, first bad {np.flatnonzero(res.scores != s)[:5]}"
+                assert (res.end_row_col == e).all(), "end cells"
+                if strings:
+                    assert res.strings == t, "strings"
+                kernels["big"] = kernels.get("big", 0) + 1
+            except (AssertionError, api.DpxError) as ex:
+                failures.append(f"{type(ex).__name__}: {ex} :: {tag}")
+                print("FAIL", failures[-1], flush=True)
+            cases += 1
+            continue
         (blob, pairs), alpha, span, n = make_batch(rng, int(rng.integers(1 << 30)))
         algo = int(rng.integers(4))
         m = int(rng.integers(1, 7)); x = -int(rng.integers(0, 6)); g = -int(rng.integers(1, 8))
@@ -107,7 +137,7 @@ def main():
     if failures:
         print(f"fuzz FAILED: {len(failures)} of {cases} batches")
         sys.exit(1)
-    print(f"fuzz ok: {cases} batches in {seconds:.0f} s, kernel ids used {dict(sorted(kernels.items()))}")
+    print(f"fuzz ok: {cases} batches in {seconds:.0f} s, kernel ids used {dict(sorted(kernels.items(), key=str))}")
 
 
 if __name__ == "__main__":

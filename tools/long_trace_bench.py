@@ -1,7 +1,7 @@
 """BASELINE config 5 with its alignment: 1 Mbp x 1 Mbp LinearSmithWaterman, score + end cell + the three printed lines, on one GPU.
 Prints one JSON line with the stage times (device ms) and the structural checks of the result (no full-matrix oracle exists at
 this size: the score / end cell are checked against the rolling-row oracle only when --oracle is given, ~20 min of CPU).
-usage: python tools/long_trace_bench.py [R] [Q] [--oracle]"""
+usage: python tools/long_trace_bench.py [R] [Q] [--oracle] [--mut=sub,ins,del]"""
 import json
 import os
 import sys
@@ -20,11 +20,15 @@ def main():
     Q = int(args[1]) if len(args) > 1 else R
     rng = synth.Rng(0x5EED0005)
     ref = synth.random_seq(rng, R)
-    qry = synth.mutate(rng, ref, 0.01, 0.001, 0.001)
+    mut = (0.01, 0.001, 0.001)
+    for a in sys.argv[1:]:
+        if a.startswith("--mut="):
+            mut = tuple(float(x) for x in a[6:].split(","))
+    qry = synth.mutate(rng, ref, *mut)
     qry = (qry + synth.random_seq(rng, Q))[:Q]
     eng = api.Engine(0)
     p = api.make_params(api.LSW)
-    out = {"R": R, "Q": Q}
+    out = {"R": R, "Q": Q, "mutation": list(mut)}
     for rep in range(2):                       # first call pays the 12 GB of cudaMalloc page mapping
         t0 = time.perf_counter()
         end, start, lines, st = eng.align_long_pair_strings(p, ref, qry)

@@ -12,7 +12,7 @@
 // (UP if up == H, else LEFT if left == H, else DIAG; STOP iff H == 0, :104-108 and :222), follow the directions to the tile's
 // edge, move to the neighbouring tile.  At most Q / TH + R / TW + 1 tiles are ever filled: 2 * 10^9 cells for the 10^12-cell
 // matrix.  Every H the walk looks at is the forward pass's own value, so the strings are those the reference's full-matrix
-// walk would print (tests: bit-exact against the oracle's full-matrix backtrack up to 30 kbp, tile-size invariance).
+// walk would print (tests/test_gpu_longtrace.py: bit-exact against the oracle's full-matrix backtrack up to 12 kbp at every tile size).
 //
 // Tiles do not depend on the walk, only on their borders, so they are filled AHEAD of it, many at a time: the host predicts
 // the tiles the path will cross (a band around the line through the current cell along the walk's recent direction, diagonal

@@ -47,3 +47,29 @@ def test_dropin_main_reports_parse_errors_like_the_reference(tmp_path):
     assert r.returncode == 1 and b"Number of lines not a multiple of 3" in r.stderr
     r = subprocess.run([os.path.join(HOST, "main"), "-pairs", str(tmp_path / "nope.txt")], capture_output=True)
     assert r.returncode == 1 and b"Could not open file" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["adversarial", "mid"])
+def test_dropin_main_long_flag_prints_the_same_blocks(name):
+    """-long sends every pair through the checkpointed long-pair path (dpx_align_long_pair_strings): same bytes as the batch path."""
+    path = os.path.join(GOLD, f"{name}.in.txt")
+    out = subprocess.run([os.path.join(HOST, "main"), "-pairs", path, "-match", "3", "-mismatch", "-1", "-open", "-2", "-algo", "LSW", "-long"],
+                         check=True, capture_output=True).stdout
+    lines = out.split(b"\n")
+    body = b"\n".join(lines[2:-3]) + b"\n"
+    assert body == open(os.path.join(GOLD, f"{name}.LSW.out.txt"), "rb").read()
+
+
+def test_dropin_main_reads_fasta_pairs(tmp_path):
+    """-fastx: the same pairs as FASTA records (multi-line) give the golden blocks of the 3-line file."""
+    src = open(os.path.join(GOLD, "mid.in.txt"), "rb").read().split(b"\n")
+    fa = tmp_path / "mid.fa"
+    with open(fa, "wb") as f:
+        for k in range(len(src) // 3):
+            for tag, seq in ((b"r", src[3 * k + 1]), (b"q", src[3 * k + 2])):
+                f.write(b">" + tag + b"%d\n" % k + b"\n".join(seq[i:i + 50] for i in range(0, len(seq), 50)) + b"\n")
+    out = subprocess.run([os.path.join(HOST, "main"), "-fastx", str(fa), "-match", "3", "-mismatch", "-1", "-open", "-2", "-algo", "LNW"],
+                         check=True, capture_output=True).stdout
+    lines = out.split(b"\n")
+    body = b"\n".join(lines[2:-3]) + b"\n"
+    assert body == open(os.path.join(GOLD, "mid.LNW.out.txt"), "rb").read()

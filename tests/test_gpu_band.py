@@ -97,3 +97,19 @@ def test_wider_bands_and_odd_weights_fall_back(eng):
     blob, pairs = _ragged(5, 40, 1, 200)
     _check(eng, blob, pairs, 97, want_kernel=KERNEL_WAVEFRONT)
     _check(eng, blob, pairs, 20, want_kernel=KERNEL_WAVEFRONT, match=3, mismatch=0, gap_open=-2)
+
+
+@pytest.mark.parametrize("n", [8192, 13001])
+def test_large_batches_with_strings_and_repeated_runs(eng, n):
+    """Thousands of pairs with strings (several waves of warps, the traceback slab of the whole batch), run twice on the same batch:
+    the second run reuses the slab and the string buffers."""
+    blob, pairs = synth.ragged_mutated_blob_pairs(n, 20, 90, 0xBA5D + n, 0.05, 0.02, 0.02)
+    b = eng.upload(blob, pairs)
+    s, e, t = ol.align_batch(ol.params(ol.BSW, band=9), blob, pairs, strings=True, threads=16)
+    for _ in range(2):
+        b.run(api.make_params(api.BSW, flags=ALL, band=9)); b.sync()
+        assert b.stats()["kernel_id"] == KERNEL_BAND
+        res = b.fetch()
+        assert (res.scores == s).all() and (res.end_row_col == e).all()
+        assert res.strings == t
+    b.free()

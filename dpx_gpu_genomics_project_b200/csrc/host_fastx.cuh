@@ -21,35 +21,45 @@ static int fastx_slurp(const char* path, std::vector<char>& buf) {
     return got == (size_t)sz ? DPX_OK : DPX_ERR_IO;
 }
 
-// Appends every record's bases to `blob` (NUL-terminated) and its (offset, length) to `recs`.
+// Appends every record's bases to `blob` (NUL-terminated) and its (offset, length) to `recs`.  Works a line at a time (memchr + one
+// bulk append per line), so multi-GB files parse at memory speed.
 static int fastx_records(const std::vector<char>& in, std::vector<char>& blob, std::vector<std::pair<size_t, size_t>>& recs) {
     const size_t n = in.size();
+    const char* d = in.data();
     size_t i = 0;
-    auto skip_blank = [&]() { while (i < n && (in[i] == '\n' || in[i] == '\r' || in[i] == ' ' || in[i] == '\t')) ++i; };
-    auto skip_line = [&]() { while (i < n && in[i] != '\n') ++i; if (i < n) ++i; };
+    auto skip_blank = [&]() { while (i < n && (d[i] == '\n' || d[i] == '\r' || d[i] == ' ' || d[i] == '\t')) ++i; };
+    auto line_end = [&](size_t from) { const void* p = from < n ? memchr(d + from, '\n', n - from) : nullptr; return p ? (size_t)((const char*)p - d) : n; };
+    auto skip_line = [&]() { i = line_end(i); if (i < n) ++i; };
+    // appends the line starting at i without blanks / '\r', leaves i on the next line
+    auto take_line = [&]() {
+        const size_t e = line_end(i);
+        size_t a = i, b = e;
+        while (b > a && (d[b - 1] == '\r' || d[b - 1] == ' ' || d[b - 1] == '\t')) --b;
+        if (memchr(d + a, ' ', b - a) || memchr(d + a, '\t', b - a)) { for (size_t k = a; k < b; ++k) if (d[k] != ' ' && d[k] != '\t' && d[k] != '\r') blob.push_back(d[k]); }
+        else blob.insert(blob.end(), d + a, d + b);
+        i = e < n ? e + 1 : n;
+    };
+    blob.reserve(blob.size() + n);
     skip_blank();
     while (i < n) {
-        const char kind = in[i];
+        const char kind = d[i];
         if (kind != '>' && kind != '@') return DPX_ERR_FORMAT;
         skip_line();                                                 // header
         const size_t start = blob.size();
         if (kind == '>') {
-            while (i < n && in[i] != '>') {                          // sequence lines up to the next record
-                const char c = in[i++];
-                if (c != '\n' && c != '\r' && c != ' ' && c != '\t') blob.push_back(c);
-            }
+            while (i < n && d[i] != '>') take_line();                // sequence lines up to the next record
         } else {
-            while (i < n && in[i] != '+') {                          // sequence lines up to the '+' separator (never a base)
-                const char c = in[i++];
-                if (c != '\n' && c != '\r' && c != ' ' && c != '\t') blob.push_back(c);
-            }
+            while (i < n && d[i] != '+') take_line();                // sequence lines up to the '+' separator (never a base)
             if (i >= n) return DPX_ERR_FORMAT;
             skip_line();                                             // '+' line
             size_t q = 0;
             const size_t len = blob.size() - start;
             while (i < n && q < len) {                               // quality: as many characters as bases, '@' and '>' included
-                const char c = in[i++];
-                if (c != '\n' && c != '\r') ++q;
+                const size_t e = line_end(i);
+                size_t b = e;
+                while (b > i && d[b - 1] == '\r') --b;
+                q += b - i;
+                i = e < n ? e + 1 : n;
             }
             if (q != len) return DPX_ERR_FORMAT;
         }

@@ -364,6 +364,86 @@ int orc_align_batch(const orc_params* p, const char* seqs, const orc_pair* pairs
     return 0;
 }
 
+/* ---------------------------------------------------------------------------------
+ * LinearSmithWaterman with BACKTRACK_ALL (c++/LinearSmithWaterman.h:9, off as shipped; pinned on the reference compiled with
+ * -DBACKTRACK_ALL, oracle/_ref/ref_align_all): EVERY cell holding the maximum starts a walk.  Start cells are queued bottom-right
+ * to top-left (rows descending, columns descending, c++/LinearSmithWaterman.cpp:126-143); the queue advances every walk by one
+ * move in turn (:163-226), so finished alignments come out ordered by their number of moves, ties in queue order.  Each walk
+ * follows the ONE stored direction per cell (UP > LEFT > DIAG), like the single-path mode.  Score 0: the reference's all-maxima
+ * mode walks uninitialised cells (undefined behaviour); this restatement prints the three empty lines of the single-path mode.
+ * Returns a malloc'ed text of the reference's stdout blocks for the batch ("<i> | <score>" then REF / REL / QRY per alignment). */
+typedef struct { int i, j; int64_t len; size_t order; } orc_start;
+static int orc_start_cmp(const void* a, const void* b) {
+    const orc_start* x = (const orc_start*)a; const orc_start* y = (const orc_start*)b;
+    if (x->len != y->len) return x->len < y->len ? -1 : 1;
+    return x->order < y->order ? -1 : (x->order > y->order ? 1 : 0);
+}
+int orc_lsw_all_text(const orc_params* p, const char* seqs, const orc_pair* pairs, size_t n, int first_index,
+                     char** text_out, size_t* bytes_out, int64_t* n_alignments) {
+    size_t cap = 1 << 16, len = 0; char* out = (char*)malloc(cap);
+    int64_t total = 0;
+    #define ORC_RESERVE(extra) do { if (len + (size_t)(extra) + 64 > cap) { while (len + (size_t)(extra) + 64 > cap) cap *= 2; out = (char*)realloc(out, cap); } } while (0)
+    for (size_t k = 0; k < n; ++k) {
+        const char* r = seqs + pairs[k].referenceIdx; const char* q = seqs + pairs[k].queryIdx;
+        const int R = pairs[k].referenceSize, Q = pairs[k].querySize;
+        const size_t W = (size_t)R + 1, N = W * ((size_t)Q + 1);
+        int32_t* H = (int32_t*)calloc(N, sizeof(int32_t));
+        uint8_t* D = (uint8_t*)calloc(N, 1);
+        const int32_t g = p->gap_open;
+        int32_t best = 0;
+        for (int i = 1; i <= Q; ++i)
+            for (int j = 1; j <= R; ++j) {
+                int32_t up = H[(i - 1) * W + j] + g, left = H[i * W + (j - 1)] + g;
+                int32_t diag = H[(i - 1) * W + (j - 1)] + (q[i - 1] == r[j - 1] ? p->match : p->mismatch);
+                int32_t lc = left > diag ? left : diag, t = up > lc ? up : lc, h = t > 0 ? t : 0;
+                H[i * W + j] = h;
+                if (h > best) best = h;
+                if (t < 0) continue;
+                D[i * W + j] = up == h ? D_UP : (left == h ? D_LEFT : D_DIAG);
+            }
+        ORC_RESERVE(32);
+        len += (size_t)snprintf(out + len, cap - len, "%d | %d\n", first_index + (int)k, best);
+        if (best == 0) { ORC_RESERVE(3); memcpy(out + len, "\n\n\n", 3); len += 3; free(H); free(D); continue; }
+        size_t ns = 0, scap = 16; orc_start* st = (orc_start*)malloc(scap * sizeof(orc_start));
+        for (int i = Q; i >= 1; --i)
+            for (int j = R; j >= 1; --j)
+                if (H[i * W + j] == best) {
+                    if (ns == scap) { scap *= 2; st = (orc_start*)realloc(st, scap * sizeof(orc_start)); }
+                    int a = i, b = j; int64_t L = 0;
+                    for (;;) {
+                        const uint8_t d = D[a * W + b];
+                        if (d == D_DIAG) { --a; --b; } else if (d == D_LEFT) --b; else --a;
+                        ++L;
+                        if (H[a * W + b] == 0) break;
+                    }
+                    st[ns] = (orc_start){i, j, L, ns}; ++ns;
+                }
+        qsort(st, ns, sizeof(orc_start), orc_start_cmp);
+        for (size_t m = 0; m < ns; ++m) {
+            const int64_t L = st[m].len;
+            ORC_RESERVE(3 * (L + 1));
+            char* o0 = out + len; char* o1 = o0 + L + 1; char* o2 = o1 + L + 1;
+            int a = st[m].i, b = st[m].j; int64_t pos = L;
+            while (pos > 0) {
+                const uint8_t d = D[a * W + b];
+                --pos;
+                if (d == D_DIAG) { o0[pos] = r[b - 1]; o1[pos] = q[a - 1] == r[b - 1] ? '*' : '|'; o2[pos] = q[a - 1]; --a; --b; }
+                else if (d == D_LEFT) { o0[pos] = r[b - 1]; o1[pos] = ' '; o2[pos] = '_'; --b; }
+                else { o0[pos] = '_'; o1[pos] = ' '; o2[pos] = q[a - 1]; --a; }
+            }
+            o0[L] = o1[L] = o2[L] = '\n';
+            len += (size_t)(3 * (L + 1));
+        }
+        total += (int64_t)ns;
+        free(st); free(H); free(D);
+    }
+    #undef ORC_RESERVE
+    out[len] = 0;
+    *text_out = out; *bytes_out = len; if (n_alignments) *n_alignments = total;
+    return 0;
+}
+void orc_free(void* p) { free(p); }
+
 /* Reference stdout block for one pair: "<pairNum> | <score>\nREF\nREL\nQRY\n"
  * (c++/LinearNeedlemanWunsch.cpp:207-213, c++/AffineNeedlemanWunsch.cpp:386-391,
  * c++/LinearSmithWaterman.cpp:252-279; LSW score 0 prints three empty lines :253-257,

@@ -43,6 +43,10 @@ def lib():
         _lib.orc_align_batch.restype = C.c_int
         _lib.orc_align_batch.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        _lib.orc_lsw_all_text.restype = C.c_int
+        _lib.orc_lsw_all_text.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                          C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int64)]
+        _lib.orc_free.restype = None; _lib.orc_free.argtypes = [C.c_void_p]
         _lib.orc_lsw_score_only.restype = C.c_int
         _lib.orc_lsw_score_only.argtypes = [C.POINTER(OrcParams), C.c_int, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
                                             C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
@@ -116,6 +120,26 @@ def lsw_score_only(p: OrcParams, ref: bytes, qry: bytes, band: int = -1):
     s = C.c_int32(); r = C.c_int64(); c = C.c_int64()
     lib().orc_lsw_score_only(C.byref(p), band, ref, len(ref), qry, len(qry), C.byref(s), C.byref(r), C.byref(c))
     return s.value, r.value, c.value
+
+
+def lsw_all_text(p: OrcParams, blob: np.ndarray, pairs: np.ndarray, first_index: int = 0):
+    """LinearSmithWaterman with BACKTRACK_ALL: (stdout blocks with one alignment per maximum cell, number of alignments)."""
+    blob = np.ascontiguousarray(blob); pairs = np.ascontiguousarray(pairs)
+    txt = C.c_void_p(); nb = C.c_size_t(); na = C.c_int64()
+    lib().orc_lsw_all_text(C.byref(p), blob.ctypes.data, pairs.ctypes.data, len(pairs), first_index, C.byref(txt), C.byref(nb), C.byref(na))
+    try:
+        return C.string_at(txt, nb.value), na.value
+    finally:
+        lib().orc_free(txt)
+
+
+REF_ALIGN_ALL = os.path.join(os.path.dirname(REF_ALIGN), "ref_align_all")
+
+
+def run_reference_all(path: str, match=3, mismatch=-1, gap_open=-2) -> bytes:
+    """stdout blocks of the reference's LinearSmithWaterman compiled with -DBACKTRACK_ALL (oracle/_ref/ref_align_all)."""
+    cmd = [REF_ALIGN_ALL, "-algo", "LSW", "-pairs", path, "-match", str(match), "-mismatch", str(mismatch), "-open", str(gap_open), "-noheader"]
+    return subprocess.run(cmd, check=True, capture_output=True).stdout
 
 
 def have_ref_binary() -> bool:

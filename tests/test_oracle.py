@@ -113,3 +113,43 @@ def test_bsw_bandmem_and_linear_memory_agree_with_full_matrix():
 def test_parse_image_rejects_bad_line_count():
     with pytest.raises(ValueError):
         ol.parse_image(b"0\n0123\n")
+
+
+@pytest.mark.skipif(not os.path.exists(ol.REF_ALIGN_ALL), reason="reference binary (BACKTRACK_ALL build) not available")
+@pytest.mark.parametrize("seed,alphabet,w", [(1, b"01", (3, -1, -2)), (2, b"0", (1, -1, -1)), (3, b"012", (2, -3, -2)), (4, b"0123", (3, -1, -2)),
+                                             (5, b"01", (5, -4, -3))])
+def test_all_maxima_mode_is_pinned_on_the_reference_built_with_backtrack_all(seed, alphabet, w, tmp_path):
+    """c++/LinearSmithWaterman.h:9 BACKTRACK_ALL: one alignment per maximum cell, queued bottom-right first, finished alignments ordered by
+    their number of moves.  Byte-identical stdout against the unmodified reference compiled with -DBACKTRACK_ALL, on tie-heavy inputs
+    (periodic and low-entropy sequences give many equal maxima).  Pairs that score 0 are left out: there the reference's all-maxima
+    mode walks uninitialised cells."""
+    m, x, g = w
+    rng = synth.Rng(seed)
+    pp = []
+    while len(pp) < 120:
+        R, Q = 1 + int(rng.below(1, 40)[0]), 1 + int(rng.below(1, 40)[0])
+        kind = len(pp) % 3
+        if kind == 0:
+            unit = synth.random_seq(rng, 1 + int(rng.below(1, 4)[0]), alphabet)
+            r, q = (unit * 40)[:R], (unit * 40)[1:1 + Q]                    # periodic: many equal maxima
+        elif kind == 1:
+            r = synth.random_seq(rng, R, alphabet); q = synth.random_seq(rng, Q, alphabet)
+        else:
+            core = synth.random_seq(rng, 2 + int(rng.below(1, 6)[0]), alphabet)
+            r = synth.random_seq(rng, R // 3, alphabet) + core + synth.random_seq(rng, R // 3, alphabet) + core
+            q = core + synth.random_seq(rng, Q // 2, alphabet) + core       # repeated core: several copies of the best local alignment
+        if set(r) & set(q):                                                 # at least one match: score > 0 with match > 0
+            pp.append((r, q))
+    img = synth.pairs_to_file_bytes(pp)
+    path = tmp_path / "pairs.txt"
+    path.write_bytes(bytes(img))
+    blob, pairs = ol.parse_image(img)
+    txt, n_alignments = ol.lsw_all_text(ol.params(ol.LSW, match=m, mismatch=x, gap_open=g), blob, pairs)
+    assert n_alignments > len(pp)                                           # the inputs do have ties
+    assert txt == ol.run_reference_all(str(path), m, x, g)
+    # the single-path mode's alignment (first maximum in row-major order) is one of them
+    s, e, t = ol.align_batch(ol.params(ol.LSW, match=m, mismatch=x, gap_open=g), blob, pairs)
+    blocks = txt.split(b" | ")
+    assert len(blocks) == len(pp) + 1
+    for k in (0, 7, 50, 119):
+        assert b"\n".join(t[k]) + b"\n" in blocks[k + 1]

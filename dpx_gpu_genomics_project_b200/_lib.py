@@ -101,6 +101,9 @@ def lib() -> C.CDLL:
     L.dpx_align_long_pair.restype = C.c_int
     L.dpx_align_long_pair.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                       i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.dpx_align_batch_text_all.restype = C.c_int
+    L.dpx_align_batch_text_all.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_longlong, C.POINTER(vp), C.POINTER(C.c_size_t),
+                                           C.POINTER(C.c_longlong)]
     L.dpx_align_long_pair_strings.restype = C.c_int
     L.dpx_align_long_pair_strings.argtypes = [vp, C.POINTER(Params), C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t,
                                               i32p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64),

@@ -144,6 +144,18 @@ class Engine:
         finally:
             self.L.dpx_free(txt)
 
+    def align_batch_text_all(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray, first_index: int = 0):
+        """LinearSmithWaterman, every maximum cell walked (the reference's BACKTRACK_ALL mode): (stdout blocks, number of alignments)."""
+        sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        txt, nb, na = C.c_void_p(), C.c_size_t(), C.c_longlong()
+        _check(self.L.dpx_align_batch_text_all(self.ctx, C.byref(params), sequences.ctypes.data, sequences.size, pairs.ctypes.data, len(pairs),
+                                               first_index, C.byref(txt), C.byref(nb), C.byref(na)), self.ctx)
+        try:
+            return C.string_at(txt, nb.value), na.value
+        finally:
+            self.L.dpx_free(txt)
+
     def align_file_text(self, params: _lib.Params, path: str, first_index: int = 0):
         """(text, info): the reference driver's stdout blocks for a whole input file; parser, alignment and formatting on the GPU."""
         txt, nb, info = C.c_void_p(), C.c_size_t(), _lib.InputInfo()

@@ -24,6 +24,7 @@
 #include "shortread.cuh"
 #include "longpair.cuh"
 #include "longtrace.cuh"
+#include "allmax.cuh"
 #include "pairwf.cuh"
 #include "band.cuh"
 
@@ -913,5 +914,6 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
 }
 
 #include "host_long_abi.cuh"
+#include "host_allmax.cuh"
 
 }  // extern "C"

@@ -185,6 +185,15 @@ int         dpx_batch_stats(const dpx_batch* b, dpx_run_stats* out);
 #define DPX_KERNEL_PAIR_S32       6u  /* the same kernel family in int32, one pair per warp (scores beyond the int16 budget) */
 #define DPX_KERNEL_PAIR_S16X2     5u  /* two pairs per warp, packed int16x2, directions in the low score bits (NW / Gotoh + traceback) */
 
+/* ---- LinearSmithWaterman in the reference's BACKTRACK_ALL mode (c++/LinearSmithWaterman.h:9, .cpp:126-143,163-226):
+ * one alignment per cell that holds the maximum, start cells queued bottom-right to top-left, finished alignments ordered by
+ * their number of moves; text = the stdout blocks of the reference compiled with -DBACKTRACK_ALL ("<i> | <score>", then REF /
+ * REL / QRY per alignment; score 0: three empty lines).  An inspection mode: whole int32 score matrices are kept on the device
+ * (DPX_ERR_RANGE beyond 12 GiB).  text is library-allocated (dpx_free). */
+int         dpx_align_batch_text_all(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
+                                     const dpx_seq_pair* pairs, size_t n_pairs, long long first_index,
+                                     char** text, size_t* text_bytes, long long* n_alignments);
+
 /* ---- one very long pair, score + end cell only (BASELINE config 5) ----------------------
  * The reference cannot run this (8 B/cell full matrix). */
 int         dpx_align_long_pair(dpx_ctx* ctx, const dpx_params* params,

@@ -6,6 +6,8 @@
 //                                                                default LSW = what the reference ships enabled)
 //                                        -band W                 (BSW only, default 64)
 //                                        -scores                 score (+ end cell) lines only, no alignment strings
+//                                        -all                    LSW, every maximum cell walked: the output of the reference built with
+//                                                                -DBACKTRACK_ALL (c++/LinearSmithWaterman.h:9)
 //                                        -long                   LSW on pairs too long for a batch (Mbp): every pair of the file goes
 //                                                                through dpx_align_long_pair_strings (checkpoints + tile walk), same blocks
 //                                        -fastx F [-fastx2 G]    pairs from FASTA / FASTQ records instead of -pairs (one file: records
@@ -27,7 +29,7 @@ int main(int argc, char* argv[]) {
     }
     const char* pairFileName = nullptr;
     int matchWeight = 3, mismatchWeight = -1, gapOpenWeight = -4, gapExtendWeight = -1;   // defaults of main.cpp:128-132
-    int algo = DPX_ALGO_LSW, band = 64; bool scores_only = false, long_pairs = false;
+    int algo = DPX_ALGO_LSW, band = 64; bool scores_only = false, long_pairs = false, all_maxima = false;
     const char* fastx = nullptr; const char* fastx2 = nullptr;
     for (int i = 1; i < argc; ++i) {
         const bool has = i + 1 < argc;
@@ -39,6 +41,7 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "-band") && has) band = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-scores")) scores_only = true;
         else if (!strcmp(argv[i], "-long")) long_pairs = true;
+        else if (!strcmp(argv[i], "-all")) all_maxima = true;
         else if (!strcmp(argv[i], "-fastx") && has) fastx = argv[++i];
         else if (!strcmp(argv[i], "-fastx2") && has) fastx2 = argv[++i];
         else if (!strcmp(argv[i], "-algo") && has) {
@@ -62,7 +65,7 @@ int main(int argc, char* argv[]) {
     char* text = nullptr; size_t text_bytes = 0;
     dpx_ctx* ctx = dpxhost::engine();
     int st;
-    if (fastx || long_pairs) {
+    if (fastx || long_pairs || all_maxima) {
         // host-side parsers: the project's 3-line records (parseInput) or FASTA / FASTQ records, then one batch — or, with -long, one
         // checkpointed alignment per pair, printed as LinearSmithWaterman::print_results does (c++/LinearSmithWaterman.cpp:240-288)
         dpx_seq_pair* idx = nullptr; char* seqs = nullptr; dpx_input_info info{};
@@ -79,6 +82,9 @@ int main(int argc, char* argv[]) {
                 else for (int l = 0; l < 3; ++l) { fwrite(lines + (size_t)l * (len + 1), 1, len, stdout); fputc('\n', stdout); }
                 dpx_free(lines);
             }
+        } else if (st == DPX_OK && all_maxima) {
+            if (algo != DPX_ALGO_LSW) { fprintf(stderr, "-all is a LinearSmithWaterman mode\n"); exit(EXIT_FAILURE); }
+            st = dpx_align_batch_text_all(ctx, &p, seqs, info.numBytes, idx, info.numPairs, 0, &text, &text_bytes, nullptr);
         } else if (st == DPX_OK) {
             st = dpx_align_batch_text(ctx, &p, seqs, info.numBytes, idx, info.numPairs, 0, nullptr, nullptr, &text, &text_bytes);
         }

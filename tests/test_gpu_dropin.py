@@ -73,3 +73,20 @@ def test_dropin_main_reads_fasta_pairs(tmp_path):
     lines = out.split(b"\n")
     body = b"\n".join(lines[2:-3]) + b"\n"
     assert body == open(os.path.join(GOLD, "mid.LNW.out.txt"), "rb").read()
+
+
+def test_dropin_main_all_flag_prints_every_maximum(tmp_path):
+    """-all: the stdout of the reference built with -DBACKTRACK_ALL (checked here against the oracle restatement pinned on that build)."""
+    import oracle_lib as ol
+    from dpx_gpu_genomics_project_b200 import synth
+    pp = [(b"0101", b"1010"), (b"0123012", b"0123"), (b"000", b"111"), (b"00100", b"00"), (b"0101010101", b"01010"), (b"012012012", b"12")]
+    img = synth.pairs_to_file_bytes(pp)
+    path = tmp_path / "ties.txt"
+    path.write_bytes(bytes(img))
+    out = subprocess.run([os.path.join(HOST, "main"), "-pairs", str(path), "-match", "3", "-mismatch", "-1", "-open", "-2", "-algo", "LSW", "-all"],
+                         check=True, capture_output=True).stdout
+    lines = out.split(b"\n")
+    body = b"\n".join(lines[2:-3]) + b"\n"
+    blob, pairs = ol.parse_image(img)
+    want, n = ol.lsw_all_text(ol.params(ol.LSW), blob, pairs)
+    assert n == 11 and body == want

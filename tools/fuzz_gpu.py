@@ -108,6 +108,11 @@ def main():
                 assert res.strings == t, "strings"
                 if rng.integers(4) == 0:
                     assert eng.align_batch_text(api.make_params(algo, flags=flags, **w), blob, pairs) == ol.format_text(s, t), "text"
+            if algo == api.LSW and span[1] <= 320 and rng.integers(4) == 0:
+                # the reference's BACKTRACK_ALL mode: every maximum cell walked, blocks in the reference's order
+                want_all, n_all = ol.lsw_all_text(ol.params(algo, **w), blob, pairs, 3)
+                got_all, n_got = eng.align_batch_text_all(api.make_params(api.LSW, **w), blob, pairs, 3)
+                assert n_got == n_all and got_all == want_all, "all-maxima text"
             if algo == api.LSW and len(pairs) and rng.integers(3) == 0:
                 # the long-pair entry points on one pair of the batch, at a random lane width / tile geometry / round size
                 k = int(rng.integers(len(pairs))); pr = pairs[k]

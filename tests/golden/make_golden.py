@@ -4,7 +4,8 @@ COMPILED, UNMODIFIED reference classes (oracle/_ref/ref_align, built by oracle/M
 
     make -C oracle && python tests/golden/make_golden.py
 
-Outputs (committed): tests/golden/<name>.in.txt, tests/golden/<name>.<ALGO>.out.txt,
+Outputs (committed): tests/golden/<name>.in.txt, tests/golden/<name>.<ALGO>.out.txt, tests/golden/ties.LSW_ALL.out.txt (the
+reference built with -DBACKTRACK_ALL, oracle/_ref/ref_align_all),
 tests/golden/bsw_python_scores.json (scores of the reference's Python banded prototype).
 Scoring = the reference's golden parameters (correct-outputs/LNW/web-scraper-LNW.py:139-141,
 correct-outputs/ANW/web-scraper-ANW.py): match 3, mismatch -1, gap -2; Gotoh open -3, extend -1.
@@ -65,6 +66,28 @@ def shapes(seed):
     return pairs
 
 
+def ties(seed):
+    """Pairs with SEVERAL maximum cells (periodic sequences, repeated cores, tiny alphabets), all scoring > 0: the input of the
+    BACKTRACK_ALL golden (score-0 pairs are left out: there the reference's all-maxima mode walks uninitialised cells)."""
+    rng = synth.Rng(seed)
+    pairs = [(b"0101", b"1010"), (b"0123012", b"0123"), (b"00100", b"00"), (b"0101010101", b"01010"), (b"012012012", b"12")]
+    for alpha in (b"0", b"01", b"012", b"0123"):
+        for k in range(40):
+            R = 1 + int(rng.below(1, 40)[0]); Q = 1 + int(rng.below(1, 40)[0])
+            if k % 3 == 0:
+                unit = synth.random_seq(rng, 1 + int(rng.below(1, 4)[0]), alpha)
+                r, q = (unit * 40)[:R], (unit * 40)[1:1 + Q]
+            elif k % 3 == 1:
+                r, q = synth.random_seq(rng, R, alpha), synth.random_seq(rng, Q, alpha)
+            else:
+                core = synth.random_seq(rng, 2 + int(rng.below(1, 6)[0]), alpha)
+                r = synth.random_seq(rng, R // 3, alpha) + core + synth.random_seq(rng, R // 3, alpha) + core
+                q = core + synth.random_seq(rng, Q // 2, alpha) + core
+            if set(r) & set(q):
+                pairs.append((r, q))
+    return pairs
+
+
 SETS = {
     "adversarial": lambda: adversarial(0x5EED0000 + 101),
     "cfg1_small": lambda: cfg1_like(0x5EED0000 + 1, 120, 100, 300, 20),
@@ -108,6 +131,15 @@ def main():
             with open(os.path.join(HERE, f"{name}.{ol.ALGO_NAMES[algo]}.out.txt"), "wb") as f:
                 f.write(out)
             print(name, ol.ALGO_NAMES[algo], len(out), "bytes")
+    # LinearSmithWaterman built with -DBACKTRACK_ALL (c++/LinearSmithWaterman.h:9): oracle/_ref/ref_align_all
+    img = synth.pairs_to_file_bytes(ties(0x5EED0000 + 105))
+    path = os.path.join(HERE, "ties.in.txt")
+    with open(path, "wb") as f:
+        f.write(img)
+    out = ol.run_reference_all(path, 3, -1, -2)
+    with open(os.path.join(HERE, "ties.LSW_ALL.out.txt"), "wb") as f:
+        f.write(out)
+    print("ties LSW_ALL", len(out), "bytes")
     with open(os.path.join(HERE, "bsw_python_scores.json"), "w") as f:
         json.dump(python_banded_scores(), f, indent=0)
     print("done")

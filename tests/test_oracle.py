@@ -153,3 +153,12 @@ def test_all_maxima_mode_is_pinned_on_the_reference_built_with_backtrack_all(see
     assert len(blocks) == len(pp) + 1
     for k in (0, 7, 50, 119):
         assert b"\n".join(t[k]) + b"\n" in blocks[k + 1]
+
+
+def test_all_maxima_golden_fixture():
+    """tests/golden/ties.LSW_ALL.out.txt = stdout of the reference compiled with -DBACKTRACK_ALL (tests/golden/make_golden.py)."""
+    img = open(os.path.join(GOLD, "ties.in.txt"), "rb").read()
+    blob, pairs = ol.parse_image(img)
+    txt, n = ol.lsw_all_text(ol.params(ol.LSW), blob, pairs)
+    assert txt == open(os.path.join(GOLD, "ties.LSW_ALL.out.txt"), "rb").read()
+    assert n > len(pairs)

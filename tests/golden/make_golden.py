@@ -4,7 +4,7 @@ COMPILED, UNMODIFIED reference classes (oracle/_ref/ref_align, built by oracle/M
 
     make -C oracle && python tests/golden/make_golden.py
 
-Outputs (committed): tests/golden/<name>.in.txt, tests/golden/<name>.<ALGO>.out.txt, tests/golden/ties.LSW_ALL.out.txt (the
+Outputs (committed): tests/golden/<name>.in.txt, tests/golden/<name>.<ALGO>.out.txt, tests/golden/ties.pairs.txt + ties.LSW_ALL.out.txt (the
 reference built with -DBACKTRACK_ALL, oracle/_ref/ref_align_all),
 tests/golden/bsw_python_scores.json (scores of the reference's Python banded prototype).
 Scoring = the reference's golden parameters (correct-outputs/LNW/web-scraper-LNW.py:139-141,
@@ -133,7 +133,7 @@ def main():
             print(name, ol.ALGO_NAMES[algo], len(out), "bytes")
     # LinearSmithWaterman built with -DBACKTRACK_ALL (c++/LinearSmithWaterman.h:9): oracle/_ref/ref_align_all
     img = synth.pairs_to_file_bytes(ties(0x5EED0000 + 105))
-    path = os.path.join(HERE, "ties.in.txt")
+    path = os.path.join(HERE, "ties.pairs.txt")
     with open(path, "wb") as f:
         f.write(img)
     out = ol.run_reference_all(path, 3, -1, -2)

@@ -66,6 +66,6 @@ def test_single_maximum_gives_the_ordinary_output_and_other_algorithms_are_refus
 def test_golden_output_of_the_reference_built_with_backtrack_all(eng):
     import os
     gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    blob, pairs = ol.parse_image(open(os.path.join(gold, "ties.in.txt"), "rb").read())
+    blob, pairs = ol.parse_image(open(os.path.join(gold, "ties.pairs.txt"), "rb").read())
     got, n = eng.align_batch_text_all(api.make_params(api.LSW), blob, pairs)
     assert got == open(os.path.join(gold, "ties.LSW_ALL.out.txt"), "rb").read()

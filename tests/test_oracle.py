@@ -157,7 +157,7 @@ def test_all_maxima_mode_is_pinned_on_the_reference_built_with_backtrack_all(see
 
 def test_all_maxima_golden_fixture():
     """tests/golden/ties.LSW_ALL.out.txt = stdout of the reference compiled with -DBACKTRACK_ALL (tests/golden/make_golden.py)."""
-    img = open(os.path.join(GOLD, "ties.in.txt"), "rb").read()
+    img = open(os.path.join(GOLD, "ties.pairs.txt"), "rb").read()
     blob, pairs = ol.parse_image(img)
     txt, n = ol.lsw_all_text(ol.params(ol.LSW), blob, pairs)
     assert txt == open(os.path.join(GOLD, "ties.LSW_ALL.out.txt"), "rb").read()

@@ -31,8 +31,8 @@ typedef enum {
     DPX_ERR_NO_DEVICE    = -2,   /* no usable CUDA device / driver */
     DPX_ERR_CUDA         = -3,   /* a CUDA runtime call or kernel failed; see dpx_last_error */
     DPX_ERR_NOMEM        = -4,   /* host or device allocation failed */
-    DPX_ERR_IO           = -5,   /* dpx_parse_input: cannot open / read the file */
-    DPX_ERR_FORMAT       = -6,   /* dpx_parse_input: number of lines not a multiple of 3 */
+    DPX_ERR_IO           = -5,   /* dpx_parse_input / dpx_parse_fastx: cannot open / read the file */
+    DPX_ERR_FORMAT       = -6,   /* dpx_parse_input: number of lines not a multiple of 3; dpx_parse_fastx: malformed or unpaired records */
     DPX_ERR_RANGE        = -7,   /* a sequence / score does not fit the selected kernel's range */
     DPX_ERR_UNSUPPORTED  = -8
 } dpx_status;

@@ -1,24 +1,17 @@
 // parseInput.cpp — the reference's parser entry points (c++/parseInput.cpp:9-143) on top of dpx_parse_input.
 // Error behaviour of the reference is kept: a message on stderr and exit(1) (:14, :40).
 #include "parseInput.h"
-#include "../../include/dpxalign.h"
 
-static_assert(sizeof(seqPair) == sizeof(dpx_seq_pair), "seqPair layout must match the C ABI");
+static_assert(sizeof(int) == sizeof(int32_t), "the reference's seqPair holds four ints (c++/parseInput.h:22-29)");
 
 inputInfo parseInput(const char* pairFileName, seqPair*& sequence_indices, char*& sequences) {
-    dpx_seq_pair* pairs = nullptr; char* seqs = nullptr; dpx_input_info in;
-    const int st = dpx_parse_input(pairFileName, &pairs, &seqs, &in);
+    inputInfo in;
+    sequence_indices = nullptr; sequences = nullptr;
+    const int st = dpx_parse_input(pairFileName, &sequence_indices, &sequences, &in);
     if (st == DPX_ERR_IO) { fprintf(stderr, "Could not open file: %s\n", pairFileName); exit(1); }
     if (st == DPX_ERR_FORMAT) { fprintf(stderr, "Number of lines not a multiple of 3: %s\n", pairFileName); exit(1); }
     if (st != DPX_OK) { fprintf(stderr, "parseInput: %s\n", dpx_strerror(st)); exit(1); }
-    sequence_indices = reinterpret_cast<seqPair*>(pairs);
-    sequences = seqs;
-    inputInfo r;
-    r.numPairs = in.numPairs; r.numBytes = in.numBytes; r.numCells = in.numCells;
-    r.minReferenceLength = in.minReferenceLength; r.minQueryLength = in.minQueryLength;
-    r.maxReferenceLength = in.maxReferenceLength; r.maxQueryLength = in.maxQueryLength;
-    r.avgReferenceLength = in.avgReferenceLength; r.avgQueryLength = in.avgQueryLength;
-    return r;
+    return in;
 }
 
 void printParsedFile(const size_t numPairs, const seqPair* idx, const char* sequences) {

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,c
 
 
 def sources() -> list[str]:
-    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h")))
 
 
 def needs_build() -> bool:
@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if force or needs_build():
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              [os.path.join(CSRC, "dpxalign.cu"), "-o", LIB_PATH]
+              [os.path.join(CSRC, "dpxalign.cu"), os.path.join(CSRC, "host_pack.cpp"), os.path.join(CSRC, "host_multi.cpp"),
+               "-Xcompiler", "-pthread", "-o", LIB_PATH]
         subprocess.run(cmd, check=True)
     return LIB_PATH
 
@@ -78,6 +79,26 @@ def lib() -> C.CDLL:
     L.dpx_destroy.restype = None; L.dpx_destroy.argtypes = [vp]
     L.dpx_last_error.restype = C.c_char_p; L.dpx_last_error.argtypes = [vp]
     L.dpx_set_stream.restype = C.c_int; L.dpx_set_stream.argtypes = [vp, vp]
+    L.dpx_set_option.restype = C.c_int; L.dpx_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.dpx_trim.restype = None; L.dpx_trim.argtypes = []
+    L.dpx_parse_image.restype = C.c_int
+    L.dpx_parse_image.argtypes = [vp, C.c_size_t, C.POINTER(vp), C.POINTER(vp), C.POINTER(InputInfo)]
+    L.dpx_register_input.restype = C.c_int; L.dpx_register_input.argtypes = [vp, C.c_size_t, vp, C.c_size_t]
+    L.dpx_input_sidecar.restype = C.c_int
+    L.dpx_input_sidecar.argtypes = [vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), vp]
+    L.dpx_unregister_input.restype = None; L.dpx_unregister_input.argtypes = [vp]
+    L.dpx_bind_host_to_device.restype = C.c_int; L.dpx_bind_host_to_device.argtypes = [C.c_int]
+    L.dpx_create_multi.restype = C.c_int; L.dpx_create_multi.argtypes = [C.POINTER(vp), C.POINTER(C.c_int), C.c_int]
+    L.dpx_destroy_multi.restype = None; L.dpx_destroy_multi.argtypes = [vp]
+    L.dpx_multi_last_error.restype = C.c_char_p; L.dpx_multi_last_error.argtypes = [vp]
+    L.dpx_multi_device_count.restype = C.c_int; L.dpx_multi_device_count.argtypes = [vp]
+    L.dpx_multi_set_option.restype = C.c_int; L.dpx_multi_set_option.argtypes = [vp, C.c_char_p, C.c_longlong]
+    L.dpx_multi_align_batch.restype = C.c_int
+    L.dpx_multi_align_batch.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, vp, vp, C.POINTER(vp), C.POINTER(vp)]
+    L.dpx_multi_align_batch_text.restype = C.c_int
+    L.dpx_multi_align_batch_text.argtypes = [vp, C.POINTER(Params), vp, C.c_size_t, vp, C.c_size_t, C.c_longlong, vp, vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.dpx_multi_shard_bounds.restype = C.c_int
+    L.dpx_multi_shard_bounds.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_size_t)]
     L.dpx_parse_input.restype = C.c_int
     L.dpx_parse_input.argtypes = [C.c_char_p, C.POINTER(vp), C.POINTER(vp), C.POINTER(InputInfo)]
     L.dpx_parse_fastx.restype = C.c_int

@@ -62,6 +62,74 @@ def parse_input(path: str) -> ParsedInput:
     return ParsedInput(seqs, pairs, {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_})
 
 
+class NativeInput:
+    """parseInput's outputs LEFT IN LIBRARY MEMORY (numpy views, no copies): the blob / index pointers are the ones the parser
+    registered its packed 2-bit sidecar under, so `Engine.align_batch(params, inp.sequences, inp.pairs)` uploads the packed
+    words instead of the bytes (include/dpxalign.h, "Packed sidecar").  Treat both arrays as read-only; call free() when done."""
+
+    def __init__(self, pairs_p, seq_p, info):
+        self._L = _lib.lib()
+        self._pairs_p, self._seq_p = pairs_p, seq_p
+        self.info = {f: getattr(info, f) for f, _ in _lib.InputInfo._fields_}
+        n, nb = info.numPairs, info.numBytes
+        self.sequences = np.ctypeslib.as_array(C.cast(seq_p, C.POINTER(C.c_uint8)), shape=(max(nb, 1),))[:nb]
+        raw = np.ctypeslib.as_array(C.cast(pairs_p, C.POINTER(C.c_int32)), shape=(max(4 * n, 4),))[:4 * n]
+        self.pairs = raw.view(PAIR_DTYPE)
+
+    def free(self):
+        if self._seq_p:
+            self.sequences = self.pairs = None
+            self._L.dpx_free(self._pairs_p); self._L.dpx_free(self._seq_p)
+            self._pairs_p = self._seq_p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def parse_input_native(path: str) -> NativeInput:
+    L = _lib.lib()
+    pairs_p, seq_p, info = C.c_void_p(), C.c_void_p(), _lib.InputInfo()
+    _check(L.dpx_parse_input(path.encode(), C.byref(pairs_p), C.byref(seq_p), C.byref(info)))
+    return NativeInput(pairs_p, seq_p, info)
+
+
+def parse_image_native(image) -> NativeInput:
+    """dpx_parse_image: the parser on a file image in memory (bytes or a uint8 array)."""
+    L = _lib.lib()
+    a = np.ascontiguousarray(np.frombuffer(image, dtype=np.uint8) if isinstance(image, (bytes, bytearray)) else image, dtype=np.uint8)
+    pairs_p, seq_p, info = C.c_void_p(), C.c_void_p(), _lib.InputInfo()
+    _check(L.dpx_parse_image(a.ctypes.data, a.size, C.byref(pairs_p), C.byref(seq_p), C.byref(info)))
+    return NativeInput(pairs_p, seq_p, info)
+
+
+def register_input(sequences: np.ndarray, pairs: np.ndarray) -> None:
+    """dpx_register_input: packs a caller-built (blob, index) once on the host; both arrays must stay alive and unmodified."""
+    _check(_lib.lib().dpx_register_input(sequences.ctypes.data, sequences.size, pairs.ctypes.data, len(pairs)))
+
+
+def input_sidecar(sequences: np.ndarray):
+    """dpx_input_sidecar: None when `sequences` is not a registered blob, else a dict with the packed words (a copy), the word
+    offsets, the symbol count, the code -> byte map, whether the lengths are uniform and whether the memory is page-locked."""
+    L = _lib.lib()
+    n, nw, w, off, ns, pl = C.c_size_t(), C.c_size_t(), C.c_void_p(), C.c_void_p(), C.c_int(), C.c_int()
+    inv = (C.c_ubyte * 4)()
+    kind = L.dpx_input_sidecar(sequences.ctypes.data, C.byref(n), C.byref(nw), C.byref(w), C.byref(off), C.byref(ns), C.byref(pl), inv)
+    if kind == 0:
+        return None
+    words = np.frombuffer(C.string_at(w, 4 * nw.value), dtype=np.uint32).copy()
+    woff = np.frombuffer(C.string_at(off, 4 * (n.value + 1)), dtype=np.uint32).copy()
+    upload = 4 * nw.value + (0 if kind == 2 else 8 * n.value + 4)
+    return dict(n_pairs=n.value, words=words, word_offsets=woff, n_symbols=ns.value, code_to_byte=bytes(inv), uniform=kind == 2,
+                page_locked=bool(pl.value), upload_bytes=upload)
+
+
+def unregister_input(sequences: np.ndarray) -> None:
+    _lib.lib().dpx_unregister_input(sequences.ctypes.data)
+
+
 def parse_fastx(path_refs: str, path_queries: str | None = None) -> ParsedInput:
     """FASTA / FASTQ records as pairs (dpx_parse_fastx): one file = records alternate reference, query; two files = paired by order."""
     L = _lib.lib()
@@ -118,19 +186,28 @@ class Engine:
     def set_stream(self, cuda_stream: int | None):
         _check(self.L.dpx_set_stream(self.ctx, C.c_void_p(cuda_stream or 0)), self.ctx)
 
+    def set_option(self, name: str, value: int):
+        """dpx_set_option: debug / test knobs (the library never reads the environment)."""
+        _check(self.L.dpx_set_option(self.ctx, name.encode(), int(value)), self.ctx)
+
+    def options(self, **kw):
+        """Context manager: set the given 0-default options for the duration of a `with` block, then reset them to 0."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            for k, v in kw.items():
+                self.set_option(k, v)
+            try:
+                yield self
+            finally:
+                for k in kw:
+                    self.set_option(k, 0)
+        return cm()
+
     # ---- one call: host buffers in, host buffers out ---------------------------------------------
     def align_batch(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray) -> BatchResult:
-        n = len(pairs)
-        sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
-        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
-        scores = np.zeros(n, dtype=np.int32)
-        end_rc = np.zeros((n, 2), dtype=np.int32)
-        sb, so = C.c_void_p(), C.c_void_p()
-        want = bool(params.flags & OUT_STRINGS)
-        _check(self.L.dpx_align_batch(self.ctx, C.byref(params), sequences.ctypes.data, sequences.size,
-                                      pairs.ctypes.data, n, scores.ctypes.data, end_rc.ctypes.data,
-                                      C.byref(sb) if want else None, C.byref(so) if want else None), self.ctx)
-        return BatchResult(scores, end_rc, self._take_strings(sb, so, n) if want else None)
+        return _align_batch_call(self.L.dpx_align_batch, self.ctx, self.L.dpx_last_error, params, sequences, pairs, self._take_strings)
 
     def align_batch_text(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray, first_index: int = 0) -> bytes:
         """The reference's stdout blocks for the batch ("<i> | <score>\\n" + REF/REL/QRY lines), formatted on the GPU."""
@@ -213,6 +290,79 @@ class Engine:
         self.L.dpx_free(blob)
         lines = tuple(raw[k * (L + 1): k * (L + 1) + L] for k in range(3))
         return (s.value, r.value, c.value), (r0.value, c0.value), lines, dict(fwd_ms=ms[0], rounds=int(ms[1]), walk_ms=ms[2], tiles=int(ms[3]), tile_rows=int(ms[4]), tile_cols=int(ms[5]))
+
+
+def _align_batch_call(fn, handle, errfn, params, sequences, pairs, take_strings) -> BatchResult:
+    n = len(pairs)
+    sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
+    pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+    scores = np.zeros(n, dtype=np.int32)
+    end_rc = np.zeros((n, 2), dtype=np.int32)
+    sb, so = C.c_void_p(), C.c_void_p()
+    want = bool(params.flags & OUT_STRINGS)
+    st = fn(handle, C.byref(params), sequences.ctypes.data, sequences.size, pairs.ctypes.data, n, scores.ctypes.data, end_rc.ctypes.data,
+            C.byref(sb) if want else None, C.byref(so) if want else None)
+    if st != 0:
+        raise DpxError(st, errfn(handle).decode())
+    return BatchResult(scores, end_rc, take_strings(sb, so, n) if want else None)
+
+
+class MultiEngine:
+    """Several GPUs of one node behind ONE host process (dpx_create_multi): contiguous shards balanced by cell count, one worker
+    thread + context per device, results in pair order (multi-GPU mode A through the C ABI)."""
+
+    def __init__(self, devices=None, n_devices: int | None = None):
+        self.L = _lib.lib()
+        self.h = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(self.L.dpx_create_multi(C.byref(self.h), arr, len(devices)))
+        else:
+            _check(self.L.dpx_create_multi(C.byref(self.h), None, int(n_devices or self.L.dpx_device_count())))
+
+    @property
+    def n_devices(self) -> int:
+        return self.L.dpx_multi_device_count(self.h)
+
+    def set_option(self, name: str, value: int):
+        st = self.L.dpx_multi_set_option(self.h, name.encode(), int(value))
+        if st:
+            raise DpxError(st, self.L.dpx_multi_last_error(self.h).decode())
+
+    def shard_bounds(self, pairs: np.ndarray, n_shards: int | None = None):
+        k = n_shards or self.n_devices
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        out = (C.c_size_t * (k + 1))()
+        _check(self.L.dpx_multi_shard_bounds(pairs.ctypes.data, len(pairs), k, out))
+        return list(out)
+
+    def align_batch(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray) -> BatchResult:
+        return _align_batch_call(self.L.dpx_multi_align_batch, self.h, self.L.dpx_multi_last_error, params, sequences, pairs,
+                                 lambda sb, so, n: Engine._take_strings(self, sb, so, n))
+
+    def align_batch_text(self, params: _lib.Params, sequences: np.ndarray, pairs: np.ndarray, first_index: int = 0) -> bytes:
+        sequences = np.ascontiguousarray(sequences, dtype=np.uint8)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        txt, nb = C.c_void_p(), C.c_size_t()
+        st = self.L.dpx_multi_align_batch_text(self.h, C.byref(params), sequences.ctypes.data, sequences.size, pairs.ctypes.data, len(pairs),
+                                               first_index, None, None, C.byref(txt), C.byref(nb))
+        if st:
+            raise DpxError(st, self.L.dpx_multi_last_error(self.h).decode())
+        try:
+            return C.string_at(txt, nb.value)
+        finally:
+            self.L.dpx_free(txt)
+
+    def close(self):
+        if self.h:
+            self.L.dpx_destroy_multi(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Batch:

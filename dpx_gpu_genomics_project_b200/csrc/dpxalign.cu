@@ -17,6 +17,7 @@
 #include <thrust/iterator/counting_iterator.h>
 
 #include "common.cuh"
+#include "host_pack.h"
 #include "dpx_ops.cuh"
 #include "wavefront.cuh"
 #include "pack.cuh"
@@ -59,13 +60,14 @@ struct DevPool {
 // speed instead of through the driver's pageable staging; dpx_free returns them to this process-wide cache (bounded),
 // so a driver that aligns batch after batch does not pay cudaHostAlloc each time.  Anything not allocated here (the
 // parser's malloc'ed arrays) still goes to free().
+#include <atomic>
 #include <mutex>
 struct HostCache {
     std::mutex mu;
     std::multimap<size_t, void*> free_;
     std::unordered_map<void*, size_t> live_;
     size_t cached_bytes = 0;
-    static constexpr size_t kMaxCached = (size_t)6 << 30;
+    static constexpr size_t kMaxCached = (size_t)2 << 30;     // documented in dpxalign.h (dpx_free / dpx_trim)
     void* take(size_t bytes) {
         bytes = std::max<size_t>((bytes + 4095) & ~(size_t)4095, 4096);
         {
@@ -91,11 +93,34 @@ struct HostCache {
         cudaFreeHost(p);
         return true;
     }
+    // gives every cached (not handed-out) block back to the driver
+    void trim() {
+        std::multimap<size_t, void*> drop;
+        { std::lock_guard<std::mutex> g(mu); drop.swap(free_); cached_bytes = 0; }
+        for (auto& kv : drop) cudaFreeHost(kv.second);
+    }
 };
 static HostCache g_host;
+static std::atomic<int> g_live_ctx{0};
+
+// Debug / test knobs, set only through dpx_set_option (never read from the environment).
+struct DpxOptions {
+    int long_k = 0;            // long pair: force the lane width (2, 4, 8, 16, 32); 0 = cost model
+    int long_cap = 0;          // long pair: cap on co-resident warps (forces several passes); 0 = occupancy
+    int long_notable = 0;      // long pair: byte-compare kernel even for <= 4 symbols
+    int long_bt_tiles = 0;     // long-pair traceback: tiles per round; 0 = 2 per SM
+    int no_pairwf = 0;         // skip the packed pair-wavefront kernels (general wavefront instead)
+    int pairwf_int32 = 0;      // pair-wavefront kernels in int32 even when int16x2 would fit
+    int no_bandkernel = 0;     // skip the band-on-a-warp kernel
+    int no_shortread = 0;      // skip the short-read kernel
+    int serial_chunks = 0;     // traceback chunk pipeline: one buffer, chunks in series (times the fill kernel alone)
+    int trace = 0;             // one-call pipeline: per-chunk timeline on stderr
+    int no_sidecar = 0;        // dpx_align_batch: ignore the parser's packed sidecar (upload the raw blob)
+};
 
 struct dpx_ctx {
     int device = 0;
+    DpxOptions opt;
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;             // lane 0 (unless the caller supplies a stream)
     cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // lanes 1..3 of the chunked one-call pipeline
@@ -107,7 +132,8 @@ struct dpx_ctx {
     int32_t* boundary[4] = {nullptr, nullptr, nullptr, nullptr}; size_t boundary_ints[4] = {0, 0, 0, 0};
     unsigned int* counters = nullptr;              // 64 dynamic-work counters per lane
     size_t tb_budget_bytes = (size_t)16 << 30;     // traceback chunk budget
-    int chunks = 12;                               // one-call pipeline: equal middle chunks (env DPX_CHUNKS)
+    int chunks = 12;                               // one-call pipeline: equal middle chunks (dpx_set_option "chunks")
+    bool counted = false;                          // registered in g_live_ctx (dpx_create succeeded)
 };
 
 struct dpx_batch {
@@ -127,6 +153,10 @@ struct dpx_batch {
     const uint8_t* d_blob = nullptr;               // d_blob_alloc - byte_lo: indexable with the seqPair offsets
     dpx_seq_pair* d_pairs = nullptr;
     uint32_t* d_packed = nullptr;
+    uint32_t inv4 = 0;                             // sidecar batches: code -> byte (4 bytes), for ensure_blob
+    bool from_sidecar = false;
+    uint32_t* d_stage[2] = {nullptr, nullptr};     // sidecar batches: staged sizes / word offsets (released with the batch)
+    size_t h2d_bytes = 0;                          // bytes this batch's upload moved over PCIe
     uint8_t* d_codes = nullptr;                    // 5..8 symbols: byte codes, same indexing as d_blob (allocated at d_codes_alloc - byte_lo)
     uint8_t* d_codes_alloc = nullptr;
     unsigned long long* d_pk_off = nullptr; unsigned long long pk_stride = 0;
@@ -145,6 +175,7 @@ struct dpx_batch {
     BatchInfo* d_info = nullptr;
     // run state
     bool ran = false; dpx_params params{};
+    bool used_aux = false;           // a run queued work on the ctx's auxiliary streams (dpx_batch_free drains them too)
     std::vector<cudaEvent_t> ev;     // pairs of (start, end) per kernel; kind in ev_kind
     std::vector<int> ev_kind;        // 0 fill, 1 backtrack
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_h2d = nullptr;
@@ -208,10 +239,13 @@ int dpx_create(dpx_ctx** out, int device) {
     ctx->stream = ctx->own_stream;
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess) ctx->tb_budget_bytes = std::min<size_t>((size_t)48 << 30, fr / 3);
-    if (const char* e = getenv("DPX_CHUNKS")) { int c = atoi(e); if (c >= 1 && c <= 64) ctx->chunks = c; }
     *out = ctx;
+    ctx->counted = true;
+    g_live_ctx.fetch_add(1);
     return DPX_OK;
 }
+
+void dpx_trim(void) { g_host.trim(); }
 
 void dpx_destroy(dpx_ctx* ctx) {
     if (!ctx) return;
@@ -223,6 +257,7 @@ void dpx_destroy(dpx_ctx* ctx) {
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     for (int l = 0; l < 3; ++l) if (ctx->aux_stream[l]) cudaStreamDestroy(ctx->aux_stream[l]);
+    if (ctx->counted && g_live_ctx.fetch_sub(1) == 1) g_host.trim();       // last context gone: release the cached page-locked blocks
     delete ctx;
 }
 
@@ -234,30 +269,44 @@ int dpx_set_stream(dpx_ctx* ctx, void* s) {
     return DPX_OK;
 }
 
-void dpx_free(void* p) { if (p && !g_host.give_back(p)) free(p); }
+int dpx_set_option(dpx_ctx* ctx, const char* name, long long value) {
+    if (!ctx || !name) return DPX_ERR_INVALID;
+    const std::string k(name);
+    DpxOptions& o = ctx->opt;
+    if (k == "long_k") { if (value != 0 && value != 2 && value != 4 && value != 8 && value != 16 && value != 32) return DPX_ERR_INVALID; o.long_k = (int)value; }
+    else if (k == "long_cap") { if (value < 0 || value > (1 << 20)) return DPX_ERR_INVALID; o.long_cap = (int)value; }
+    else if (k == "long_notable") o.long_notable = value != 0;
+    else if (k == "long_bt_tiles") { if (value < 0 || value > 4096) return DPX_ERR_INVALID; o.long_bt_tiles = (int)value; }
+    else if (k == "no_pairwf") o.no_pairwf = value != 0;
+    else if (k == "pairwf_int32") o.pairwf_int32 = value != 0;
+    else if (k == "no_bandkernel") o.no_bandkernel = value != 0;
+    else if (k == "no_shortread") o.no_shortread = value != 0;
+    else if (k == "serial_chunks") o.serial_chunks = value != 0;
+    else if (k == "trace") o.trace = value != 0;
+    else if (k == "no_sidecar") o.no_sidecar = value != 0;
+    else if (k == "chunks") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks = (int)value; }
+    else if (k == "tb_budget_bytes") { if (value < (1 << 16)) return DPX_ERR_INVALID; ctx->tb_budget_bytes = (size_t)value; }
+    else { ctx->err = "unknown option: " + k; return DPX_ERR_INVALID; }
+    return DPX_OK;
+}
+
+void dpx_free(void* p) {
+    if (!p) return;
+    dpxhost_pack::forget(p);                       // a parser blob / index: its packed sidecar goes with it
+    if (!g_host.give_back(p)) free(p);
+}
 
 // ---- parser (replaces c++/parseInput.cpp:9-119) -------------------------------------------------
-int dpx_parse_input(const char* path, dpx_seq_pair** pairs_out, char** seq_out, dpx_input_info* info) {
-    if (!path || !pairs_out || !seq_out) return DPX_ERR_INVALID;
-    *pairs_out = nullptr; *seq_out = nullptr;
-    FILE* f = fopen(path, "rb");
-    if (!f) return DPX_ERR_IO;
-    if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return DPX_ERR_IO; }
-    long sz = ftell(f);
-    if (sz < 0) { fclose(f); return DPX_ERR_IO; }
-    rewind(f);
-    char* buf = (char*)malloc((size_t)sz + 1);
-    if (!buf) { fclose(f); return DPX_ERR_NOMEM; }
-    size_t got = fread(buf, 1, (size_t)sz, f);
-    fclose(f);
-    if (got != (size_t)sz) { free(buf); return DPX_ERR_IO; }
+// buf holds the file image (got bytes, newlines in place) and becomes the blob; on success it is owned by the caller.
+static int parse_buffer(char* buf, size_t got, dpx_seq_pair** pairs_out, dpx_input_info* info) {
+    if (got > 0x7fffffffull) return DPX_ERR_RANGE;                   // seqPair offsets are int (parseInput.h:22-29)
     size_t lines = 0;
     for (size_t i = 0; i < got; ++i) lines += (buf[i] == '\n');
-    if (lines % 3 != 0) { free(buf); return DPX_ERR_FORMAT; }      // parseInput.cpp:38-41
+    if (lines % 3 != 0) return DPX_ERR_FORMAT;                       // parseInput.cpp:38-41
     size_t n = lines / 3;
     const size_t cap = 10000000;                                     // INPUT_CAP, parseInput.cpp:7,102-105
     dpx_seq_pair* idx = (dpx_seq_pair*)malloc(std::max<size_t>(n, 1) * sizeof(dpx_seq_pair));
-    if (!idx) { free(buf); return DPX_ERR_NOMEM; }
+    if (!idx) return DPX_ERR_NOMEM;
     dpx_input_info in{}; in.minReferenceLength = SIZE_MAX; in.minQueryLength = SIZE_MAX;
     int mode = 0; size_t k = 0;
     for (size_t i = 0; i < got && k < n; ++i) {
@@ -282,10 +331,67 @@ int dpx_parse_input(const char* path, dpx_seq_pair** pairs_out, char** seq_out, 
     }
     in.numPairs = k; in.numBytes = got;
     if (k) { in.avgReferenceLength /= (double)k; in.avgQueryLength /= (double)k; }
-    *pairs_out = idx; *seq_out = buf;
+    *pairs_out = idx;
     if (info) *info = in;
+    // 2-bit sidecar for the one-call path (host_pack.h); inputs with a fifth symbol simply stay unregistered
+    if (k) dpxhost_pack::register_input(buf, got, idx, k);
     return DPX_OK;
 }
+
+int dpx_parse_input(const char* path, dpx_seq_pair** pairs_out, char** seq_out, dpx_input_info* info) {
+    if (!path || !pairs_out || !seq_out) return DPX_ERR_INVALID;
+    *pairs_out = nullptr; *seq_out = nullptr;
+    FILE* f = fopen(path, "rb");
+    if (!f) return DPX_ERR_IO;
+    if (fseek(f, 0, SEEK_END) != 0) { fclose(f); return DPX_ERR_IO; }
+    long sz = ftell(f);
+    if (sz < 0) { fclose(f); return DPX_ERR_IO; }
+    rewind(f);
+    char* buf = (char*)malloc((size_t)sz + 1);
+    if (!buf) { fclose(f); return DPX_ERR_NOMEM; }
+    size_t got = fread(buf, 1, (size_t)sz, f);
+    fclose(f);
+    if (got != (size_t)sz) { free(buf); return DPX_ERR_IO; }
+    const int st = parse_buffer(buf, got, pairs_out, info);
+    if (st) { free(buf); return st; }
+    *seq_out = buf;
+    return DPX_OK;
+}
+
+int dpx_parse_image(const char* image, size_t n_bytes, dpx_seq_pair** pairs_out, char** seq_out, dpx_input_info* info) {
+    if ((!image && n_bytes) || !pairs_out || !seq_out) return DPX_ERR_INVALID;
+    *pairs_out = nullptr; *seq_out = nullptr;
+    char* buf = (char*)malloc(n_bytes + 1);
+    if (!buf) return DPX_ERR_NOMEM;
+    if (n_bytes) memcpy(buf, image, n_bytes);
+    const int st = parse_buffer(buf, n_bytes, pairs_out, info);
+    if (st) { free(buf); return st; }
+    *seq_out = buf;
+    return DPX_OK;
+}
+
+int dpx_register_input(const char* sequences, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs) {
+    if ((!sequences && n_bytes) || (!pairs && n_pairs)) return DPX_ERR_INVALID;
+    return dpxhost_pack::register_input(sequences, n_bytes, pairs, n_pairs);
+}
+
+int dpx_input_sidecar(const char* sequences, size_t* n_pairs, size_t* n_words, const uint32_t** words, const uint32_t** word_offsets,
+                      int* n_symbols, int* page_locked, unsigned char* code_to_byte) {
+    const dpxhost_pack::Sidecar* s = sequences ? dpxhost_pack::find_blob(sequences) : nullptr;
+    if (!s) return 0;
+    if (n_pairs) *n_pairs = s->n_pairs;
+    if (n_words) *n_words = s->n_words;
+    if (words) *words = s->words;
+    if (word_offsets) *word_offsets = s->woff;
+    if (n_symbols) *n_symbols = s->nsym;
+    if (page_locked) *page_locked = s->pinned ? 1 : 0;
+    if (code_to_byte) memcpy(code_to_byte, s->inv, 4);
+    return s->uniform ? 2 : 1;
+}
+
+void dpx_unregister_input(const char* sequences) { if (sequences) dpxhost_pack::forget(sequences); }
+
+int dpx_bind_host_to_device(int device) { return dpxhost_pack::bind_thread_to_device(device); }
 
 #include "host_fastx.cuh"
 
@@ -295,20 +401,25 @@ int dpx_dpx_eval(dpx_ctx* ctx, int op, const uint32_t* a, const uint32_t* b, con
     if (!ctx || !a || !b || !c || !out || !pred_hi || !pred_lo || n < 0 || op < 0 || op >= OP_COUNT) return DPX_ERR_INVALID;
     if (n == 0) return DPX_OK;
     CU(cudaSetDevice(ctx->device));
-    uint32_t *da, *db, *dc, *dout; uint8_t *dh, *dl;
-    CU(cudaMalloc(&da, 4 * (size_t)n)); CU(cudaMalloc(&db, 4 * (size_t)n)); CU(cudaMalloc(&dc, 4 * (size_t)n));
-    CU(cudaMalloc(&dout, 4 * (size_t)n)); CU(cudaMalloc(&dh, n)); CU(cudaMalloc(&dl, n));
-    CU(cudaMemcpyAsync(da, a, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(db, b, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(dc, c, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    dpx_eval_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(op, da, db, dc, n, dout, dh, dl);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(out, dout, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(pred_hi, dh, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(pred_lo, dl, n, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    uint32_t *da = nullptr, *db = nullptr, *dc = nullptr, *dout = nullptr; uint8_t *dh = nullptr, *dl = nullptr;
+    auto run = [&]() -> int {
+        CU(cudaMalloc(&da, 4 * (size_t)n)); CU(cudaMalloc(&db, 4 * (size_t)n)); CU(cudaMalloc(&dc, 4 * (size_t)n));
+        CU(cudaMalloc(&dout, 4 * (size_t)n)); CU(cudaMalloc(&dh, n)); CU(cudaMalloc(&dl, n));
+        CU(cudaMemcpyAsync(da, a, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(db, b, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(dc, c, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        dpx_eval_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(op, da, db, dc, n, dout, dh, dl);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, dout, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(pred_hi, dh, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(pred_lo, dl, n, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        return DPX_OK;
+    };
+    const int st = run();
+    if (st) cudaStreamSynchronize(ctx->stream);
     cudaFree(da); cudaFree(db); cudaFree(dc); cudaFree(dout); cudaFree(dh); cudaFree(dl);
-    return DPX_OK;
+    return st;
 }
 
 int dpx_selftest_dpx(dpx_ctx* ctx) {
@@ -346,6 +457,7 @@ static void batch_release(dpx_batch* b) {
     DevPool& P = b->ctx->pool;
     P.release(b->d_blob_alloc); P.release(b->d_pairs); P.release(b->d_packed); P.release(b->d_codes_alloc); P.release(b->d_pk_off); P.release(b->d_str_len);
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
+    P.release(b->d_stage[0]); P.release(b->d_stage[1]);
     P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
     for (auto e : b->ev) cudaEventDestroy(e);
     for (auto e : b->ev_sync) cudaEventDestroy(e);
@@ -500,6 +612,88 @@ static int batch_create(dpx_ctx* ctx, cudaStream_t st, int lane, const char* seq
     *out = b;
     return DPX_OK;
 }
+// Upload of pairs [p0, p0 + n) of a registered input from its host-side 2-bit sidecar (host_pack.h): the packed words cross
+// PCIe as they are (0.25 B per base), plus 8 B per pair of sizes / word offsets when the lengths are ragged and nothing at
+// all when they are uniform; no device pass over the bytes, no host sync.  Returns DPX_ERR_UNSUPPORTED when the chunk does
+// not fit the synthetic int32 byte layout (the caller then takes the raw-byte route).
+static int batch_from_sidecar(dpx_ctx* ctx, cudaStream_t st, int lane, const dpxhost_pack::Sidecar* sc, size_t p0, size_t n, dpx_batch** out) {
+    const size_t w0 = sc->woff[p0], w1 = sc->woff[p0 + n], nw = w1 - w0;
+    if (16ull * (unsigned long long)nw + 16ull > 0x7fffffffull) return DPX_ERR_UNSUPPORTED;
+    dpx_batch* b = new dpx_batch();
+    b->ctx = ctx; b->stream = st; b->lane = lane; b->n_pairs = n; b->byte_lo = 0; b->byte_hi = (long long)(16ull * nw);
+    b->from_sidecar = true; b->packed2 = true; b->n_symbols = sc->nsym;
+    memcpy(b->lut.code, sc->code, 256);
+    b->inv4 = (uint32_t)sc->inv[0] | (uint32_t)sc->inv[1] << 8 | (uint32_t)sc->inv[2] << 16 | (uint32_t)sc->inv[3] << 24;
+    auto fail = [&](int s) { cudaStreamSynchronize(st); batch_release(b); return s; };
+    // facts of the chunk: closed form for uniform lengths, one host loop over the sizes otherwise
+    if (sc->uniform) {
+        b->max_r = b->min_r = sc->R; b->max_q = b->min_q = sc->Q; b->uniform = true;
+        b->info.cells = (unsigned long long)n * (unsigned long long)sc->R * (unsigned long long)sc->Q;
+        b->info.sum_r = (unsigned long long)n * sc->R; b->info.sum_q = (unsigned long long)n * sc->Q;
+        b->pk_stride = (unsigned long long)((sc->R + 15) >> 4) + (unsigned long long)((sc->Q + 15) >> 4);
+    } else if (n == sc->n_pairs) {
+        b->max_r = sc->max_r; b->max_q = sc->max_q; b->min_r = sc->min_r; b->min_q = sc->min_q;
+        b->info.cells = sc->cells; b->info.sum_r = sc->sum_r; b->info.sum_q = sc->sum_q;
+    } else {
+        int maxr = 0, maxq = 0, minr = 0x7fffffff, minq = 0x7fffffff; unsigned long long cells = 0, sr = 0, sq = 0;
+        for (size_t i = p0; i < p0 + n; ++i) {
+            const int R = sc->small ? (int)(sc->sizes[i] & 0xffffu) : (int)sc->sizes[2 * i], Q = sc->small ? (int)(sc->sizes[i] >> 16) : (int)sc->sizes[2 * i + 1];
+            maxr = std::max(maxr, R); maxq = std::max(maxq, Q); minr = std::min(minr, R); minq = std::min(minq, Q);
+            cells += (unsigned long long)R * (unsigned long long)Q; sr += (unsigned long long)R; sq += (unsigned long long)Q;
+        }
+        b->max_r = maxr; b->max_q = maxq; b->min_r = minr; b->min_q = minq;
+        b->info.cells = cells; b->info.sum_r = sr; b->info.sum_q = sq;
+    }
+    if (!sc->uniform) b->uniform = (b->max_r == b->min_r && b->max_q == b->min_q);
+    if (b->uniform && !sc->uniform) b->pk_stride = (unsigned long long)((b->max_r + 15) >> 4) + (unsigned long long)((b->max_q + 15) >> 4);
+    b->info.max_r = b->max_r; b->info.max_q = b->max_q; b->info.packed_words = nw;
+    b->info.str_bytes = 3ull * (b->info.sum_r + b->info.sum_q + (unsigned long long)n);
+    uint32_t *d_sizes = nullptr, *d_woff = nullptr;
+    const bool ragged = !sc->uniform;
+    const size_t sz_words = ragged ? n * (sc->small ? 1 : 2) : 0;
+    if (!pool_alloc(ctx, &b->d_packed, nw + 4) || !pool_alloc(ctx, &b->d_pairs, n) || !pool_alloc(ctx, &b->d_scores, n) ||
+        !pool_alloc(ctx, &b->d_end_rc, 2 * n) || !pool_alloc(ctx, &b->d_str_len, n + 1) ||
+        (!b->uniform && !pool_alloc(ctx, &b->d_pk_off, n + 1)) ||
+        (ragged && (!pool_alloc(ctx, &d_sizes, sz_words) || !pool_alloc(ctx, &d_woff, n + 1)))) { ctx->pool.release(d_sizes); ctx->pool.release(d_woff); return fail(DPX_ERR_NOMEM); }
+    auto fail2 = [&](int s) { cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->copy_stream); ctx->pool.release(d_sizes); ctx->pool.release(d_woff); batch_release(b); return s; };
+#define CUS_(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail2(e__ == cudaErrorMemoryAllocation ? DPX_ERR_NOMEM : DPX_ERR_CUDA); } } while (0)
+    CUS_(cudaEventCreate(&b->ev_begin)); CUS_(cudaEventCreate(&b->ev_end));
+    CUS_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    if (nw) CUS_(cudaMemcpyAsync(b->d_packed, sc->words + w0, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+    if (ragged) {
+        CUS_(cudaMemcpyAsync(d_sizes, sc->sizes + p0 * (sc->small ? 1 : 2), sz_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CUS_(cudaMemcpyAsync(d_woff, sc->woff + p0, (n + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    CUS_(cudaEventRecord(b->ev_h2d, ctx->copy_stream));
+    CUS_(cudaStreamWaitEvent(st, b->ev_h2d, 0));
+    sidecar_expand_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>((int)n, sc->R, sc->Q, b->pk_stride, d_sizes, sc->small ? 1 : 0, d_woff,
+                                                                 b->d_pairs, b->uniform ? nullptr : b->d_pk_off, b->d_str_len);
+    CUS_(cudaGetLastError());
+#undef CUS_
+    // the staging arrays go back to the pool now: the pool hands memory out in stream order of THIS lane only when the next
+    // user is queued behind the expand kernel, which holds for every allocation made for this batch or after it on this lane;
+    // other lanes could grab them earlier, so they stay with the batch until it is released
+    b->d_stage[0] = d_sizes; b->d_stage[1] = d_woff;
+    b->h2d_bytes = nw * sizeof(uint32_t) + (ragged ? (sz_words + n + 1) * sizeof(uint32_t) : 0);
+    *out = b;
+    return DPX_OK;
+}
+
+// Raw bytes of a sidecar batch, materialised on the device from the packed words the first time a kernel needs them
+// (alignment strings, the byte-compare wavefront kernels).
+static int ensure_blob(dpx_batch* b) {
+    if (b->d_blob_alloc || !b->from_sidecar || b->n_pairs == 0) return DPX_OK;
+    dpx_ctx* ctx = b->ctx;
+    const unsigned long long nw = b->info.packed_words;
+    if (!pool_alloc(ctx, &b->d_blob_alloc, (size_t)(16ull * nw) + 64)) return DPX_ERR_NOMEM;
+    b->d_blob = b->d_blob_alloc;
+    if (nw) {
+        const int blocks = (int)std::min<unsigned long long>((nw + 255) / 256, (unsigned long long)ctx->sm_count * 16);
+        unpack2_kernel<<<blocks, 256, 0, b->stream>>>(b->d_packed, nw, reinterpret_cast<uint4*>(b->d_blob_alloc), b->inv4);
+        CU(cudaGetLastError());
+    }
+    return DPX_OK;
+}
 #undef CUB_
 
 #include "host_run.cuh"
@@ -512,6 +706,8 @@ void dpx_batch_free(dpx_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
     cudaStreamSynchronize(b->stream);
+    // the chunked traceback pipeline also queues work on the auxiliary streams; a run that failed half-way never joined them
+    if (b->used_aux) for (int l = 0; l < 3; ++l) cudaStreamSynchronize(b->ctx->aux_stream[l]);
     batch_release(b);
 }
 
@@ -520,6 +716,11 @@ int dpx_batch_upload(dpx_ctx* ctx, const char* sequences, size_t n_bytes, const 
     if (!ctx || !out || (!sequences && n_bytes) || (!pairs && n_pairs) || n_pairs > 0x7fffffffu) return DPX_ERR_INVALID;
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
+    size_t p0 = 0;
+    if (const dpxhost_pack::Sidecar* sc = (n_pairs && !ctx->opt.no_sidecar) ? dpxhost_pack::find(sequences, pairs, n_pairs, &p0) : nullptr) {
+        const int s = batch_from_sidecar(ctx, ctx->stream, 0, sc, p0, n_pairs, out);
+        if (s != DPX_ERR_UNSUPPORTED) return s;
+    }
     return batch_create(ctx, ctx->stream, 0, sequences, 0, (long long)n_bytes, pairs, n_pairs, out);
 }
 
@@ -811,7 +1012,7 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     const size_t nchunks = bound.size() - 1;
     std::vector<dpx_batch*> chunk_batch(nchunks, nullptr);
     int status = DPX_OK;
-    const bool trace = getenv("DPX_TRACE") != nullptr;
+    const bool trace = ctx->opt.trace != 0;
     const auto t_call = std::chrono::steady_clock::now();
     auto now_us = [&]() { return (long long)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t_call).count(); };
     bool have_lut = false; PackLut lut; int nsym = 0;
@@ -819,11 +1020,28 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     if (!pool_alloc(ctx, &d_unknown, 1)) return DPX_ERR_NOMEM;
     CU(cudaMemsetAsync(d_unknown, 0, sizeof(int), ctx->copy_stream));
 
+    // Registered input (parser output / dpx_register_input): every chunk uploads its slice of the host-side 2-bit sidecar --
+    // a quarter of the bytes, no device pass, no alphabet handshake with chunk 0.
+    size_t sc_first = 0;
+    const dpxhost_pack::Sidecar* sc = ctx->opt.no_sidecar ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
+    for (size_t c = 0; sc && c < nchunks; ++c)
+        if (16ull * (unsigned long long)(sc->woff[sc_first + bound[c + 1]] - sc->woff[sc_first + bound[c]]) + 16ull > 0x7fffffffull) sc = nullptr;
+
     std::vector<char> chunk_fast(nchunks, 0);
     // A(c): host scan of the chunk's index, buffers, input copies (and the device pass when the chunk is not uniform)
     auto stage_a = [&](size_t c) -> int {
         const size_t p0 = bound[c], p1 = bound[c + 1];
         const long long ta = now_us();
+        if (sc) {
+            const int lane = (int)(c % NL);
+            if (inflight[lane]) { cudaStreamSynchronize(lanes[lane]); batch_release(inflight[lane]); inflight[lane] = nullptr; }
+            dpx_batch* b = nullptr;
+            const int s = batch_from_sidecar(ctx, lanes[lane], lane, sc, sc_first + p0, p1 - p0, &b);
+            if (s) return s;
+            inflight[lane] = b; chunk_batch[c] = b;
+            if (trace) fprintf(stderr, "[dpx] A(%zu) sidecar pairs %zu bytes %zu  issue %lld..%lld us\n", c, p1 - p0, b->h2d_bytes, ta, now_us());
+            return DPX_OK;
+        }
         long long lo = (long long)n_bytes, hi = 0;
         int minr = 0x7fffffff, maxr = -1, minq = 0x7fffffff, maxq = -1;
         // is the index an arithmetic progression?  (fixed-length files: every record has the same size)
@@ -861,6 +1079,12 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
         dpx_batch* b = chunk_batch[c];
         const long long tb0 = now_us();
         int s;
+        if (sc) {
+            s = batch_run(b, params);
+            if (!s) s = batch_fetch_async(b, scores + p0, end_row_col ? end_row_col + 2 * p0 : nullptr);
+            if (trace) fprintf(stderr, "[dpx] B(%zu) issued %lld..%lld us\n", c, tb0, now_us());
+            return s;
+        }
         if (chunk_fast[c] && have_lut && nsym <= 4) {
             s = batch_known_pack(b, lut, nsym, d_unknown);
         } else {

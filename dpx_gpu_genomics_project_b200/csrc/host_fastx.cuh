@@ -105,5 +105,6 @@ int dpx_parse_fastx(const char* path_refs, const char* path_queries, dpx_seq_pai
     if (n) { in.avgReferenceLength /= (double)n; in.avgQueryLength /= (double)n; }
     *pairs_out = idx; *seq_out = seq;
     if (info) *info = in;
+    if (n) dpxhost_pack::register_input(seq, blob.size(), idx, n);     // 2-bit sidecar for the one-call path (host_pack.h)
     return DPX_OK;
 }

@@ -155,14 +155,14 @@ static int long_pair_single(dpx_ctx* ctx, const dpx_params* p, const char* ref, 
                             int32_t* score, int64_t* end_row, int64_t* end_col, LongCkpt* ck = nullptr) {
     cudaStream_t st = ctx->stream;
     uint8_t code[256];
-    const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !getenv("DPX_LONG_NOTABLE");
+    const bool table = long_table_ok(p, R, Q) && long_alphabet(ref, R, qry, Q, code) <= 4 && !ctx->opt.long_notable;
     const bool allow32 = table && (long double)p->match * (long double)std::min(R, Q) < 6.0e7L;
     int K = long_pick_k(ctx, (long long)R, allow32);
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && allow32)) K = k; }   // tests
+    if (const int k = ctx->opt.long_k) { if (k != 32 || allow32) K = k; }                                                    // dpx_set_option("long_k")
     int capacity = 0;
     const int mode = (long_can_pack(p, R, Q) ? 1 : 0) | (table ? 2 : 0) | (ck ? 4 : 0);
     { int s = long_capacity_k(ctx, K, mode, &capacity); if (s) return s; }
-    if (const char* e = getenv("DPX_LONG_CAP")) { const int c = atoi(e); if (c >= 4 && c < capacity) capacity = c & ~3; }   // tests: force passes
+    if (const int c = ctx->opt.long_cap) { if (c >= 4 && c < capacity) capacity = c & ~3; }                                   // dpx_set_option("long_cap"): force passes
     if (capacity < 4) { ctx->err = "long-pair kernel does not fit"; return DPX_ERR_RANGE; }
     const long long CW = 32LL * K;
     const long long nw_total = ((long long)R + CW - 1) / CW;
@@ -322,7 +322,7 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     const size_t fill_smem = long_bt_fill_smem(TH, nt), walk_smem = long_bt_walk_smem(TH, TW), slot_words = long_bt_slot_words(TH, TW);
     if (nt > 256 || walk_smem > (size_t)200 * 1024) { ctx->err = "long-pair traceback: tile does not fit shared memory"; cleanup(); return DPX_ERR_RANGE; }
     int max_tiles = 2 * ctx->sm_count;
-    if (const char* e = getenv("DPX_LONG_BT_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 4096) max_tiles = v; }   // tests: short rounds
+    if (ctx->opt.long_bt_tiles >= 1) max_tiles = ctx->opt.long_bt_tiles;                                                      // dpx_set_option("long_bt_tiles"): short rounds
     if (!pool_alloc(ctx, &d_tiles, (size_t)max_tiles) || !pool_alloc(ctx, &d_slots, slot_words * (size_t)max_tiles) ||
         !pool_alloc(ctx, &d_edges, long_bt_edge_words(TH, TW) * (size_t)max_tiles) || !pool_alloc(ctx, &d_segs, (size_t)max_tiles) ||
         !pool_alloc(ctx, &d_seg_off, (size_t)max_tiles)) { cleanup(); return DPX_ERR_NOMEM; }

@@ -11,19 +11,22 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
     dpx_stripe* s = new dpx_stripe();
     s->ctx = ctx; s->params = *params; s->R_local = R_local; s->col_offset = col_offset; s->Q = Q; s->index = stripe_index; s->n = n_stripes;
     auto fail = [&](int st) { dpx_stripe_free(s); return st; };
-    // The code map must be identical on every rank, so it is fixed instead of data-derived: digits '0'..'3' and A/C/G/T
-    // (either case) map to 0..3; any other byte in this rank's data switches this stripe to the byte-compare kernel, which
-    // is still exact because all ranks then compare (query byte, reference byte) pairs -- but the QUERY must be coded the
-    // same way everywhere, so TABLE is only used when the whole query and this stripe's reference are inside the map.
+    // Every stripe must realise the reference's relation, plain byte equality (c++/LinearSmithWaterman.cpp:92), whatever
+    // kernel it picks, so that per-rank choices cannot disagree.  The table kernel codes bytes with a FIXED injective map
+    // of ONE family -- digits '0'..'3', or upper-case ACGT, or lower-case acgt -- and is only taken when the whole query
+    // and this stripe's reference lie inside that one family (code equality == byte equality there).  Anything else
+    // (a fifth symbol, mixed case such as a soft-masked reference against upper-case reads, digits next to letters) sends
+    // this stripe to the byte-compare kernel, which is the same relation by construction.
     static const auto fixed_code = [](uint8_t c) -> int {
         switch (c) { case '0': case 'A': case 'a': return 0; case '1': case 'C': case 'c': return 1;
                      case '2': case 'G': case 'g': return 2; case '3': case 'T': case 't': return 3; default: return -1; }
     };
-    bool table = long_table_ok(params, Q, Q) && !getenv("DPX_LONG_NOTABLE");
-    bool digits = false, letters = false;
-    for (size_t i = 0; i < Q && table; ++i) { const uint8_t c = (uint8_t)qry[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
-    for (size_t i = 0; i < R_local && table; ++i) { const uint8_t c = (uint8_t)ref_stripe[i]; if (fixed_code(c) < 0) table = false; (c <= '9' ? digits : letters) = true; }
-    if (digits && letters) table = false;         // '0' and 'A' would collide
+    static const auto family = [](uint8_t c) -> int { return c <= '9' ? 1 : (c < 'a' ? 2 : 4); };
+    bool table = long_table_ok(params, Q, Q) && !ctx->opt.long_notable;
+    int fam = 0;
+    for (size_t i = 0; i < Q && table; ++i) { const uint8_t c = (uint8_t)qry[i]; if (fixed_code(c) < 0) table = false; fam |= family(c); }
+    for (size_t i = 0; i < R_local && table; ++i) { const uint8_t c = (uint8_t)ref_stripe[i]; if (fixed_code(c) < 0) table = false; fam |= family(c); }
+    if (fam & (fam - 1)) table = false;           // two families: 'a' and 'A' (or '0' and 'A') would share a code
     s->mode = ((long double)params->match * (long double)Q < 8.0e6L && params->match > 0 ? 1 : 0) | (table ? 2 : 0);
     // lane width: the whole stripe must be one co-resident pass
     // The right edge a stripe exports is the last column of its last warp, so every stripe but the last must be made of WHOLE
@@ -32,7 +35,7 @@ int dpx_stripe_create(dpx_ctx* ctx, const dpx_params* params, const char* ref_st
     auto whole = [&](int k) { return last || R_local % (32ull * (unsigned)k) == 0; };
     const bool allow32 = table && (long double)params->match * (long double)Q < 6.0e7L && whole(32);
     int K = long_pick_k(ctx, (long long)R_local, allow32), cap = 0;
-    if (const char* e = getenv("DPX_LONG_K")) { const int k = atoi(e); if (k == 2 || k == 4 || k == 8 || k == 16 || (k == 32 && allow32)) K = k; }
+    if (const int k = ctx->opt.long_k) { if (k != 32 || allow32) K = k; }
     while (K > 2 && !whole(K)) K /= 2;
     if (!whole(K)) { ctx->err = "a stripe that is not the last one must be a multiple of 64 columns wide"; return fail(DPX_ERR_INVALID); }
     for (;;) {

@@ -54,7 +54,7 @@ static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xorm
 
 // Eligibility of the packed int16x2 short-read kernel (shortread.cuh).
 static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, bool* xormode, int* kbits_out) {
-    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || !b->packed2) return false;
+    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || !b->packed2 || b->ctx->opt.no_shortread) return false;
     const int m = p->match, x = p->mismatch, g = p->gap_open;
     if (!(m > 0 && x < 0 && g < 0)) return false;                 // pads must stay strictly below real cells
     if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
@@ -113,7 +113,7 @@ struct PwPlan { int K; bool packed, wide; uint32_t lut_lo, lut_hi, ext2, addc, a
 static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl) {
     const bool sw = p->algo == DPX_ALGO_LSW;
     const bool wide = !b->packed2 && b->d_codes != nullptr;       // 5..8 symbols: int32, both table registers for one pair
-    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || (!b->packed2 && !wide) || getenv("DPX_NO_PAIRWF")) return false;
+    if ((p->algo != DPX_ALGO_LNW && p->algo != DPX_ALGO_ANW && !sw) || (!b->packed2 && !wide) || b->ctx->opt.no_pairwf) return false;
     if (sw && !(p->flags & DPX_OUT_STRINGS)) return false;      // score / end cell alone: the short-read kernel (or the int32 wavefront)
     const bool aff = p->algo == DPX_ALGO_ANW;
     const long long m = p->match, x = p->mismatch, go = p->gap_open, ge = aff ? p->gap_extend : 0;
@@ -133,7 +133,7 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
     const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
     const long long B = -4 * lo + margin;
-    const bool packed = !wide && 4 * hi + B + 16 <= 32767 && !getenv("DPX_PAIRWF_INT32");     // else one pair per warp in int32
+    const bool packed = !wide && 4 * hi + B + 16 <= 32767 && !b->ctx->opt.pairwf_int32;     // else one pair per warp in int32
     if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
     pl->K = K; pl->packed = packed; pl->wide = wide;
     pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
@@ -176,7 +176,7 @@ static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t 
 struct BandPlan { uint32_t lut_lo, lut_hi; int gadd, zerog, kb; };
 
 static bool band_eligible(const dpx_batch* b, const dpx_params* p, int band, BandPlan* pl) {
-    if (p->algo != DPX_ALGO_BSW || !b->packed2 || getenv("DPX_NO_BANDKERNEL")) return false;
+    if (p->algo != DPX_ALGO_BSW || !b->packed2 || b->ctx->opt.no_bandkernel) return false;
     const long long m = p->match, x = p->mismatch, g = p->gap_open;
     if (!(m > 0 && x < 0 && g < 0) || band < 0 || band > 96) return false;
     const long long tm = 4 * (m - g) - 1, tx = 4 * (x - g) - 1;
@@ -243,7 +243,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
 
     // one-time (per batch) preparation, outside the timed first-kernel -> last-byte window
     { int s = ensure_order(b); if (s) return s; }
-    if (want_strings) { int s = ensure_str_off(b); if (s) return s; }
+    if (want_strings) { int s = ensure_str_off(b); if (s) return s; s = ensure_blob(b); if (s) return s; }
     if (algo == DPX_ALGO_BSW) {
         if (!b->d_band_cells && !pool_alloc(ctx, &b->d_band_cells, 1)) return DPX_ERR_NOMEM;
         CU(cudaMemsetAsync(b->d_band_cells, 0, sizeof(unsigned long long), st));
@@ -310,10 +310,10 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 const size_t slots_total = (n + ppw - 1) / ppw;
                 const size_t max_slots = std::max<size_t>(1, (ctx->tb_budget_bytes / 2 / 4) / std::max<unsigned long long>(tbs, 1));
                 size_t nchunks = (slots_total + max_slots - 1) / max_slots;
-                if (!getenv("DPX_SERIAL_CHUNKS"))                                               // (set by bench.py to time the fill kernel alone)
+                if (!ctx->opt.serial_chunks)                                               // (set by bench.py to time the fill kernel alone)
                     nchunks = std::max<size_t>(nchunks, std::min<size_t>(8, n / 16384));        // >= 16k pairs per chunk: whole waves of warps
                 const size_t slots = (slots_total + nchunks - 1) / nchunks;
-                per_chunk = ppw * slots; nbuf = (nchunks > 1 && !getenv("DPX_SERIAL_CHUNKS")) ? 2 : 1;
+                per_chunk = ppw * slots; nbuf = (nchunks > 1 && !ctx->opt.serial_chunks) ? 2 : 1;
                 const size_t need = (size_t)nbuf * slots * (size_t)tbs;
                 if (b->d_tb && b->tb_words < need) { CU(cudaStreamSynchronize(st)); ctx->pool.release(b->d_tb); b->d_tb = nullptr; }
                 if (!b->d_tb) { if (!pool_alloc(ctx, &b->d_tb, need)) return DPX_ERR_NOMEM; b->tb_words = need; }
@@ -326,11 +326,13 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             auto sync_event = [&](cudaEvent_t* ev) -> int { CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming)); b->ev_sync.push_back(*ev); return DPX_OK; };
             std::vector<cudaEvent_t> bt_done, fill_done;
             if (nbuf > 1) {
+                b->used_aux = true;
                 cudaEvent_t start;
                 { int r2 = sync_event(&start); if (r2) return r2; }
                 CU(cudaEventRecord(start, st));
                 CU(cudaStreamWaitEvent(fill2_st, start, 0));
             }
+            size_t bnd_slice = 0;
             PwArgs a{};
             a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
             a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu; a.zero2 = pl.zero2;
@@ -342,7 +344,10 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             size_t smem = (size_t)4 * a.bnd_stride * (aff ? 2 : 1) * 4 + (size_t)4 * a.rsel_stride * 2;
             if (smem > 44 * 1024) {
                 // long references: the boundary rows would leave fewer than 5 blocks per SM; keep them in a per-warp global buffer
-                const size_t warps = (size_t)ctx->sm_count * 16 * 4, need = warps * (size_t)a.bnd_stride * (aff ? 2 : 1);
+                // (one slice per slab buffer: with nbuf = 2 the fills of chunks c and c + 1 run concurrently on two streams)
+                const size_t warps = (size_t)ctx->sm_count * 16 * 4;
+                bnd_slice = warps * (size_t)a.bnd_stride * (aff ? 2 : 1);
+                const size_t need = (size_t)nbuf * bnd_slice;
                 if (ctx->boundary_ints[b->lane] < need) {
                     if (ctx->boundary[b->lane]) { CU(cudaStreamSynchronize(st)); cudaFree(ctx->boundary[b->lane]); ctx->boundary[b->lane] = nullptr; ctx->boundary_ints[b->lane] = 0; }
                     CU(cudaMalloc(&ctx->boundary[b->lane], need * sizeof(int32_t))); ctx->boundary_ints[b->lane] = need;
@@ -356,6 +361,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 a.first = (int)first; a.count = (int)std::min(per_chunk, n - first);
                 a.counter = counters + (c % 64);
                 a.tb = want_strings ? b->d_tb + (size_t)(c % nbuf) * (per_chunk / (pl.packed ? 2 : 1)) * (size_t)tbs : nullptr;
+                if (bnd_slice) a.bnd_global = reinterpret_cast<uint32_t*>(ctx->boundary[b->lane]) + (size_t)(c % nbuf) * bnd_slice;
                 cudaStream_t fst = (c & 1) ? fill2_st : st;
                 if (nbuf > 1 && c >= nbuf) CU(cudaStreamWaitEvent(fst, bt_done[c - nbuf], 0));     // the buffer's previous walk is over
                 CU(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int), fst));
@@ -471,6 +477,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     }
 
     // ---- general path: warp-per-pair wavefront (+ traceback and GPU backtrack) ----------------------------
+    { int s = ensure_blob(b); if (s) return s; }              // byte-compare kernels: sidecar batches materialise their bytes first
     const unsigned long long tb_stride = want_strings ? WfGeom::make(K, CB, b->max_q, b->max_r, band).words() : 0;
     size_t per_chunk = n;
     if (want_strings) {

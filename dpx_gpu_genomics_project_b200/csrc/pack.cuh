@@ -180,4 +180,42 @@ __global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ 
     }
 }
 
+// ---- batches uploaded from the host-side 2-bit sidecar (host_pack.h): the packed words arrive as they are; what the other
+// kernels expect beside them is rebuilt here.  Byte layout of such a batch is synthetic: packed word w covers bytes
+// [16 w, 16 w + 16), so a pair whose words start at w has referenceIdx = 16 w and queryIdx = 16 (w + ceil(R / 16)).
+__global__ void __launch_bounds__(256) sidecar_expand_kernel(int n, int uni_r, int uni_q, unsigned long long stride,
+                                                              const uint32_t* __restrict__ sizes, int small_sizes, const uint32_t* __restrict__ woff,
+                                                              dpx_seq_pair* __restrict__ pairs, unsigned long long* __restrict__ pk_off,
+                                                              unsigned long long* __restrict__ str_len) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    int R = uni_r, Q = uni_q; unsigned long long w = (unsigned long long)k * stride;
+    if (sizes) {
+        if (small_sizes) { const uint32_t v = sizes[k]; R = (int)(v & 0xffffu); Q = (int)(v >> 16); }
+        else { R = (int)sizes[2 * k]; Q = (int)sizes[2 * k + 1]; }
+        w = (unsigned long long)(woff[k] - woff[0]);
+    }
+    dpx_seq_pair p;
+    p.referenceIdx = (int32_t)(16ull * w); p.referenceSize = R;
+    p.queryIdx = (int32_t)(16ull * (w + (unsigned long long)((R + 15) >> 4))); p.querySize = Q;
+    pairs[k] = p;
+    if (pk_off) pk_off[k] = w;
+    if (str_len) str_len[k] = 3ull * ((unsigned long long)R + (unsigned long long)Q + 1ull);
+}
+
+// packed words -> bytes in the synthetic layout (only when a kernel needs the raw bytes: alignment strings, byte-compare fall-back)
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint32_t* __restrict__ packed, unsigned long long n_words, uint4* __restrict__ blob16, uint32_t inv4) {
+    for (unsigned long long w = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t v = packed[w];
+        uint32_t o[4];
+        #pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t c = v >> (8 * q);
+            const uint32_t sel = (c & 3u) | ((c >> 2 & 3u) << 4) | ((c >> 4 & 3u) << 8) | ((c >> 6 & 3u) << 12);
+            o[q] = __byte_perm(inv4, 0u, sel);
+        }
+        blob16[w] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 }  // namespace dpx

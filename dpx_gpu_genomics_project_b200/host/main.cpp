@@ -10,6 +10,8 @@
 //                                                                -DBACKTRACK_ALL (c++/LinearSmithWaterman.h:9)
 //                                        -long                   LSW on pairs too long for a batch (Mbp): every pair of the file goes
 //                                                                through dpx_align_long_pair_strings (checkpoints + tile walk), same blocks
+//                                        -gpus N | -devices a,b,..  every GPU named aligns one contiguous shard of the file (dpx_create_multi:
+//                                                                one host thread + context per device, results in pair order)
 //                                        -fastx F [-fastx2 G]    pairs from FASTA / FASTQ records instead of -pairs (one file: records
 //                                                                alternate reference, query; two files: paired by order)
 // Output: "Parsing input file: F", "Pair # | Score", then per pair "<i> | <score>" REF REL QRY, then
@@ -31,6 +33,7 @@ int main(int argc, char* argv[]) {
     int matchWeight = 3, mismatchWeight = -1, gapOpenWeight = -4, gapExtendWeight = -1;   // defaults of main.cpp:128-132
     int algo = DPX_ALGO_LSW, band = 64; bool scores_only = false, long_pairs = false, all_maxima = false;
     const char* fastx = nullptr; const char* fastx2 = nullptr;
+    std::vector<int> devices;
     for (int i = 1; i < argc; ++i) {
         const bool has = i + 1 < argc;
         if (!strcmp(argv[i], "-pairs") && has) pairFileName = argv[++i];
@@ -42,6 +45,8 @@ int main(int argc, char* argv[]) {
         else if (!strcmp(argv[i], "-scores")) scores_only = true;
         else if (!strcmp(argv[i], "-long")) long_pairs = true;
         else if (!strcmp(argv[i], "-all")) all_maxima = true;
+        else if (!strcmp(argv[i], "-gpus") && has) { const int n = atoi(argv[++i]); devices.clear(); for (int d = 0; d < n; ++d) devices.push_back(d); }
+        else if (!strcmp(argv[i], "-devices") && has) { devices.clear(); for (char* t = strtok(argv[++i], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t)); }
         else if (!strcmp(argv[i], "-fastx") && has) fastx = argv[++i];
         else if (!strcmp(argv[i], "-fastx2") && has) fastx2 = argv[++i];
         else if (!strcmp(argv[i], "-algo") && has) {
@@ -63,8 +68,28 @@ int main(int argc, char* argv[]) {
     dpx_params p = dpxhost::make_params(algo, matchWeight, mismatchWeight, gapOpenWeight, gapExtendWeight, band);
     if (scores_only) p.flags = DPX_OUT_SCORE | DPX_OUT_END_COORDS;
     char* text = nullptr; size_t text_bytes = 0;
-    dpx_ctx* ctx = dpxhost::engine();
     int st;
+    if (!devices.empty() && !long_pairs && !all_maxima) {
+        // several GPUs, one process: parse on the host (the parser also leaves the packed 2-bit copy every shard uploads from),
+        // then one multi-device batch call; the text blocks come back in pair order
+        dpx_multi* m = nullptr;
+        st = dpx_create_multi(&m, devices.data(), (int)devices.size());
+        if (st != DPX_OK) { fprintf(stderr, "dpxalign: cannot create the device contexts: %s\n", dpx_strerror(st)); exit(1); }
+        dpx_seq_pair* idx = nullptr; char* seqs = nullptr; dpx_input_info info{};
+        st = fastx ? dpx_parse_fastx(fastx, fastx2, &idx, &seqs, &info) : dpx_parse_input(pairFileName, &idx, &seqs, &info);
+        if (st == DPX_OK) st = dpx_multi_align_batch_text(m, &p, seqs, info.numBytes, idx, info.numPairs, 0, nullptr, nullptr, &text, &text_bytes);
+        if (st == DPX_ERR_IO) { fprintf(stderr, "Could not open file: %s\n", pairFileName); exit(1); }
+        if (st == DPX_ERR_FORMAT) { fprintf(stderr, "Number of lines not a multiple of 3: %s\n", pairFileName); exit(1); }
+        if (st != DPX_OK) { fprintf(stderr, "dpxalign: %s (%s)\n", dpx_strerror(st), dpx_multi_last_error(m)); exit(1); }
+        dpx_free(idx); dpx_free(seqs);
+        fwrite(text, 1, text_bytes, stdout); dpx_free(text);
+        dpx_destroy_multi(m);
+        const long long usec = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        printf("Elapsed time (usec): %lld\n", usec);
+        printf("Cleaning up\n");
+        return 0;
+    }
+    dpx_ctx* ctx = dpxhost::engine();
     if (fastx || long_pairs || all_maxima) {
         // host-side parsers: the project's 3-line records (parseInput) or FASTA / FASTQ records, then one batch — or, with -long, one
         // checkpointed alignment per pair, printed as LinearSmithWaterman::print_results does (c++/LinearSmithWaterman.cpp:240-288)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DPX_ABI_VERSION 1
+#define DPX_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------- */
 typedef enum {
@@ -105,12 +105,43 @@ const char* dpx_last_error(const dpx_ctx* ctx);
  * caller's CUDA events bracket the kernels.  NULL restores the ctx's own stream. */
 int         dpx_set_stream(dpx_ctx* ctx, void* cuda_stream);
 
+/* Debug / test knobs (the library never reads the environment).  Unknown names return DPX_ERR_INVALID.
+ *   "chunks" (1..64)         equal middle chunks of the one-call pipeline          "tb_budget_bytes"  traceback slab budget
+ *   "serial_chunks" 0/1      traceback chunks in series on one buffer              "trace" 0/1        chunk timeline on stderr
+ *   "no_sidecar" 0/1         ignore the parser's packed copy, upload raw bytes     "no_shortread" / "no_pairwf" / "no_bandkernel" /
+ *   "pairwf_int32" 0/1       kernel selection overrides (fall back to the next kernel family; still CUDA, never the CPU)
+ *   "long_k" (0,2,..32) "long_cap" "long_notable" "long_bt_tiles"   long-pair lane width / forced passes / byte-compare kernel / tiles per round */
+int         dpx_set_option(dpx_ctx* ctx, const char* name, long long value);
+/* Binds the calling host thread to the CPUs local to a CUDA device (its NUMA node) so that page-locked buffers allocated
+ * afterwards sit next to that GPU's PCIe root.  Returns the number of CPUs in the new mask, 0 if nothing was changed. */
+int         dpx_bind_host_to_device(int device);
+
 /* ---- parser: replaces parseInput / cleanupParsedFile (c++/parseInput.cpp:9-119,140-143) --
  * Same file format and outputs (blob with '\n' -> '\0', seqPair index, inputInfo) but returns
  * DPX_ERR_IO / DPX_ERR_FORMAT instead of exit(1).  Both arrays are malloc'ed; release them with
  * dpx_free.  numCells is accumulated in 64-bit (the reference multiplies two ints, :100). */
 int         dpx_parse_input(const char* path, dpx_seq_pair** pairs, char** sequences, dpx_input_info* info);
+/* Same parser on a file image already in memory (copied; the caller keeps `image`). */
+int         dpx_parse_image(const char* image, size_t n_bytes, dpx_seq_pair** pairs, char** sequences, dpx_input_info* info);
+/* Releases anything the library handed out.  Page-locked result blobs are recycled through a process-wide cache of at most
+ * 2 GiB; dpx_trim() (and the destruction of the last context) gives the cached blocks back to the driver. */
 void        dpx_free(void* p);
+void        dpx_trim(void);
+/* Packed sidecar.  The parsers above also keep a 2-bit copy of the sequences in page-locked host memory (inputs with at most
+ * four distinct symbols; the reference's timer likewise starts after parseInput, c++/main.cpp:157-164).  dpx_align_batch /
+ * dpx_batch_upload / dpx_multi_align_batch recognise the blob pointer (with the index, or any sub-range of it) and move the
+ * packed words over PCIe instead of the bytes: 4x fewer.  The blob and the index must therefore not be MODIFIED between parsing
+ * and aligning (the reference's driver never does, c++/main.cpp:237-252); dpx_free of either drops the sidecar.
+ * dpx_register_input does the same for a (blob, index) the caller built itself; dpx_unregister_input undoes it. */
+int         dpx_register_input(const char* sequences, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs);
+void        dpx_unregister_input(const char* sequences);
+/* Introspection of a registered input's sidecar (tests, logging, byte accounting): 0 = `sequences` is not registered (more than
+ * four symbols, or never parsed / registered); 1 = registered, ragged lengths (the upload adds 8 B per pair of sizes / offsets);
+ * 2 = registered, uniform lengths (packed words only).  Pair p occupies words[word_offsets[p] .. word_offsets[p+1]): ceil(R/16)
+ * reference words, then ceil(Q/16) query words, base k at bits 2*(k%16) of word k/16; code_to_byte[4] maps codes back to bytes.
+ * Any output pointer may be NULL. */
+int         dpx_input_sidecar(const char* sequences, size_t* n_pairs, size_t* n_words, const uint32_t** words, const uint32_t** word_offsets,
+                              int* n_symbols, int* page_locked, unsigned char* code_to_byte);
 /* FASTA / FASTQ front-end: the same blob + index from '>' / '@' records (multi-line sequences joined,
  * qualities skipped).  path_queries == NULL: the records of path_refs alternate reference, query; otherwise record k of
  * path_refs is the reference of pair k and record k of path_queries its query (DPX_ERR_FORMAT if the counts differ).
@@ -132,6 +163,29 @@ int         dpx_align_batch(dpx_ctx* ctx, const dpx_params* params,
                             const dpx_seq_pair* pairs, size_t n_pairs,
                             int32_t* scores, int32_t* end_row_col,
                             char** strings_blob, size_t** string_offsets);
+
+/* ---- the same call on SEVERAL GPUs of one node from ONE host process (multi-GPU mode A): one worker thread
+ * (bound to the device's NUMA node) + one dpx_ctx per device.  The pairs are cut into contiguous shards of equal cell count
+ * (prefix sums of Q*R), so every GPU uploads one contiguous slice of the blob / sidecar; inside a shard the device scheduler
+ * length-buckets as usual.  No collective: results are written straight into the caller's arrays, in pair order; strings are
+ * stitched into one blob + offset table.  devices == NULL: devices 0 .. n_devices-1.
+ * dpx_multi_shard_bounds: the shard boundaries the call would use (bounds[n_devices + 1]) -- for tests and logging. */
+typedef struct dpx_multi dpx_multi;
+int         dpx_create_multi(dpx_multi** out, const int* devices, int n_devices);
+void        dpx_destroy_multi(dpx_multi* m);
+int         dpx_multi_device_count(const dpx_multi* m);
+const char* dpx_multi_last_error(const dpx_multi* m);
+int         dpx_multi_set_option(dpx_multi* m, const char* name, long long value);     /* dpx_set_option on every device */
+int         dpx_multi_align_batch(dpx_multi* m, const dpx_params* params,
+                                  const char* sequences, size_t n_bytes,
+                                  const dpx_seq_pair* pairs, size_t n_pairs,
+                                  int32_t* scores, int32_t* end_row_col,
+                                  char** strings_blob, size_t** string_offsets);
+int         dpx_multi_align_batch_text(dpx_multi* m, const dpx_params* params,
+                                       const char* sequences, size_t n_bytes,
+                                       const dpx_seq_pair* pairs, size_t n_pairs, long long first_index,
+                                       int32_t* scores, int32_t* end_row_col, char** text, size_t* text_bytes);
+int         dpx_multi_shard_bounds(const dpx_seq_pair* pairs, size_t n_pairs, int n_shards, size_t* bounds);
 
 /* ---- staged form of the same call (what bench.py times stage by stage) ------------------
  * upload : H2D of blob + index, alphabet scan, 2-bit (4-bit escape) pack, length bucketing.

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(L):
 
 
 def test_abi_version_and_strerror(L):
-    assert L.dpx_abi_version() == 1
+    assert L.dpx_abi_version() == 2
     assert b"CPU fallback" in L.dpx_strerror(-2)
     assert L.dpx_strerror(0) == b"ok"
 

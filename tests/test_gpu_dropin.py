@@ -31,6 +31,26 @@ def test_dropin_main_stdout_equals_reference_driver(algo, flags, name):
     assert body == open(os.path.join(GOLD, f"{name}.{algo}.out.txt"), "rb").read()
 
 
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("algo,flags", [("LNW", ["-open", "-2"]), ("LSW", ["-open", "-2"]), ("ANW", ["-open", "-3", "-extend", "-1"])])
+@pytest.mark.parametrize("name", ["cfg1_small", "mid", "adversarial"])
+def test_dropin_main_on_several_devices_prints_reference_bytes(algo, flags, name):
+    """-devices / -gpus: dpx_create_multi + dpx_multi_align_batch_text (one process, one worker per device, contiguous shards).
+    On a one-GPU box the three workers share device 0 (same sharding / stitching code); with more GPUs every GPU takes a shard."""
+    path = os.path.join(GOLD, f"{name}.in.txt")
+    n = _ngpu()
+    for sel in (["-devices", "0,0,0"], ["-gpus", str(n)]) if n > 1 else (["-devices", "0,0,0"],):
+        out = subprocess.run([os.path.join(HOST, "main"), "-pairs", path, "-match", "3", "-mismatch", "-1"] + flags + ["-algo", algo] + sel,
+                             check=True, capture_output=True).stdout
+        lines = out.split(b"\n")
+        body = b"\n".join(lines[2:-3]) + b"\n"
+        assert body == open(os.path.join(GOLD, f"{name}.{algo}.out.txt"), "rb").read(), sel
+
+
 @pytest.mark.parametrize("algo", ["LNW", "LSW", "ANW", "BSW"])
 def test_reference_per_pair_loop_compiles_against_shims_and_matches(algo):
     """c++/main.cpp:237-252's loop (construct aligner, align()) against the shim classes; BSW with a full band == LSW."""

@@ -36,17 +36,15 @@ def test_long_pair_matches_oracle(eng, R, Q):
 
 
 @pytest.mark.parametrize("k,cap", [("2", "8"), ("4", "16"), ("8", "4"), ("16", "4"), ("2", "0"), ("8", "0")])
-def test_long_pair_forced_geometry_and_passes(eng, k, cap, monkeypatch):
+def test_long_pair_forced_geometry_and_passes(eng, k, cap):
     """Every lane width, several passes over column super-blocks (full-length boundary arrays between passes), ring wrap-around."""
-    monkeypatch.setenv("DPX_LONG_K", k)
-    if cap != "0":
-        monkeypatch.setenv("DPX_LONG_CAP", cap)
-    r, q = _pair(5000, 6000, 77)
-    p = api.make_params(api.LSW, match=2, mismatch=-3, gap_open=-2)
-    assert eng.align_long_pair(p, r, q) == ol.lsw_score_only(ol.params(ol.LSW, match=2, mismatch=-3, gap_open=-2), r, q)
-    # tie-heavy input: the end cell must be the first maximum in row-major order
-    r2, q2 = b"01" * 1500, b"10" * 1700
-    assert eng.align_long_pair(api.make_params(api.LSW), r2, q2) == ol.lsw_score_only(ol.params(ol.LSW), r2, q2)
+    with eng.options(long_k=int(k), long_cap=int(cap)):
+        r, q = _pair(5000, 6000, 77)
+        p = api.make_params(api.LSW, match=2, mismatch=-3, gap_open=-2)
+        assert eng.align_long_pair(p, r, q) == ol.lsw_score_only(ol.params(ol.LSW, match=2, mismatch=-3, gap_open=-2), r, q)
+        # tie-heavy input: the end cell must be the first maximum in row-major order
+        r2, q2 = b"01" * 1500, b"10" * 1700
+        assert eng.align_long_pair(api.make_params(api.LSW), r2, q2) == ol.lsw_score_only(ol.params(ol.LSW), r2, q2)
 
 
 def test_long_pair_equals_batch_engine(eng):
@@ -57,14 +55,14 @@ def test_long_pair_equals_batch_engine(eng):
     assert (s, row, col) == (int(res.scores[0]), int(res.end_row_col[0][0]), int(res.end_row_col[0][1]))
 
 
-def test_long_pair_byte_kernel_for_wide_alphabets(eng, monkeypatch):
-    """More than four symbols (or DPX_LONG_NOTABLE) use the byte-compare kernel instead of the score-table kernel."""
+def test_long_pair_byte_kernel_for_wide_alphabets(eng):
+    """More than four symbols (or the long_notable option) use the byte-compare kernel instead of the score-table kernel."""
     rng = synth.Rng(9)
     r = synth.random_seq(rng, 3000, b"01234"); q = synth.mutate(rng, r, 0.05, 0.01, 0.01, b"01234")[:2800]
     assert eng.align_long_pair(api.make_params(api.LSW), r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
-    monkeypatch.setenv("DPX_LONG_NOTABLE", "1")
-    r, q = _pair(4000, 5000, 31)
-    assert eng.align_long_pair(api.make_params(api.LSW), r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
+    with eng.options(long_notable=1):
+        r, q = _pair(4000, 5000, 31)
+        assert eng.align_long_pair(api.make_params(api.LSW), r, q) == ol.lsw_score_only(ol.params(ol.LSW), r, q)
 
 
 def test_long_pair_letters_and_odd_weights(eng):

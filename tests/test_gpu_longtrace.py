@@ -51,37 +51,37 @@ def test_strings_match_full_matrix_backtrack(eng, R, Q):
 
 
 @pytest.mark.parametrize("k", ["2", "4", "8", "16"])
-def test_every_tile_geometry_gives_the_same_strings(eng, k, monkeypatch):
-    """DPX_LONG_K forces the lane width, hence the checkpoint spacing: tiles of 64, 128, 256 and 512 rows and columns."""
-    monkeypatch.setenv("DPX_LONG_K", k)
-    r, q = _pair(5000, 6000, 77)
-    st = _check(eng, r, q, match=2, mismatch=-3, gap_open=-2)
-    assert st["tiles"] >= (5000 // (32 * int(k))) // 2
-    # gap-rich alignment: long horizontal and vertical runs across tile edges
-    rng = synth.Rng(5)
-    r = synth.random_seq(rng, 3000)
-    q = r[:700] + r[1100:2000] + synth.random_seq(rng, 300) + r[2000:]
-    _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
+def test_every_tile_geometry_gives_the_same_strings(eng, k):
+    """The long_k option forces the lane width, hence the checkpoint spacing: tiles of 64, 128, 256 and 512 rows and columns."""
+    with eng.options(long_k=int(k)):
+        r, q = _pair(5000, 6000, 77)
+        st = _check(eng, r, q, match=2, mismatch=-3, gap_open=-2)
+        assert st["tiles"] >= (5000 // (32 * int(k))) // 2
+        # gap-rich alignment: long horizontal and vertical runs across tile edges
+        rng = synth.Rng(5)
+        r = synth.random_seq(rng, 3000)
+        q = r[:700] + r[1100:2000] + synth.random_seq(rng, 300) + r[2000:]
+        _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
 
 
 @pytest.mark.parametrize("tiles_per_round", ["1", "2", "5"])
-def test_mispredicted_rounds_only_cost_rounds(eng, tiles_per_round, monkeypatch):
-    """The tiles ahead of the walk are predicted and filled in bulk; DPX_LONG_BT_TILES shrinks a round to a few tiles so that the
-    walk keeps stepping onto tiles nobody predicted (and, with long gaps, off the predicted diagonal)."""
-    monkeypatch.setenv("DPX_LONG_K", "2"); monkeypatch.setenv("DPX_LONG_BT_TILES", tiles_per_round)
-    rng = synth.Rng(15)
-    r = synth.random_seq(rng, 3000)
-    q = r[:500] + r[900:1500] + synth.random_seq(rng, 400) + r[1500:]
-    st = _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
-    assert st["rounds"] >= st["tiles"] // int(tiles_per_round)
-    r, q = _pair(2500, 2600, 16)
-    _check(eng, r, q)
+def test_mispredicted_rounds_only_cost_rounds(eng, tiles_per_round):
+    """The tiles ahead of the walk are predicted and filled in bulk; the long_bt_tiles option shrinks a round to a few tiles so that
+    the walk keeps stepping onto tiles nobody predicted (and, with long gaps, off the predicted diagonal)."""
+    with eng.options(long_k=2, long_bt_tiles=int(tiles_per_round)):
+        rng = synth.Rng(15)
+        r = synth.random_seq(rng, 3000)
+        q = r[:500] + r[900:1500] + synth.random_seq(rng, 400) + r[1500:]
+        st = _check(eng, r, q, match=3, mismatch=-4, gap_open=-1)
+        assert st["rounds"] >= st["tiles"] // int(tiles_per_round)
+        r, q = _pair(2500, 2600, 16)
+        _check(eng, r, q)
 
 
-def test_several_passes_with_checkpoints(eng, monkeypatch):
-    monkeypatch.setenv("DPX_LONG_K", "2"); monkeypatch.setenv("DPX_LONG_CAP", "8")
-    r, q = _pair(4000, 3500, 12)
-    _check(eng, r, q)
+def test_several_passes_with_checkpoints(eng):
+    with eng.options(long_k=2, long_cap=8):
+        r, q = _pair(4000, 3500, 12)
+        _check(eng, r, q)
 
 
 def test_ties_wide_alphabets_and_zero_score(eng):

@@ -66,12 +66,11 @@ def _worker(rank, world, port, out_path):
     job.free()
     # every lane width the stripes can take (the exported right edge must be the stripe's last REAL column)
     wide = []
-    for k in ("32", "16", "8", "2"):
-        os.environ["DPX_LONG_K"] = k
-        job = longpair.StripedLongPair(eng, api.make_params(api.LSW), ref, qry, rank, world, dist)
-        wide.append(job.run()[0])
-        job.free()
-    del os.environ["DPX_LONG_K"]
+    for k in (32, 16, 8, 2):
+        with eng.options(long_k=k):
+            job = longpair.StripedLongPair(eng, api.make_params(api.LSW), ref, qry, rank, world, dist)
+            wide.append(job.run()[0])
+            job.free()
     if rank == 0:
         np.savez(out_path, s=s, e=e, long1=np.array(res1), long2=np.array(res2), wide=np.array(wide))
     dist.barrier()

@@ -116,16 +116,16 @@ def test_out_of_range_batches_take_the_int32_variant_or_the_wavefront_kernel(eng
 
 
 @pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
-def test_int32_variant_on_the_small_cases(eng, algo, monkeypatch):
-    """DPX_PAIRWF_INT32 forces the one-pair-per-warp int32 instantiation of the same kernels onto inputs the packed one handles."""
-    monkeypatch.setenv("DPX_PAIRWF_INT32", "1")
-    blob, pairs = _ragged(21, 151, 1, 140)
-    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])
-    pp = [(b"", b""), (b"0123", b""), (b"", b"3210"), (b"0", b"0"), (b"0123012301", b"0123012301")]
-    rng = synth.Rng(4)
-    r = synth.random_seq(rng, 600); pp.append((r, synth.mutate(rng, r, 0.04, 0.02, 0.02)))
-    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
-    _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][1])
+def test_int32_variant_on_the_small_cases(eng, algo):
+    """The pairwf_int32 option forces the one-pair-per-warp int32 instantiation of the same kernels onto inputs the packed one handles."""
+    with eng.options(pairwf_int32=1):
+        blob, pairs = _ragged(21, 151, 1, 140)
+        _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][0])
+        pp = [(b"", b""), (b"0123", b""), (b"", b"3210"), (b"0", b"0"), (b"0123012301", b"0123012301")]
+        rng = synth.Rng(4)
+        r = synth.random_seq(rng, 600); pp.append((r, synth.mutate(rng, r, 0.04, 0.02, 0.02)))
+        blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+        _check(eng, algo, blob, pairs, KERNEL_PAIR_INT32, **WEIGHTS[algo][1])
 
 
 @pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])

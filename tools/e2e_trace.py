@@ -1,4 +1,4 @@
-"""Prints the host-side timeline of one dpx_align_batch call (DPX_TRACE=1) for the bench workload."""
+"""Prints the host-side timeline of one dpx_align_batch call (option "trace") for the bench workload."""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -11,11 +11,10 @@ eng = api.Engine(0); p = api.make_params(api.LSW, flags=3)
 def once():
     st = eng.L.dpx_align_batch(eng.ctx, C.byref(p), pb.numpy().ctypes.data, pb.numel(), pp.numpy().ctypes.data, n, sc.numpy().ctypes.data, rc.numpy().ctypes.data, None, None)
     assert st == 0
-os.environ.pop("DPX_TRACE", None)
 for _ in range(3): once()
 ts = []
 for _ in range(5):
     t0 = time.perf_counter(); once(); ts.append((time.perf_counter() - t0) * 1e3)
 print("ms per call:", [round(t, 2) for t in ts])
-os.environ["DPX_TRACE"] = "1"
+eng.set_option("trace", 1)
 once()

@@ -119,21 +119,20 @@ def main():
                 ref = blob[int(pr["referenceIdx"]): int(pr["referenceIdx"]) + int(pr["referenceSize"])].tobytes()
                 qry = blob[int(pr["queryIdx"]): int(pr["queryIdx"]) + int(pr["querySize"])].tobytes()
                 if len(ref) and len(qry):
-                    os.environ["DPX_LONG_K"] = str(int(rng.choice([0, 2, 4, 8, 16, 32])))
-                    os.environ["DPX_LONG_BT_TILES"] = str(int(rng.choice([0, 1, 3, 40])))
-                    os.environ["DPX_LONG_CAP"] = str(int(rng.choice([0, 0, 8, 16])))
-                    tag += f" long pair {k} env K={os.environ['DPX_LONG_K']} tiles={os.environ['DPX_LONG_BT_TILES']} cap={os.environ['DPX_LONG_CAP']}"
+                    lk, lt, lc = int(rng.choice([0, 2, 4, 8, 16, 32])), int(rng.choice([0, 1, 3, 40])), int(rng.choice([0, 0, 8, 16]))
+                    eng.set_option("long_k", lk); eng.set_option("long_bt_tiles", lt); eng.set_option("long_cap", lc)
+                    tag += f" long pair {k} options K={lk} tiles={lt} cap={lc}"
                     p1 = api.make_params(api.LSW, **w)
                     s1, e1, t1 = ol.align_batch(ol.params(algo, **w), blob, pairs[k:k + 1], strings=True)
                     want = (int(s1[0]), int(e1[0][0]), int(e1[0][1]))
                     assert eng.align_long_pair(p1, ref, qry) == want, "long pair score / end cell"
                     end, start, lines, st = eng.align_long_pair_strings(p1, ref, qry)
                     assert end == want and lines == t1[0], "long pair strings"
-                    for v in ("DPX_LONG_K", "DPX_LONG_BT_TILES", "DPX_LONG_CAP"):
-                        os.environ.pop(v, None)
+                    for v in ("long_k", "long_bt_tiles", "long_cap"):
+                        eng.set_option(v, 0)
         except (AssertionError, api.DpxError) as ex:       # keep going: one run should list every distinct failure
-            for v in ("DPX_LONG_K", "DPX_LONG_BT_TILES", "DPX_LONG_CAP"):
-                os.environ.pop(v, None)
+            for v in ("long_k", "long_bt_tiles", "long_cap"):
+                eng.set_option(v, 0)
             failures.append(f"{type(ex).__name__}: {ex} :: {tag}")
             print("FAIL", failures[-1], flush=True)
             if len(failures) >= 10:

@@ -4,8 +4,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from dpx_gpu_genomics_project_b200 import api, synth, longpair
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-os.environ["DPX_LONG_K"] = str(K)
 eng = api.Engine(0)
+eng.set_option("long_k", K)
 p = api.make_params(api.LSW)
 rng = synth.Rng(5)
 for nw in (1, 4, 148, 592, 1184, 2368):

@@ -10,7 +10,7 @@ p = api.make_params(api.LSW)
 rng = synth.Rng(5)
 ref = synth.random_seq(rng, R)
 for K in sys.argv[2].split(",") if len(sys.argv) > 2 else ["4"]:
-    os.environ["DPX_LONG_K"] = K
+    eng.set_option("long_k", int(K))
     row = []
     for Q in (25_000, 50_000, 100_000, 200_000, 400_000):
         qry = synth.random_seq(rng, Q)

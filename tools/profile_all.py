@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from dpx_gpu_genomics_project_b200 import api, synth
 eng = api.Engine(0)
 ALL = api.OUT_SCORE | api.OUT_END_COORDS | api.OUT_STRINGS
-os.environ["DPX_SERIAL_CHUNKS"] = "1"          # kernels one after the other: clean per-kernel captures
+eng.set_option("serial_chunks", 1)          # kernels one after the other: clean per-kernel captures
 # config 2: short-read kernel, 1M pairs
 blob, pairs = synth.uniform_blob_pairs(1_000_000, 150, 150, 0x5EED0002)
 b = eng.upload(blob, pairs)

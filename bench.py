@@ -21,7 +21,16 @@ collective, weak scaling); value = cells of all ranks / max-over-ranks device ti
             port, because the reference's banded class is not executable).
 
 `--config 5` is BASELINE configs[4]: ONE 1 Mbp x 1 Mbp LinearSmithWaterman pair, score + end cell; with N > 1 the pair is split into
-column stripes (strong scaling, see main_long).
+column stripes (strong scaling, see bench_long); its (score, row, col) is asserted against the full-size CPU pin tests/golden/cfg5_1m.json.
+
+Without --config the line is the headline (config 2, score + end cells) and carries, under "configs", the other things the metric names,
+measured the same way in the same run: config 2 score-only, config 3 (Gotoh + traceback: BASELINE's multi-GPU config), config 1, config 4
+and config 5 (striped over the N GPUs when N > 1) -- so that the one command the driver runs records score-only, traceback and
+long-pair numbers at every N.  `--config K` runs that config alone.
+
+Inputs go through the library's own parser (dpx_parse_image), like a user's file would: the parser leaves a packed 2-bit copy in
+page-locked memory (include/dpxalign.h "Packed sidecar"; the reference's timer also starts after parseInput, c++/main.cpp:157-164), and
+both the resident batch behind `value` and the one-call `e2e` upload that copy -- 0.25 B per base over PCIe instead of 1.
 
 `--impl reference` times that CPU path alone (rank 0 only) and prints the same line shape.
 """
@@ -201,18 +210,92 @@ def cpu_sample_size(wl, n_pairs, cores, seconds=12.0):
     return int(max(min(n_pairs, 2 * cores), min(n_pairs, wl["cpu_per_core"] * cores * seconds / cells_per_pair)))
 
 
-def main_long(args):
-    """--config 5: one step = one alignment of the 1 Mbp x 1 Mbp pair.  N > 1: the reference columns are split into one stripe per
+
+
+def ragged_uniform_blob_pairs(n_pairs, lo, hi, seed):
+    """Independent random pairs with R, Q ~ U[lo, hi] (score-only throughput is data-independent): parseInput-form blob + index."""
+    from dpx_gpu_genomics_project_b200 import synth
+    rng = synth.Rng(seed)
+    R = lo + rng.below(n_pairs, hi - lo + 1); Q = lo + rng.below(n_pairs, hi - lo + 1)
+    rec = 2 + R + 1 + Q + 1
+    off = np.zeros(n_pairs + 1, dtype=np.int64); np.cumsum(rec, out=off[1:])
+    total = int(off[-1])
+    words = synth.splitmix64(seed ^ 0xABCDEF, (total + 31) // 32)
+    sh = np.arange(0, 64, 2, dtype=np.uint64)
+    blob = (((words[:, None] >> sh[None, :]) & np.uint64(3)).astype(np.uint8).reshape(-1)[:total] + np.uint8(ord("0")))
+    o = off[:-1]
+    blob[o] = ord("0"); blob[o + 1] = 0; blob[o + 2 + R] = 0; blob[o + rec - 1] = 0
+    pairs = np.zeros(n_pairs, dtype=[("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
+    pairs["referenceIdx"] = o + 2; pairs["referenceSize"] = R; pairs["queryIdx"] = o + 3 + R; pairs["querySize"] = Q
+    return blob, pairs
+
+
+_INPUT_CACHE = {}
+
+
+class Run:
+    """Per-process state shared by every config of one bench invocation."""
+
+    def __init__(self, args):
+        import torch
+        from dpx_gpu_genomics_project_b200 import api
+        self.torch, self.api, self.args = torch, api, args
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        self.cores = os.cpu_count() or 1
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: libdpxalign has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group(backend="nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        self.eng = api.Engine(self.local)
+        # host thread next to this GPU's PCIe root before any page-locked buffer exists (parser sidecar, result buffers)
+        self.numa_cpus = self.eng.L.dpx_bind_host_to_device(self.local)
+        self.stream = torch.cuda.Stream()                 # a real (non-default) stream shared by torch events and the library
+        torch.cuda.set_stream(self.stream)
+        self.eng.set_stream(self.stream.cuda_stream)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        self.sms = torch.cuda.get_device_properties(self.local).multi_processor_count
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, vals):
+        if self.dist is None:
+            return [float(v) for v in vals]
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def close(self):
+        self.eng.close()
+        if self.dist is not None:
+            self.dist.destroy_process_group()
+
+
+def golden_cfg5():
+    try:
+        return json.load(open(os.path.join(ROOT, "tests", "golden", "cfg5_1m.json")))
+    except Exception:
+        return None
+
+
+def bench_long(C, steps, warmup, with_cpu):
+    """config 5: one step = one alignment of the 1 Mbp x 1 Mbp pair.  N > 1: the reference columns are split into one stripe per
     GPU (multi-GPU mode B, the right edge of a stripe streams to the next GPU by NVLink P2P stores): total work is fixed, so
     scaling is "strong".  value = R*Q / max-over-ranks kernel time (CUDA events inside the library, sequences resident);
     e2e = the host-buffer call (N = 1: dpx_align_long_pair, H2D of both sequences + kernel + D2H of the result;
     N > 1: reset + barrier + run + gather of the per-stripe results, sequences resident since stripe creation)."""
     import oracle_lib as ol
-    from dpx_gpu_genomics_project_b200 import synth
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    cores = os.cpu_count() or 1
+    from dpx_gpu_genomics_project_b200 import synth, longpair
+    args, api, torch = C.args, C.api, C.torch
+    rank, world = C.rank, C.world
     R, Q, w = LONG["R"], LONG["Q"], LONG["weights"]
-    if args.pairs:                                            # --pairs N shrinks the pair to N x N bases (smoke runs)
+    if args.config == 5 and args.pairs:                       # --config 5 --pairs N shrinks the pair to N x N bases (smoke runs)
         R = Q = args.pairs
 
     def make_pair(r_len, q_len):
@@ -221,49 +304,20 @@ def main_long(args):
 
     config = {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp (query = reference mutated 1 % / 0.1 % / 0.1 %), score + end cell, "
                           "match 3 / mismatch -1 / gap -2", "baseline_config": 5, "R": R, "Q": Q,
-              "sharding": f"{max(args.gpus, world)} column stripe(s), right edges streamed GPU to GPU over NVLink P2P (no NCCL on the data path)",
+              "sharding": f"{world} column stripe(s), right edges streamed GPU to GPU over NVLink P2P (no NCCL on the data path)",
               "l2": "256 MiB memset between timed steps", "seed": f"{LONG['seed']:#x}"}
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        n = min(LONG["cpu_sample"], R)
-        ref, qry = make_pair(n, n)
-        secs = []
-        for _ in range(max(1, min(args.steps, 2))):
-            t0 = time.perf_counter(); ol.lsw_score_only(ol.params(ol.LSW, **w), ref, qry); secs.append(time.perf_counter() - t0)
-        v = n * n / float(np.mean(secs)) / 1e9
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": max(args.gpus, world), "steps": len(secs), "warmup": 0,
-            "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": 1, "kind": "port",
-                             "sample": f"a {n} x {n} bp pair of the same generator; rolling-row C port of LinearSmithWaterman (the reference's "
-                                       "full-matrix class needs 8 B per cell: 8 TB at 1 Mbp x 1 Mbp), 1 thread"},
-            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
-        return
-
-    import torch
-    from dpx_gpu_genomics_project_b200 import api, longpair
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libdpxalign has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
     ref, qry = make_pair(R, Q)
-    eng = api.Engine(local)
+    eng = C.eng
     params = api.make_params(api.LSW, **w)
-    job = longpair.StripedLongPair(eng, params, ref, qry, rank, world, dist)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    steps = min(args.steps, 10)
-    for _ in range(args.warmup):
+    job = longpair.StripedLongPair(eng, params, ref, qry, rank, world, C.dist)
+    steps = max(1, min(steps, 10))
+    for _ in range(warmup):
         res, _ = job.run()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(C.local)
     sampler.start()
     ms_steps, wall = [], []
     for _ in range(steps):
-        flush.zero_(); torch.cuda.synchronize()
+        C.flush.zero_(); torch.cuda.synchronize()
         t0 = time.perf_counter()
         res, ms = job.run()                                   # barrier inside; ms = max over ranks of the stripes' kernel times
         wall.append(time.perf_counter() - t0); ms_steps.append(ms)
@@ -273,16 +327,15 @@ def main_long(args):
     if world == 1:                                            # the host-buffer call of the ABI
         eng.align_long_pair(params, ref, qry)
         t0 = time.perf_counter()
-        for _ in range(3):
+        for _ in range(2):
             res1 = eng.align_long_pair(params, ref, qry)
-        e2e_s = (time.perf_counter() - t0) / 3
+        e2e_s = (time.perf_counter() - t0) / 2
         assert tuple(res1) == tuple(res), "one-call and striped paths disagree"
         h2d = R + Q
+    stripe_k = getattr(job, "lane_width", None)
     job.free()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+        return None
     ms_per_step = float(np.mean(ms_steps))
     cells = float(R) * float(Q)
     value = cells / (ms_per_step * 1e-3) / 1e9
@@ -291,20 +344,25 @@ def main_long(args):
     f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
     roofline = {"bound": "dpx_issue", "achieved": value, "unit": "GCUPS", "kernel": LONG["kernel"], "traffic": None, "kernel_ms": ms_per_step}
     alu_pc, issue_pc = sass_counts(LONG["sass"])
-    if alu_pc and world == 1 and R >= 600_000:                # the lane width (hence the SASS loop) is K = 32 only for one wide stripe
-        sms = torch.cuda.get_device_properties(local).multi_processor_count
-        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * sms * f_mhz * 1e6 / 1e9
+    if alu_pc:
+        # the steady loop's instruction mix is the same at every lane width the table kernels use; the roof is the whole machine's
+        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * C.sms * world * f_mhz * 1e6 / 1e9
         roofline.update({"peak": peak, "frac": value / peak,
-                         "model": {"alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "sms": sms, "sm_mhz": f_mhz, "sass_key": LONG["sass"],
-                                   "note": "a chain of 977 warps (1.65 per SM sub-partition), each row step a dependent chain: latency-bound below the issue roofline"}})
-    out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                         "model": {"alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "sms": C.sms, "gpus": world, "sm_mhz": f_mhz, "sass_key": LONG["sass"],
+                                   "note": "a systolic chain of warps, each row step a dependent chain: latency- and fill-bound below the issue roofline"}})
+    out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
            "clocks": clocks, "result": list(res),
            "e2e": {"value": cells / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 20 * world, "ms_per_step": e2e_s * 1e3,
                    "api": "dpx_align_long_pair (C ABI), host sequences in, (score, row, col) out" if world == 1 else
                           "dpx_stripe_reset + barrier + dpx_stripe_run + gather of the per-stripe results; sequences resident since dpx_stripe_create"},
-           "gpu_launches": steps * 1, "roofline": roofline}
-    if not args.no_cpu_baseline and world == 1:
+           "gpu_launches": steps * world, "roofline": roofline}
+    g = golden_cfg5()
+    if g and (g["R"], g["Q"]) == (R, Q):
+        out["golden"] = {"file": "tests/golden/cfg5_1m.json", "want": [g["score"], g["end_row"], g["end_col"]],
+                         "oracle": g["oracle"], "match": list(res) == [g["score"], g["end_row"], g["end_col"]]}
+        assert out["golden"]["match"], f"config 5 result {list(res)} differs from the full-size CPU pin {out['golden']['want']}"
+    if with_cpu and world == 1:
         n = min(LONG["cpu_sample"], R)
         r2, q2 = make_pair(n, n)
         t0 = time.perf_counter(); want = ol.lsw_score_only(ol.params(ol.LSW, **w), r2, q2); dt = time.perf_counter() - t0
@@ -313,10 +371,329 @@ def main_long(args):
         out["cpu_baseline"] = {"value": n * n / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port", "seconds": dt,
                                "sample": f"a {n} x {n} bp pair of the same generator, rolling-row C port (the reference's full-matrix class cannot "
                                          "allocate this problem), 1 thread; also the parity check of the GPU result at that size"}
-    print(json.dumps(out))
-    eng.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    return out
+
+
+def reference_long(args):
+    import oracle_lib as ol
+    from dpx_gpu_genomics_project_b200 import synth
+    R, Q, w = LONG["R"], LONG["Q"], LONG["weights"]
+    n = min(LONG["cpu_sample"], args.pairs or R)
+    img = synth.mutated_fixed_file_bytes(1, n, n, LONG["seed"], *LONG["mutate"])
+    ref, qry = img[2:2 + n].tobytes(), img[3 + n:3 + n + n].tobytes()
+    secs = []
+    for _ in range(max(1, min(args.steps, 2))):
+        t0 = time.perf_counter(); ol.lsw_score_only(ol.params(ol.LSW, **w), ref, qry); secs.append(time.perf_counter() - t0)
+    v = n * n / float(np.mean(secs)) / 1e9
+    config = {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp, score + end cell", "baseline_config": 5, "R": R, "Q": Q}
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": max(args.gpus, env_int("WORLD_SIZE", 1)), "steps": len(secs), "warmup": 0,
+        "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": 1, "kind": "port",
+                         "sample": f"a {n} x {n} bp pair of the same generator; rolling-row C port of LinearSmithWaterman (the reference's "
+                                   "full-matrix class needs 8 B per cell: 8 TB at 1 Mbp x 1 Mbp), 1 thread"},
+        "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def bench_batched(C, cfg_no, steps, warmup, score_only=False, n_pairs=0, with_cpu=True, cpu_seconds=12.0, extras=False, gen_override=None, label=None):
+    """One batched config (1-4) on this rank's shard; returns the bench line as a dict on rank 0, None elsewhere.  All ranks must call it."""
+    import ctypes as Ct
+    import oracle_lib as ol
+    from dpx_gpu_genomics_project_b200 import synth
+    args, api, torch, eng = C.args, C.api, C.torch, C.eng
+    rank, world = C.rank, C.world
+    wl = dict(WORKLOADS[cfg_no])
+    if gen_override:
+        wl["gen"] = gen_override
+    n_pairs = n_pairs or wl["pairs"]
+    want_strings = wl["strings"] and not score_only
+    ends = "" if (cfg_no == 2 and score_only) else (" + end coords" if cfg_no == 2 else "")
+    config = {"workload": (label or wl["title"]).format(pairs=n_pairs, ends=ends) + ("" if want_strings or not wl["strings"] else " [score only]"),
+              "baseline_config": cfg_no, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
+              "sharding": f"independent pairs x{world} (no collective)", "l2": "256 MiB memset between timed steps",
+              "seed": f"{wl['seed']:#x} + rank", "input": "file image -> dpx_parse_image (blob, index, packed 2-bit sidecar in page-locked memory)"}
+
+    key = (cfg_no, str(wl["gen"]), n_pairs, wl["seed"] + rank)
+    if _INPUT_CACHE.get("key") != key:                      # the score-only variant of a config reuses the input just generated
+        _INPUT_CACHE.clear()
+        if wl["gen"][0] == "ragged_uniform":
+            _INPUT_CACHE["val"] = ragged_uniform_blob_pairs(n_pairs, wl["gen"][1], wl["gen"][2], wl["seed"] + rank)
+        else:
+            _INPUT_CACHE["val"] = make_inputs(wl, n_pairs, wl["seed"] + rank)
+        _INPUT_CACHE["key"] = key
+    blob, pairs = _INPUT_CACHE["val"]
+    img = synth.blob_to_file_bytes(blob)
+    raw_blob = blob if extras else None
+    raw_pairs = pairs if extras else None
+    inp = api.parse_image_native(img)
+    del img, blob
+    assert inp.info["numPairs"] == n_pairs and (inp.pairs == pairs).all()
+    blob, pairs = inp.sequences, inp.pairs
+    side = api.input_sidecar(blob)
+    cells = total_cells(wl, pairs)
+    algo = {"LNW": api.LNW, "ANW": api.ANW, "LSW": api.LSW, "BSW": api.BSW}[wl["algo"]]
+    if cfg_no == 2:
+        flags = api.OUT_SCORE | (0 if score_only else api.OUT_END_COORDS)
+    else:
+        flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if want_strings else 0)
+    params = api.make_params(algo, flags=flags, **wl["weights"])
+
+    stream = C.stream
+    batch = eng.upload(blob, pairs)                      # resident in HBM (packed words from the sidecar) before the timed region
+    for _ in range(warmup):
+        batch.run(params)
+    batch.sync()
+    launches_per_step = int(batch.stats()["kernel_launches"])
+
+    sampler = ClockSampler(C.local)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    C.barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(steps):
+        C.flush.zero_()                                  # L2 flush, outside the per-step event bracket
+        ev[k][0].record(stream)
+        batch.run(params)
+        ev[k][1].record(stream)
+    C.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag.set(); sampler.join(timeout=1.0)
+    ms_total = float(sum(a.elapsed_time(b) for a, b in ev))
+    batch.sync()
+    st_last = batch.stats()
+    tb_bytes = float(st_last["traceback_bytes"])
+    # The dominant kernel timed ALONE (library's own event pairs): traceback runs pipeline their chunks (fill of chunk c+1 next to
+    # the walk of chunk c, on separate streams), so for the roofline the same step is repeated with the chunks serialised.
+    if want_strings:
+        eng.set_option("serial_chunks", 1)
+        for _ in range(2):
+            C.flush.zero_(); batch.run(params)
+        batch.sync()
+        st_last = batch.stats()
+        eng.set_option("serial_chunks", 0)
+        batch.run(params); batch.sync()                  # back to the pipelined slab layout before the fetch
+    fill_ms = float(st_last["fill_ms"])
+    bt_ms = float(st_last["backtrack_ms"])
+    res = batch.fetch() if not want_strings else None
+    batch.free()
+
+    # ---- e2e: the one-call ABI on the parser's host buffers, H2D + D2H inside ------------------------------------
+    n_chk = 2000 if cfg_no in (1, 2) else (64 if cfg_no == 3 else 8)
+    oalgo = {"LNW": ol.LNW, "ANW": ol.ANW, "LSW": ol.LSW, "BSW": ol.BSW}[wl["algo"]]
+    e2e_steps = max(2, min(5 if cfg_no in (1, 2) else 3, steps))
+    out_scores = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
+    out_rc = torch.empty((n_pairs, 2), dtype=torch.int32).pin_memory()
+    L = eng.L
+    e2e_first_strings = []
+
+    def e2e_once(seq, idx, keep=False):
+        sb, so = Ct.c_void_p(), Ct.c_void_p()
+        st = L.dpx_align_batch(eng.ctx, Ct.byref(params), seq.ctypes.data, seq.size, idx.ctypes.data, n_pairs,
+                               out_scores.numpy().ctypes.data, out_rc.numpy().ctypes.data,
+                               Ct.byref(sb) if want_strings else None, Ct.byref(so) if want_strings else None)
+        if st != 0:
+            raise RuntimeError(f"dpx_align_batch failed: {st} {L.dpx_last_error(eng.ctx)}")
+        if want_strings:
+            if keep:
+                last = int(np.frombuffer(Ct.string_at(so.value + (3 * n_pairs - 1) * 8, 8), dtype=np.uint64)[0])
+                e2e_first_strings.append(last + len(Ct.string_at(sb.value + last)) + 1)      # size of the compacted blob
+                offs = np.frombuffer(Ct.string_at(so, 3 * n_chk * 8), dtype=np.uint64)
+                for i in range(n_chk):
+                    e2e_first_strings.append(tuple(Ct.string_at(sb.value + int(offs[3 * i + k])) for k in range(3)))
+            L.dpx_free(sb); L.dpx_free(so)
+
+    def time_e2e(seq, idx, n):
+        C.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            e2e_once(seq, idx)
+        C.barrier()
+        return (time.perf_counter() - t0) / n
+
+    e2e_once(blob, pairs, keep=True)
+    str_bytes = e2e_first_strings.pop(0) if want_strings else 0      # what actually crosses PCIe: the compacted strings
+    e2e_s = time_e2e(blob, pairs, e2e_steps)
+    if res is not None:
+        assert (out_scores.numpy() == res.scores).all(), "e2e and staged paths disagree"
+    h2d_bytes = int(side["upload_bytes"]) if side else int(blob.size + n_pairs * 16)
+    scores_chk = out_scores.numpy()[:n_chk].copy(); rc_chk = out_rc.numpy()[:n_chk].copy()
+
+    # ---- extras (headline only): the round-1 route (raw bytes from page-locked buffers, no sidecar) and a bare copy for scale
+    e2e_raw = None
+    if extras:
+        pin_blob = torch.from_numpy(np.ascontiguousarray(raw_blob)).pin_memory()
+        pin_pairs = torch.from_numpy(np.ascontiguousarray(raw_pairs).view(np.int32)).pin_memory()
+        rb, rp = pin_blob.numpy(), pin_pairs.numpy().view(api.PAIR_DTYPE)
+        e2e_once(rb, rp)
+        raw_s = time_e2e(rb, rp, max(2, e2e_steps - 2))
+        assert (out_scores.numpy()[:n_chk] == scores_chk).all(), "raw-byte and sidecar uploads disagree"
+        dev = torch.empty(max(pin_blob.numel(), 1), dtype=torch.uint8, device="cuda")
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dev.copy_(pin_blob, non_blocking=True); torch.cuda.synchronize()
+        c0.record(stream); dev.copy_(pin_blob, non_blocking=True); c1.record(stream); torch.cuda.synchronize()
+        h2d_ms = c0.elapsed_time(c1)
+        raw_s = C.max_over_ranks([raw_s])[0]
+        e2e_raw = {"value": cells * world / raw_s / 1e9, "unit": "GCUPS", "ms_per_step": raw_s * 1e3, "h2d_bytes_per_step": int(pin_blob.numel() + pin_pairs.numel() * 4),
+                   "api": "dpx_align_batch on an UNREGISTERED page-locked copy of the same blob + index (1 byte per base over PCIe, packed on the device): the round-1 route",
+                   "bare_h2d_copy_ms": h2d_ms, "bare_h2d_gbs": pin_blob.numel() / (h2d_ms * 1e-3) / 1e9}
+        del dev, pin_blob, pin_pairs
+
+    ms_total, e2e_s, fill_ms, bt_ms = C.max_over_ranks([ms_total, e2e_s, fill_ms, bt_ms])
+    ms_per_step = ms_total / steps
+    value = cells * world / (ms_per_step * 1e-3) / 1e9
+    e2e_value = cells * world / e2e_s / 1e9
+    if rank != 0:
+        inp.free()
+        return None
+
+    # ---- parity spot check against the oracle (outside every timed region) --------------------------------
+    s_ref, e_ref, t_ref = ol.align_batch(ol.params(oalgo, **wl["weights"]), blob, pairs[:n_chk], strings=want_strings, threads=min(C.cores, 16))
+    parity_ok = bool((scores_chk == s_ref).all())
+    if wl["algo"] in ("LSW", "BSW") and not (cfg_no == 2 and score_only):
+        parity_ok = parity_ok and bool((rc_chk == e_ref).all())
+    if want_strings:
+        parity_ok = parity_ok and e2e_first_strings == t_ref
+
+    # ---- roofline ---------------------------------------------------------------------------------------
+    clocks = sampler.result()
+    peaks, peaks_src = measured_peaks()
+    f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+    sass_key = wl["sass"].format(track=not score_only)
+    if cfg_no != 2 and not want_strings:
+        sass_key = sass_key.replace("traceback=True", "traceback=False")
+    alu_pc, issue_pc = sass_counts(sass_key)
+    kern_ms = fill_ms if fill_ms > 0 else ms_per_step          # the dominant kernel = the fill kernel(s) of one step
+    kernel_gcups = cells / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "dpx_issue", "achieved": kernel_gcups, "unit": "GCUPS", "kernel": wl["kernel"].split(" (+")[0], "traffic": None,
+                "kernel_ms": kern_ms}
+    if alu_pc:
+        # real cells only: slots a kernel spends on padding (config 4: 129 diagonals on 160 slots; ragged duos) count against frac
+        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * C.sms * f_mhz * 1e6 / 1e9
+        roofline.update({"peak": peak, "frac": kernel_gcups / peak,
+                         "model": {"alu_pipe_lanes_per_clk_per_sm": 64, "issue_lanes_per_clk_per_sm": 128,
+                                   "alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc,
+                                   "sms": C.sms, "sm_mhz": f_mhz, "sass_key": sass_key,
+                                   "source": "profiles/sass_counts.json (the kernel's own SASS hot loop) + profiles/r02_dpx_microbench.json"}})
+        if cfg_no == 2:
+            floor = 1.5                                  # PRMT + 2 packed DPX per cell pair: the least this recurrence can issue on the ALU pipe
+            roofline["frac_of_floor_roof"] = kernel_gcups / (64.0 / floor * C.sms * f_mhz * 1e6 / 1e9)
+            roofline["model"]["alu_floor_instr_per_cell"] = floor
+    if cfg_no == 2:
+        algo_bytes = n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 16 + 8 + 12)     # 2-bit bases + the index entry + 12 B of results per pair
+    else:
+        # HBM view: the packed traceback stream (0.5 B/cell Gotoh, 0.25 B/cell linear / banded) written once by the fill kernel
+        algo_bytes = cells * wl["tb_bytes_per_cell"] if want_strings else n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 28)
+    if cfg_no == 1:
+        roofline["note"] = "ragged duos: a warp sweeps max(Q) x max(R) of its two pairs, so only part of its cell slots hold real cells"
+    hbm_ach = algo_bytes / (kern_ms * 1e-3) / 1e9
+    roofline["hbm"] = {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
+                       "peak_source": f"MEASURED_PEAKS.json ({peaks_src})", "algorithmic_bytes_per_launch": algo_bytes,
+                       "slab_bytes_written": tb_bytes if want_strings else None}
+    for tr_file in ("r02_traffic.json", "r01_traffic.json"):   # DRAM traffic of the dominant kernel, from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", tr_file)))[str(cfg_no)]
+            if want_strings or cfg_no == 2:
+                per_launch = tr["dram_bytes_per_pair"] * n_pairs if "dram_bytes_per_pair" in tr else tr["dram_bytes_per_cell"] * cells
+                roofline["traffic"] = per_launch
+                roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, scaled from the capture's size)"
+                roofline["traffic_source"] = tr["source"]
+            break
+        except Exception:
+            continue
+    d2h = n_pairs * 12 + str_bytes + (3 * 8 * n_pairs if want_strings else 0)
+    out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": wl["dtype"], "data": "synthetic", "config": config, "clocks": clocks,
+           "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": h2d_bytes,
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                   "api": "dpx_align_batch (C ABI) on the blob + index dpx_parse_image returned" + (", library-allocated string blob" if want_strings else ""),
+                   "h2d_note": "bytes the call moves over PCIe: the parser's packed 2-bit copy of the sequences (page-locked)" +
+                               (" -- nothing else, the lengths are uniform" if side and side["uniform"] else " + 8 B per pair of sizes / word offsets") if side else
+                               "raw blob + index (more than four symbols: no packed copy)",
+                   "raw_blob_bytes": int(blob.size), "sidecar": bool(side), "host_numa_cpus": C.numa_cpus},
+           "gpu_launches": launches_per_step * steps, "roofline": roofline,
+           "fill_ms_serialised": fill_ms, "backtrack_ms_serialised": bt_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}
+    if e2e_raw:
+        out["e2e_raw_bytes"] = e2e_raw
+    if with_cpu and world == 1:
+        n_s = cpu_sample_size(wl, n_pairs, C.cores, seconds=cpu_seconds)
+        v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, C.cores)
+        out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": C.cores, "kind": kind, "seconds": dt,
+                               "sample": f"first {n_s} pairs of the same workload, {C.cores} host threads, align loop only"}
+    inp.free()
+    return out
+
+
+def reference_batched(args, cfg_no):
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    wl = dict(WORKLOADS[cfg_no])
+    n_pairs = args.pairs or wl["pairs"]
+    ends = "" if (cfg_no == 2 and args.score_only) else (" + end coords" if cfg_no == 2 else "")
+    config = {"workload": wl["title"].format(pairs=n_pairs, ends=ends), "baseline_config": cfg_no, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
+              "sharding": f"independent pairs x{max(args.gpus, world)} (no collective)", "seed": f"{wl['seed']:#x} + rank"}
+    n_s = cpu_sample_size(wl, n_pairs, cores, seconds=8.0)
+    blob, pairs = make_inputs(wl, n_s, wl["seed"])
+    vals, secs = [], []
+    run_cpu_reference(wl, blob, pairs, max(2, n_s // 8), cores)       # warm-up
+    kind = "reference"
+    for _ in range(max(1, args.steps if args.steps <= 5 else 3)):
+        v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, cores)
+        vals.append(v); secs.append(dt)
+    v = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": max(args.gpus, world), "steps": len(vals),
+        "warmup": 1, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind,
+                         "sample": f"first {n_s} pairs of the workload per step, {cores} host threads"},
+        "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def bench_multi_abi(C, steps=3):
+    """Rank 0 only, N > 1: config 2 (score + end cells) through dpx_multi_align_batch -- ONE host process, one worker thread and
+    context per GPU, world x 1M pairs in one call (the other ranks wait at the barrier, their GPUs idle)."""
+    import ctypes as Ct
+    from dpx_gpu_genomics_project_b200 import synth
+    api, torch = C.api, C.torch
+    wl = WORKLOADS[2]
+    out = None
+    store = C.dist.distributed_c10d._get_default_store()     # the other ranks block on the CPU: no NCCL kernel spinning on their GPUs
+    if C.rank != 0:
+        store.wait(["dpx_multi_abi_done"])
+    if C.rank == 0:
+        n = wl["pairs"] * C.world
+        inp = api.parse_image_native(np.tile(synth.uniform_file_bytes(wl["pairs"], wl["R"], wl["Q"], wl["seed"] + 77), C.world))
+        m = api.MultiEngine(n_devices=C.world)
+        params = api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS, **wl["weights"])
+        sc = torch.empty(n, dtype=torch.int32).pin_memory(); rc = torch.empty((n, 2), dtype=torch.int32).pin_memory()
+
+        def once():
+            st = m.L.dpx_multi_align_batch(m.h, Ct.byref(params), inp.sequences.ctypes.data, inp.sequences.size, inp.pairs.ctypes.data, n,
+                                           sc.numpy().ctypes.data, rc.numpy().ctypes.data, None, None)
+            if st:
+                raise RuntimeError(m.L.dpx_multi_last_error(m.h))
+        once(); once()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            once()
+        dt = (time.perf_counter() - t0) / steps
+        cells = float(n) * wl["R"] * wl["Q"]
+        side = api.input_sidecar(inp.sequences)
+        # same pairs through one device: identical bytes (multi-GPU invariance)
+        one = C.eng.align_batch(params, inp.sequences, inp.pairs[:200_000])
+        same = bool((one.scores == sc.numpy()[:200_000]).all() and (one.end_row_col == rc.numpy()[:200_000]).all())
+        out = {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "pairs": n, "devices": C.world, "h2d_bytes_per_step": int(side["upload_bytes"]),
+               "d2h_bytes_per_step": 12 * n, "api": "dpx_multi_align_batch (C ABI): one host process, one worker thread + context per GPU, contiguous shards",
+               "identical_to_one_gpu": same}
+        m.close(); inp.free()
+        store.set("dpx_multi_abi_done", "1")
+    C.barrier()
+    return out
 
 
 def main():
@@ -325,270 +702,49 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dpx", choices=["dpx", "reference"])
-    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS) + [5], help="BASELINE.json config number (SURVEY.md §8d)")
+    ap.add_argument("--config", type=int, default=0, choices=[0] + sorted(WORKLOADS) + [5],
+                    help="BASELINE.json config number (SURVEY.md §8d); 0 (default) = headline config 2 + every other config under \"configs\"")
     ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU (default: the config's own size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-headline", action="store_true", help="default run without the \"configs\" block")
     ap.add_argument("--score-only", action="store_true", help="config 2: omit end coordinates; configs 3/4: no traceback / strings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "dpx":
         args.warmup = 3
-    if args.config == 5:
-        return main_long(args)
-    wl = dict(WORKLOADS[args.config])
-    n_pairs = args.pairs or wl["pairs"]
-    want_strings = wl["strings"] and not args.score_only
-    if args.config != 2 and args.steps > 10 and args.impl == "dpx":
-        args.steps = 10                                       # traceback configs: ~10-60 ms per step plus the strings download in e2e
-
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    n_gpus = max(args.gpus, world)
-    cores = os.cpu_count() or 1
-
-    ends = "" if (args.config == 2 and args.score_only) else (" + end coords" if args.config == 2 else "")
-    config = {"workload": wl["title"].format(pairs=n_pairs, ends=ends) + ("" if want_strings or not wl["strings"] else " [score only]"),
-              "baseline_config": args.config, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
-              "sharding": f"independent pairs x{n_gpus} (no collective)", "l2": "256 MiB memset between timed steps",
-              "seed": f"{wl['seed']:#x} + rank"}
-
-    # ---------------------------------------------------------------------------------------------------
     if args.impl == "reference":
-        if rank != 0:
+        if env_int("RANK", 0) != 0:
             return
-        n_s = cpu_sample_size(wl, n_pairs, cores, seconds=8.0)
-        blob, pairs = make_inputs(wl, n_s, wl["seed"])
-        vals, secs = [], []
-        run_cpu_reference(wl, blob, pairs, max(2, n_s // 8), cores)       # warm-up
-        kind = "reference"
-        for _ in range(max(1, args.steps if args.steps <= 5 else 3)):
-            v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, cores)
-            vals.append(v); secs.append(dt)
-        v = float(np.mean(vals))
-        print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": n_gpus, "steps": len(vals),
-            "warmup": 1, "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind,
-                             "sample": f"first {n_s} pairs of the workload per step, {cores} host threads"},
-            "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
-        return
+        return reference_long(args) if args.config == 5 else reference_batched(args, args.config or 2)
 
-    # ---------------------------------------------------------------------------------------------------
-    import torch
-    from dpx_gpu_genomics_project_b200 import api
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: libdpxalign has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
-
-    blob, pairs = make_inputs(wl, n_pairs, wl["seed"] + rank)
-    cells = total_cells(wl, pairs)
-    algo = {"LNW": api.LNW, "ANW": api.ANW, "LSW": api.LSW, "BSW": api.BSW}[wl["algo"]]
-    if args.config == 2:
-        flags = api.OUT_SCORE | (0 if args.score_only else api.OUT_END_COORDS)
+    C = Run(args)
+    with_cpu = not args.no_cpu_baseline
+    if args.config == 5:
+        out = bench_long(C, args.steps, min(args.warmup, 3), with_cpu)
+    elif args.config:
+        steps = args.steps if args.config == 2 else min(args.steps, 10)     # traceback configs: ~10-60 ms per step plus the strings download in e2e
+        out = bench_batched(C, args.config, steps, args.warmup, score_only=args.score_only, n_pairs=args.pairs, with_cpu=with_cpu, extras=(args.config == 2))
     else:
-        flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if want_strings else 0)
-    params = api.make_params(algo, flags=flags, **wl["weights"])
-
-    eng = api.Engine(local)
-    stream = torch.cuda.Stream()                         # a real (non-default) stream shared by torch events and the library
-    torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
-    batch = eng.upload(blob, pairs)                      # resident + packed in HBM before the timed region
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        batch.run(params)
-    batch.sync()
-    st0 = batch.stats()
-    launches_per_step = int(st0["kernel_launches"])
-
-    sampler = ClockSampler(local)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    sampler.start()
-    t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush.zero_()                                    # L2 flush, outside the per-step event bracket
-        ev[k][0].record(stream)
-        batch.run(params)
-        ev[k][1].record(stream)
-    barrier()
-    t_wall = time.perf_counter() - t_wall0
-    sampler.stop_flag.set(); sampler.join(timeout=1.0)
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    ms_total = float(sum(ms_steps))
-    batch.sync()
-    st_last = batch.stats()
-    tb_bytes = float(st_last["traceback_bytes"])
-    # The dominant kernel timed ALONE (library's own event pairs): traceback runs pipeline their chunks (fill of chunk c+1 next to
-    # the walk of chunk c, on separate streams), so for the roofline the same step is repeated with the chunks serialised.
-    if want_strings:
-        os.environ["DPX_SERIAL_CHUNKS"] = "1"
-        for _ in range(2):
-            flush.zero_(); batch.run(params)
-        batch.sync()
-        st_last = batch.stats()
-        del os.environ["DPX_SERIAL_CHUNKS"]
-        batch.run(params); batch.sync()                  # back to the pipelined slab layout before the fetch
-    fill_ms = float(st_last["fill_ms"])
-    bt_ms = float(st_last["backtrack_ms"])
-
-    # result check of the timed configuration on a sample (outside the timed region)
-    import oracle_lib as ol
-    n_chk = 2000 if args.config in (1, 2) else (64 if args.config == 3 else 8)
-    res = batch.fetch() if not want_strings else None
-    oalgo = {"LNW": ol.LNW, "ANW": ol.ANW, "LSW": ol.LSW, "BSW": ol.BSW}[wl["algo"]]
-
-    # ---- e2e: one-call ABI, pinned host buffers, H2D + D2H inside ------------------------------------------
-    e2e_steps = max(2, min(5 if args.config in (1, 2) else 3, args.steps))
-    pin_blob = torch.from_numpy(np.ascontiguousarray(blob)).pin_memory()
-    pin_pairs = torch.from_numpy(np.ascontiguousarray(pairs).view(np.int32)).pin_memory()
-    nb, npairs_bytes = pin_blob.numel(), pin_pairs.numel() * 4
-    blob_p = pin_blob.numpy()
-    pairs_p = pin_pairs.numpy().view(api.PAIR_DTYPE)
-    out_scores = torch.empty(n_pairs, dtype=torch.int32).pin_memory()
-    out_rc = torch.empty((n_pairs, 2), dtype=torch.int32).pin_memory()
-    import ctypes as C
-    L = eng.L
-    str_bytes = int(3 * (pairs["referenceSize"].astype(np.int64) + pairs["querySize"] + 1).sum()) if want_strings else 0
-    e2e_first_strings = []
-
-    def e2e_once(keep=False):
-        sb, so = C.c_void_p(), C.c_void_p()
-        st = L.dpx_align_batch(eng.ctx, C.byref(params), blob_p.ctypes.data, nb, pairs_p.ctypes.data, n_pairs,
-                               out_scores.numpy().ctypes.data, out_rc.numpy().ctypes.data,
-                               C.byref(sb) if want_strings else None, C.byref(so) if want_strings else None)
-        if st != 0:
-            raise RuntimeError(f"dpx_align_batch failed: {st} {L.dpx_last_error(eng.ctx)}")
-        if want_strings:
-            if keep:
-                last = int(np.frombuffer(C.string_at(so.value + (3 * n_pairs - 1) * 8, 8), dtype=np.uint64)[0])
-                e2e_first_strings.append(last + len(C.string_at(sb.value + last)) + 1)      # size of the compacted blob
-                offs = np.frombuffer(C.string_at(so, 3 * n_chk * 8), dtype=np.uint64)
-                for i in range(n_chk):
-                    e2e_first_strings.append(tuple(C.string_at(sb.value + int(offs[3 * i + k])) for k in range(3)))
-            L.dpx_free(sb); L.dpx_free(so)
-
-    e2e_once(keep=True)
-    if want_strings:
-        str_bytes = e2e_first_strings.pop(0)              # what actually crosses PCIe: the compacted strings
-    # context for the e2e number: what a bare pinned H2D copy of the same input bytes costs on this box
-    dev_blob = torch.empty(nb, dtype=torch.uint8, device="cuda")
-    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dev_blob.copy_(pin_blob, non_blocking=True)
-    torch.cuda.synchronize()
-    c0.record(stream); dev_blob.copy_(pin_blob, non_blocking=True); c1.record(stream)
-    torch.cuda.synchronize()
-    h2d_ms = c0.elapsed_time(c1)
-    del dev_blob
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_once()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    if res is not None:
-        assert (out_scores.numpy() == res.scores).all(), "e2e and staged paths disagree"
-
-    # ---- reduce over ranks -------------------------------------------------------------------------------
-    if dist is not None:
-        t = torch.tensor([ms_total, e2e_s, fill_ms, bt_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s, fill_ms, bt_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
-    ms_per_step = ms_total / args.steps
-    value = cells * world / (ms_per_step * 1e-3) / 1e9
-    e2e_value = cells * world / e2e_s / 1e9
-
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
-
-    # ---- parity spot check against the oracle (outside every timed region) --------------------------------
-    s_ref, e_ref, t_ref = ol.align_batch(ol.params(oalgo, **wl["weights"]), blob, pairs[:n_chk], strings=want_strings, threads=min(cores, 16))
-    parity_ok = bool((out_scores.numpy()[:n_chk] == s_ref).all())
-    if wl["algo"] in ("LSW", "BSW") and not (args.config == 2 and args.score_only):
-        parity_ok = parity_ok and bool((out_rc.numpy()[:n_chk] == e_ref).all())
-    if want_strings:
-        parity_ok = parity_ok and e2e_first_strings == t_ref
-
-    # ---- roofline ---------------------------------------------------------------------------------------
-    clocks = sampler.result()
-    peaks, peaks_src = measured_peaks()
-    f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-    sass_key = wl["sass"].format(track=not args.score_only)
-    if args.config != 2 and not want_strings:
-        sass_key = sass_key.replace("traceback=True", "traceback=False")
-    alu_pc, issue_pc = sass_counts(sass_key)
-    sms = torch.cuda.get_device_properties(local).multi_processor_count
-    kern_ms = fill_ms if fill_ms > 0 else ms_per_step          # the dominant kernel = the fill kernel(s) of one step
-    cells_rank = cells
-    kernel_gcups = cells_rank / (kern_ms * 1e-3) / 1e9
-    roofline = {"bound": "dpx_issue", "achieved": kernel_gcups, "unit": "GCUPS", "kernel": wl["kernel"].split(" (+")[0], "traffic": None,
-                "kernel_ms": kern_ms}
-    if alu_pc:
-        slot_eff = (2 * wl["weights"]["band"] + 1) / 160.0 if args.config == 4 else 1.0   # band 64: 129 diagonals on 5 slots x 32 lanes
-        cells_clk_sm = min(64.0 / alu_pc, 128.0 / issue_pc) * slot_eff
-        peak = cells_clk_sm * sms * f_mhz * 1e6 / 1e9
-        roofline.update({"peak": peak, "frac": kernel_gcups / peak,
-                         "model": {"alu_pipe_lanes_per_clk_per_sm": 64, "issue_lanes_per_clk_per_sm": 128,
-                                   "alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "slot_efficiency": slot_eff,
-                                   "sms": sms, "sm_mhz": f_mhz, "sass_key": sass_key,
-                                   "source": "profiles/sass_counts.json + profiles/r01_dpx_microbench*.json"}})
-    if args.config == 2:
-        # HBM view: algorithmic bytes = 2-bit bases + the index entry + 12 B of results per pair
-        algo_bytes = n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 16 + 8 + 12)
-    else:
-        # HBM view: the packed traceback stream (0.5 B/cell Gotoh, 0.25 B/cell linear / banded) written once by the fill kernel
-        algo_bytes = cells_rank * wl["tb_bytes_per_cell"] if want_strings else n_pairs * ((wl["R"] + wl["Q"]) * 0.25 + 28)
-    if args.config == 1:
-        roofline["note"] = "ragged duos: a warp sweeps max(Q) x max(R) of its two pairs in passes of 256 rows, so ~60 % of its cell slots hold real cells"
-    hbm_ach = algo_bytes / (kern_ms * 1e-3) / 1e9
-    roofline["hbm"] = {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"],
-                       "peak_source": f"MEASURED_PEAKS.json ({peaks_src})", "algorithmic_bytes_per_launch": algo_bytes,
-                       "slab_bytes_written": tb_bytes if want_strings else None}
-
-    try:                                                      # DRAM traffic of the dominant kernel, from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[str(args.config)]
-        if want_strings or args.config == 2:
-            per_launch = tr["dram_bytes_per_pair"] * n_pairs if "dram_bytes_per_pair" in tr else tr["dram_bytes_per_cell"] * cells_rank
-            roofline["traffic"] = per_launch
-            roofline["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, scaled from the capture's size)"
-            roofline["traffic_source"] = tr["source"]
-    except Exception:
-        pass
-    d2h = n_pairs * 12 + str_bytes + (3 * 8 * n_pairs if want_strings else 0)
-    out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": wl["dtype"], "data": "synthetic", "config": config, "clocks": clocks,
-           "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": int(nb + npairs_bytes),
-                   "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-                   "api": "dpx_align_batch (C ABI), pinned host input buffers" + (", library-allocated string blob" if want_strings else ""),
-                   "h2d_note": "bytes of the host buffers handed to the call; when the seqPair index of a chunk is an arithmetic progression "
-                               "(fixed-length records) the library rebuilds it on the device instead of copying its 16 B per pair",
-                   "bare_h2d_copy_ms": h2d_ms, "bare_h2d_gbs": nb / (h2d_ms * 1e-3) / 1e9},
-           "gpu_launches": launches_per_step * args.steps, "roofline": roofline,
-           "fill_ms_serialised": fill_ms, "backtrack_ms_serialised": bt_ms, "wall_s_timed_region": t_wall, "parity_spot_check": parity_ok}
-
-    if not args.no_cpu_baseline and world == 1:
-        n_s = cpu_sample_size(wl, n_pairs, cores)
-        v, kind, dt = run_cpu_reference(wl, blob, pairs, n_s, cores)
-        out["cpu_baseline"] = {"value": v, "unit": "GCUPS", "cores": cores, "kind": kind, "seconds": dt,
-                               "sample": f"first {n_s} pairs of the same workload, {cores} host threads, align loop only"}
-    print(json.dumps(out))
-    batch.free(); eng.close()
-    if dist is not None:
-        dist.destroy_process_group()
+        t_start = time.perf_counter()
+        out = bench_batched(C, 2, args.steps, args.warmup, score_only=args.score_only, n_pairs=args.pairs, with_cpu=with_cpu, extras=True)
+        if not args.only_headline and not args.pairs:
+            subs = {}
+            sub_steps = max(3, min(args.steps, 5))
+            subs["2_score_only"] = bench_batched(C, 2, max(5, min(args.steps, 10)), args.warmup, score_only=True, with_cpu=False)
+            subs["2_ragged"] = bench_batched(C, 2, max(5, min(args.steps, 10)), args.warmup, with_cpu=False, gen_override=("ragged_uniform", 100, 200),
+                                             label="LinearSmithWaterman batch, RAGGED lengths: {pairs} pairs, R and Q ~ U[100,200] independently (mean 150 x 150), score{ends}")
+            subs["3"] = bench_batched(C, 3, sub_steps, args.warmup, with_cpu=with_cpu, cpu_seconds=6.0)
+            subs["3_score_only"] = bench_batched(C, 3, sub_steps, args.warmup, score_only=True, with_cpu=False)
+            subs["1"] = bench_batched(C, 1, max(5, min(args.steps, 10)), args.warmup, with_cpu=with_cpu, cpu_seconds=5.0)
+            subs["4"] = bench_batched(C, 4, sub_steps, args.warmup, with_cpu=with_cpu, cpu_seconds=6.0)
+            subs["5"] = bench_long(C, 3, 1, with_cpu)
+            if C.world > 1:
+                subs["2_multi_abi"] = bench_multi_abi(C)
+            if out is not None:
+                out["configs"] = subs
+                out["wall_s_whole_run"] = time.perf_counter() - t_start
+    if C.rank == 0 and out is not None:
+        print(json.dumps(out))
+    C.close()
 
 
 if __name__ == "__main__":

@@ -23,7 +23,7 @@ import numpy as np
 
 from . import _lib
 
-LNW, ANW, LSW, BSW = 0, 1, 2, 3
+LNW, ANW, LSW, BSW, ABSW = 0, 1, 2, 3, 4
 OUT_SCORE, OUT_END_COORDS, OUT_STRINGS = 1, 2, 4
 PAIR_DTYPE = np.dtype([("referenceIdx", "<i4"), ("referenceSize", "<i4"), ("queryIdx", "<i4"), ("querySize", "<i4")])
 
@@ -510,3 +510,16 @@ class BandedSmithWaterman(SequenceAligner):
 
     def _params(self):
         return make_params(BSW, self.w[0], self.w[1], self.w[2], 0, self.band_width, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)
+
+
+class AffineBandedSmithWaterman(SequenceAligner):
+    """Not a reference class: affine banded Smith-Waterman (DPX_ALGO_ABSW, include/dpxalign.h), the variant the reference names
+    as a TODO (python/LinearBandedSmithWaterman.py:8).  Constructor shaped like BandedSmithWaterman's (pairNum after the weights)."""
+
+    def __init__(self, input_reference, input_query, match_weight, mismatch_weight, gap_open_weight, gap_extend_weight, pairNum, band_width=64):
+        super().__init__(input_reference, input_query, pairNum)
+        self.w = (match_weight, mismatch_weight, gap_open_weight, gap_extend_weight)
+        self.band_width = int(band_width)
+
+    def _params(self):
+        return make_params(ABSW, self.w[0], self.w[1], self.w[2], self.w[3], self.band_width, OUT_SCORE | OUT_END_COORDS | OUT_STRINGS)

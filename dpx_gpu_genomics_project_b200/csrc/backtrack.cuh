@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t wf_code(const uint32_t* __restrict__ tb, con
 
 template <int ALGO>
 __global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
-    constexpr int CB = (ALGO == DPX_ALGO_ANW) ? 4 : 2;
+    constexpr int CB = (ALGO == DPX_ALGO_ANW || ALGO == DPX_ALGO_ABSW) ? 4 : 2;
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= a.count) return;
     const int pid = a.order ? a.order[a.first + pos] : (a.first + pos);
@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
     const int R = pr.referenceSize, Q = pr.querySize;
     const uint8_t* __restrict__ ref = a.blob + pr.referenceIdx;
     const uint8_t* __restrict__ qry = a.blob + pr.queryIdx;
-    const WfGeom geo = WfGeom::make(a.K, CB, Q, R, ALGO == DPX_ALGO_BSW ? a.band : -1);
+    const WfGeom geo = WfGeom::make(a.K, CB, Q, R, (ALGO == DPX_ALGO_BSW || ALGO == DPX_ALGO_ABSW) ? a.band : -1);
     const uint32_t* __restrict__ tb = a.tb + (unsigned long long)pos * a.tb_stride;
 
     const size_t F = (size_t)Q + R + 1;
@@ -99,6 +99,27 @@ __global__ void __launch_bounds__(128) bt_walk_kernel(const BtArgs a) {
         }
         while (i > 0) { emit_up(i); --i; }
         while (j > 0) { emit_left(j); --j; }
+    } else if (ALGO == DPX_ALGO_ABSW) {
+        // affine banded SW: ANW's three states, LSW's stop rule (STOP code <=> H == 0, checked on arrival in SCORING)
+        if (a.scores[pid] > 0) {
+            int i = a.end_rc[2 * pid], j = a.end_rc[2 * pid + 1], state = 0;
+            while (i != 0 && j != 0) {
+                const uint32_t c = wf_code<CB>(tb, geo, i, j);
+                if (state == 0) {
+                    const uint32_t d = c & 3u;
+                    if (d == C_STOP) break;
+                    if (d == C_DIAG) { emit_diag(i, j); --i; --j; }
+                    else if (d == C_UP) state = 2;
+                    else state = 1;
+                } else if (state == 1) {
+                    state = (c & C_IOPEN) ? 0 : 1;
+                    emit_left(j); --j;
+                } else {
+                    state = (c & C_DOPEN) ? 0 : 2;
+                    emit_up(i); --i;
+                }
+            }
+        }
     } else {
         if (a.scores[pid] > 0) {
             int i = a.end_rc[2 * pid], j = a.end_rc[2 * pid + 1];

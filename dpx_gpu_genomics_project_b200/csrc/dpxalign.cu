@@ -122,6 +122,10 @@ struct dpx_ctx {
     int device = 0;
     DpxOptions opt;
     int sm_count = 0;
+    // opt-in ceiling of dynamic shared memory per block.  Kernels always get THIS as their MaxDynamicSharedMemorySize attribute:
+    // the attribute is per function and device, not per launch, so two contexts on one device (one per host thread) setting
+    // each launch's own size would race (thread A's larger launch after thread B's smaller attribute = invalid argument).
+    int smem_optin = 48 * 1024;
     cudaStream_t own_stream = nullptr;             // lane 0 (unless the caller supplies a stream)
     cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // lanes 1..3 of the chunked one-call pipeline
     cudaStream_t stream = nullptr;
@@ -182,6 +186,15 @@ struct dpx_batch {
     dpx_run_stats stats{};
 };
 
+// Kernels always get the opt-in ceiling (minus their static shared memory) as MaxDynamicSharedMemorySize: see dpx_ctx::smem_optin.
+template <typename F>
+static cudaError_t max_dyn_smem(const dpx_ctx* ctx, F kern) {
+    cudaFuncAttributes fa;
+    const cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes);
+}
+
 #define CU(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e__ = (call);                                                                  \
@@ -230,6 +243,7 @@ int dpx_create(dpx_ctx** out, int device) {
     dpx_ctx* ctx = new dpx_ctx();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
     bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaMalloc(&ctx->counters, 4 * 64 * sizeof(unsigned int)) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -842,7 +856,7 @@ int dpx_batch_sync(dpx_batch* b) {
         }
         CU(cudaEventElapsedTime(&ms, b->ev_begin, b->ev_end));
         b->stats.fill_ms = fill; b->stats.backtrack_ms = bt; b->stats.total_ms = ms;
-        if (b->params.algo == DPX_ALGO_BSW && b->d_band_cells) {
+        if ((b->params.algo == DPX_ALGO_BSW || b->params.algo == DPX_ALGO_ABSW) && b->d_band_cells) {
             unsigned long long c = 0;
             CU(cudaMemcpy(&c, b->d_band_cells, sizeof(c), cudaMemcpyDeviceToHost));
             b->stats.cells = c;

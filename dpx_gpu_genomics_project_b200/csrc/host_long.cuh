@@ -326,8 +326,8 @@ static int long_pair_strings(dpx_ctx* ctx, const dpx_params* p, const char* ref,
     if (!pool_alloc(ctx, &d_tiles, (size_t)max_tiles) || !pool_alloc(ctx, &d_slots, slot_words * (size_t)max_tiles) ||
         !pool_alloc(ctx, &d_edges, long_bt_edge_words(TH, TW) * (size_t)max_tiles) || !pool_alloc(ctx, &d_segs, (size_t)max_tiles) ||
         !pool_alloc(ctx, &d_seg_off, (size_t)max_tiles)) { cleanup(); return DPX_ERR_NOMEM; }
-    TCU(cudaFuncSetAttribute(long_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem));
-    TCU(cudaFuncSetAttribute(long_tile_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(fill_smem, 1024)));
+    TCU(max_dyn_smem(ctx, long_emit_kernel));
+    TCU(max_dyn_smem(ctx, long_tile_fill_kernel));
     a.slots = d_slots; a.tiles = d_tiles; a.edges = d_edges; a.segs = d_segs; a.seg_off = d_seg_off;
     long long state[8] = {ie, je, 0, 0, 0, 0, 0, 0};              // row, column, characters written, done, tiles walked, segments, error
     TCU(cudaMemcpyAsync(d_res, state, sizeof(state), cudaMemcpyHostToDevice, st));

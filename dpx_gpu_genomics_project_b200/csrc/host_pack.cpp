@@ -26,6 +26,11 @@ namespace {
 std::mutex g_mu;
 std::unordered_map<const void*, Sidecar*> g_by_blob, g_by_pairs;
 
+// The affinity mask the process had when the library was loaded: bind_thread_to_device narrows THIS mask, so a thread that was
+// already bound next to one GPU (or inherited such a binding from its creator) can still be moved next to another.
+cpu_set_t g_initial_mask;
+bool g_have_initial = [] { return sched_getaffinity(0, sizeof(g_initial_mask), &g_initial_mask) == 0; }();
+
 void* host_alloc(size_t bytes, bool* pinned) {
     bytes = std::max<size_t>(bytes, 64);
     void* p = nullptr;
@@ -239,7 +244,8 @@ int bind_thread_to_device(int device) {
         if (k == 1) b = a;
         if (k >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; ++c) if (c >= 0) CPU_SET(c, &want);
     }
-    if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 0;
+    if (g_have_initial) cur = g_initial_mask;
+    else if (sched_getaffinity(0, sizeof(cur), &cur) != 0) return 0;
     CPU_AND(&both, &want, &cur);
     const int n = CPU_COUNT(&both);
     if (n == 0) return 0;                                       // the container's cpuset does not reach that node: leave it alone

@@ -26,6 +26,7 @@ static int dispatch_wf(dpx_ctx* ctx, cudaStream_t st, int algo, bool tb, int K, 
         case DPX_ALGO_ANW: return tb ? dispatch_wf_k<DPX_ALGO_ANW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_ANW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
         case DPX_ALGO_LSW: return tb ? dispatch_wf_k<DPX_ALGO_LSW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_LSW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
         case DPX_ALGO_BSW: return tb ? dispatch_wf_k<DPX_ALGO_BSW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_BSW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
+        case DPX_ALGO_ABSW: return tb ? dispatch_wf_k<DPX_ALGO_ABSW, true>(ctx, st, K, a, blocks, query_only, slots, blocks_out) : dispatch_wf_k<DPX_ALGO_ABSW, false>(ctx, st, K, a, blocks, query_only, slots, blocks_out);
     }
     return DPX_ERR_INVALID;
 }
@@ -37,7 +38,7 @@ static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xorm
     a.rsel_stride = (b->max_r + 2 * G + 18 + 1) & ~1;          // the table is written 16 entries (one packed word) at a time
     const size_t smem = (size_t)gpb * ((size_t)a.bnd_stride * 4 + (size_t)a.rsel_stride * 2);
     auto launch = [&](auto kern) -> int {
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(max_dyn_smem(ctx, kern));
         int per_sm = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
         if (per_sm < 1) { ctx->err = "short-read kernel does not fit on an SM"; return DPX_ERR_RANGE; }
@@ -155,7 +156,7 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
 template <int ALGO, bool TB, bool PACKED, bool GBND, bool WIDE = false>
 static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
     auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND, WIDE>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(max_dyn_smem(ctx, kern));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
     if (per_sm < 1) { ctx->err = "pair-wavefront kernel does not fit on an SM"; return DPX_ERR_RANGE; }
@@ -222,8 +223,9 @@ static int launch_band_any(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, boo
 static int batch_run(dpx_batch* b, const dpx_params* p) {
     dpx_ctx* ctx = b->ctx;
     cudaStream_t st = b->stream;
-    if (p->algo < DPX_ALGO_LNW || p->algo > DPX_ALGO_BSW) return DPX_ERR_INVALID;
-    if (p->algo == DPX_ALGO_BSW && p->band < 0) return DPX_ERR_INVALID;
+    if (p->algo < DPX_ALGO_LNW || p->algo > DPX_ALGO_ABSW) return DPX_ERR_INVALID;
+    const bool banded = p->algo == DPX_ALGO_BSW || p->algo == DPX_ALGO_ABSW;
+    if (banded && p->band < 0) return DPX_ERR_INVALID;
     const size_t n = b->n_pairs;
     b->params = *p; b->ran = true;
     b->stats = dpx_run_stats{};
@@ -232,10 +234,10 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     b->ev.clear(); b->ev_kind.clear(); b->ev_sync.clear();
     const bool want_strings = (p->flags & DPX_OUT_STRINGS) != 0;
     const int algo = p->algo;
-    const int CB = (algo == DPX_ALGO_ANW) ? 4 : 2;
+    const int CB = (algo == DPX_ALGO_ANW || algo == DPX_ALGO_ABSW) ? 4 : 2;
     const int K = (b->max_q <= 128) ? 4 : 8;
     int band = -1;
-    if (algo == DPX_ALGO_BSW) band = std::min(p->band, std::max(b->max_q, b->max_r));
+    if (banded) band = std::min(p->band, std::max(b->max_q, b->max_r));
     b->stats.cells = b->info.cells;
     b->stats.kernel_id = DPX_KERNEL_WAVEFRONT_S32;
     if (n == 0) { CU(cudaEventRecord(b->ev_begin, st)); CU(cudaEventRecord(b->ev_end, st)); return DPX_OK; }
@@ -244,7 +246,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     // one-time (per batch) preparation, outside the timed first-kernel -> last-byte window
     { int s = ensure_order(b); if (s) return s; }
     if (want_strings) { int s = ensure_str_off(b); if (s) return s; s = ensure_blob(b); if (s) return s; }
-    if (algo == DPX_ALGO_BSW) {
+    if (banded) {
         if (!b->d_band_cells && !pool_alloc(ctx, &b->d_band_cells, 1)) return DPX_ERR_NOMEM;
         CU(cudaMemsetAsync(b->d_band_cells, 0, sizeof(unsigned long long), st));
         band_cells_kernel<<<std::min<int>((int)((n + 7) / 8), ctx->sm_count * 8), 256, 0, st>>>(b->d_pairs, (int)n, band, b->d_band_cells);
@@ -464,7 +466,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, st));
                     const size_t bt_smem = (size_t)BAND_BT_SMEM_WORDS * sizeof(uint32_t);
-                    CU(cudaFuncSetAttribute(band_bt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bt_smem));
+                    CU(max_dyn_smem(ctx, band_bt_kernel));
                     band_bt_kernel<<<(a.count + 31) / 32, 32, bt_smem, st>>>(t);
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, st));
@@ -528,6 +530,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 case DPX_ALGO_ANW: bt_walk_kernel<DPX_ALGO_ANW><<<bt_blocks, 128, 0, st>>>(t); break;
                 case DPX_ALGO_LSW: bt_walk_kernel<DPX_ALGO_LSW><<<bt_blocks, 128, 0, st>>>(t); break;
                 case DPX_ALGO_BSW: bt_walk_kernel<DPX_ALGO_BSW><<<bt_blocks, 128, 0, st>>>(t); break;
+                case DPX_ALGO_ABSW: bt_walk_kernel<DPX_ALGO_ABSW><<<bt_blocks, 128, 0, st>>>(t); break;
             }
             CU(cudaGetLastError());
             CU(cudaEventRecord(e, st));

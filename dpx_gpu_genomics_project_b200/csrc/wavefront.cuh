@@ -15,6 +15,8 @@
 //   LSW  c++/LinearSmithWaterman.cpp:70-114     (ReLU; UP > LEFT > DIAG by equality with H)
 //        end cell = first strict max in row-major order, :145-157
 //   BSW  repaired semantics: LSW restricted to |i-j| <= band, everything else 0.
+//   ABSW affine banded SW (not in the reference; include/dpxalign.h): ANW's D / I recurrences (tie -> GAP_OPEN) under LSW's
+//        ReLU, UP > LEFT > DIAG and end-cell rules, on the band; out-of-band cells have H = 0, D = I = -inf.
 #pragma once
 #include "common.cuh"
 
@@ -40,9 +42,11 @@ template <int ALGO, bool TB, int K>
 __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
     constexpr bool IS_NW  = (ALGO == DPX_ALGO_LNW || ALGO == DPX_ALGO_ANW);
     constexpr bool IS_ANW = (ALGO == DPX_ALGO_ANW);
-    constexpr bool IS_SW  = (ALGO == DPX_ALGO_LSW || ALGO == DPX_ALGO_BSW);
-    constexpr bool BANDED = (ALGO == DPX_ALGO_BSW);
-    constexpr int  CB  = IS_ANW ? 4 : 2;
+    constexpr bool IS_ASW = (ALGO == DPX_ALGO_ABSW);
+    constexpr bool AFFINE = IS_ANW || IS_ASW;              // D travels down the lanes, I along the row
+    constexpr bool IS_SW  = (ALGO == DPX_ALGO_LSW || ALGO == DPX_ALGO_BSW || IS_ASW);
+    constexpr bool BANDED = (ALGO == DPX_ALGO_BSW || IS_ASW);
+    constexpr int  CB  = AFFINE ? 4 : 2;
     constexpr int  SPW = 32 / (K * CB);
     constexpr unsigned FULL = 0xffffffffu;
 
@@ -73,7 +77,7 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
             if (ALGO == DPX_ALGO_LNW) h0 = j * g;                       // c++/LinearNeedlemanWunsch.cpp:38-41
             if (IS_ANW) h0 = (j == 0) ? 0 : a.go + j * ge;              // c++/AffineNeedlemanWunsch.cpp:50-53
             bH[j] = h0;
-            if (IS_ANW) bD[j] = NEG_INF;                                // D[0][j] never wins: row 1 always opens (:185-189)
+            if (AFFINE) bD[j] = NEG_INF;                                // D[0][j] never wins: row 1 always opens (:185-189)
         }
         __syncwarp();
 
@@ -118,9 +122,9 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
             for (int step = 0; step < nsteps; ++step) {
                 const int j = jstart + step - lane;
                 int topH = __shfl_up_sync(FULL, botH, 1);
-                int topD = IS_ANW ? __shfl_up_sync(FULL, botD, 1) : 0;
+                int topD = AFFINE ? __shfl_up_sync(FULL, botD, 1) : 0;
                 if (j >= jstart && j <= jend) {
-                    if (lane == 0) { topH = bH[j]; if (IS_ANW) topD = bD[j]; }
+                    if (lane == 0) { topH = bH[j]; if (AFFINE) topD = bD[j]; }
                     const uint8_t rc = ref[j - 1];
                     int up = topH, upD = topD, diag = diag0;
                     diag0 = topH;
@@ -143,6 +147,17 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
                             h = __vibmax_s32(iv, m, &p2);
                             code = (p2 ? C_LEFT : (p1 ? C_UP : C_DIAG)) | (pd ? C_DOPEN : 0u) | (pi ? C_IOPEN : 0u);
                             Ireg[r] = iv; upD = dv;
+                        } else if (IS_ASW) {
+                            bool pd, pi;
+                            int dv = __vibmax_s32(up + goe, upD + ge, &pd);        // tie -> GAP_OPEN
+                            int iv = __vibmax_s32(left + goe, Ireg[r] + ge, &pi);
+                            h = __vimax3_s32_relu(dv, iv, ds);                     // max(0, D, I, diag)
+                            code = (h == 0) ? C_STOP : (dv == h ? C_UP : (iv == h ? C_LEFT : C_DIAG));
+                            code |= (pd ? C_DOPEN : 0u) | (pi ? C_IOPEN : 0u);
+                            const unsigned d = (unsigned)(j - (i_first + r) + band);
+                            if (d > (unsigned)(2 * band)) { h = 0; code = C_STOP; dv = NEG_INF; iv = NEG_INF; }   // no gap starts or continues outside the band
+                            Ireg[r] = iv; upD = dv;
+                            if (h > bestH[r]) { bestH[r] = h; bestJ[r] = j; }
                         } else {
                             const int ug = up + g, lg = left + g;
                             h = __vimax3_s32_relu(ug, lg, ds);                     // max(0, up, left, diag)
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(128) wf_fill_kernel(const WfArgs a) {
                         if (TB) codes |= code << (r * CB);
                     }
                     botH = up; botD = upD;
-                    if (lane == 31) { bH[j] = botH; if (IS_ANW) bD[j] = botD; }
+                    if (lane == 31) { bH[j] = botH; if (AFFINE) bD[j] = botD; }
                     if (TB) {
                         const int sub = step % SPW;
                         acc |= codes << (sub * K * CB);

@@ -2,7 +2,7 @@
 // (c++/main.cpp:118-262), but the whole file goes to the GPU as ONE batch instead of one aligner object per pair.
 //
 //   main -pairs <file> [-match m] [-mismatch x] [-open g] [-extend e]          (positional, as the reference :133-150)
-//   extra, after the reference's flags:  -algo LSW|LNW|ANW|BSW   (the reference picks it with a #define, :22-24;
+//   extra, after the reference's flags:  -algo LSW|LNW|ANW|BSW|ABSW   (the reference picks it with a #define, :22-24;
 //                                                                default LSW = what the reference ships enabled)
 //                                        -band W                 (BSW only, default 64)
 //                                        -scores                 score (+ end cell) lines only, no alignment strings
@@ -53,6 +53,7 @@ int main(int argc, char* argv[]) {
             const char* a = argv[++i];
             if (!strcmp(a, "LNW")) algo = DPX_ALGO_LNW; else if (!strcmp(a, "ANW")) algo = DPX_ALGO_ANW;
             else if (!strcmp(a, "LSW")) algo = DPX_ALGO_LSW; else if (!strcmp(a, "BSW")) algo = DPX_ALGO_BSW;
+            else if (!strcmp(a, "ABSW")) algo = DPX_ALGO_ABSW;        // affine banded SW (-open, -extend, -band)
             else { fprintf(stderr, "unknown -algo %s\n", a); exit(EXIT_FAILURE); }
         }
     }

@@ -42,7 +42,13 @@ typedef enum {
     DPX_ALGO_LNW = 0,   /* LinearNeedlemanWunsch   c++/LinearNeedlemanWunsch.{h,cpp}  */
     DPX_ALGO_ANW = 1,   /* AffineNeedlemanWunsch   c++/AffineNeedlemanWunsch.{h,cpp}  */
     DPX_ALGO_LSW = 2,   /* LinearSmithWaterman     c++/LinearSmithWaterman.{h,cpp}    */
-    DPX_ALGO_BSW = 3    /* BandedSmithWaterman     c++/BandedSmithWaterman.{h,cpp} (repaired semantics) */
+    DPX_ALGO_BSW = 3,   /* BandedSmithWaterman     c++/BandedSmithWaterman.{h,cpp} (repaired semantics) */
+    DPX_ALGO_ABSW = 4   /* affine banded Smith-Waterman: the variant the reference only names as a TODO
+                           (python/LinearBandedSmithWaterman.py:8).  Local Gotoh on |i-j| <= band: D / I recurrences and the
+                           tie -> GAP_OPEN rule of AffineNeedlemanWunsch (c++/AffineNeedlemanWunsch.cpp:185-213), ReLU,
+                           UP > LEFT > DIAG, first-strict-max end cell and stop-at-zero walk of LinearSmithWaterman;
+                           gap_open = 0 gives the linear BandedSmithWaterman with gap = gap_extend byte for byte.
+                           band >= max(Q, R) (or any band larger than both lengths) = unbanded local Gotoh. */
 } dpx_algo;
 
 /* ---- output selection ------------------------------------------------------------ */
@@ -59,8 +65,8 @@ typedef struct {
     int32_t  match;
     int32_t  mismatch;
     int32_t  gap_open;      /* linear: the gap weight */
-    int32_t  gap_extend;    /* ANW only */
-    int32_t  band;          /* BSW only: |i-j| <= band */
+    int32_t  gap_extend;    /* ANW, ABSW */
+    int32_t  band;          /* BSW, ABSW: |i-j| <= band */
     uint32_t flags;         /* DPX_OUT_* */
 } dpx_params;
 

@@ -17,6 +17,15 @@
  *                   prototype python/LinearBandedSmithWaterman.py:71 run with BAND = W+1
  *                   (fixtures in tests/golden/bsw_python_scores.json).
  *
+ *   ABSW (affine banded SW): NOT A REFERENCE ALGORITHM — the reference only names it as a TODO
+ *                   (python/LinearBandedSmithWaterman.py:8 "BSW evidently usually uses affine gap
+ *                   penalties").  Definition adopted: local Gotoh restricted to
+ *                   |i-j| <= W, built from the reference's own pieces — D/I recurrences and GAP_OPEN tie rule
+ *                   of AffineNeedlemanWunsch (c++/AffineNeedlemanWunsch.cpp:185-213), ReLU / UP > LEFT > DIAG /
+ *                   first-strict-max end cell / stop-at-zero walk of LinearSmithWaterman.  Pins: gap_open = 0
+ *                   degenerates byte-for-byte to the (pinned) linear banded SW with gap = gap_extend; scores
+ *                   equal an independent numpy three-state local alignment (tests/test_oracle.py).
+ *
  * Each function cites the reference file:line it follows.  Matrices are (Q+1)x(R+1)
  * row-major, rows = query, cols = reference, all arithmetic int32 (as the reference).
  */
@@ -30,6 +39,7 @@
 #define ORC_ANW 1
 #define ORC_LSW 2
 #define ORC_BSW 3
+#define ORC_ABSW 4   /* affine banded Smith-Waterman: NOT in the reference (see absw_pair) */
 
 typedef struct { int32_t referenceIdx, referenceSize, queryIdx, querySize; } orc_pair; /* c++/parseInput.h:22-29 */
 typedef struct { int32_t algo, match, mismatch, gap_open, gap_extend, band; } orc_params;
@@ -261,6 +271,76 @@ static int64_t bsw_pair_bandmem(const orc_params* p, const char* r, int R, const
     return len;
 }
 
+/* ---------------------------------------------------------------------------------
+ * Affine banded Smith-Waterman (ORC_ABSW) — see the header: local Gotoh on the cells with |i-j| <= band (band < 0: all
+ * cells).  Border and out-of-band cells: H = 0 and D = I = "minus infinity" (a gap can neither start nor continue there).
+ *   D[i][j] = vibmax(H[i-1][j] + open + extend, D[i-1][j] + extend)   tie -> GAP_OPEN   (c++/AffineNeedlemanWunsch.cpp:190-197)
+ *   I[i][j] = vibmax(H[i][j-1] + open + extend, I[i][j-1] + extend)   tie -> GAP_OPEN   (:206-213)
+ *   t = max(D, I, diag + s);  H = max(0, t);  dirH = UP if D == H, else LEFT if I == H, else DIAG   (c++/LinearSmithWaterman.cpp:97-108)
+ * End cell: first strict maximum in row-major order (:145-157).  Walk: AffineNeedlemanWunsch's three states (:257-364) —
+ * SCORING follows dirH (UP / LEFT switch state without moving), a gap state emits, moves and returns to SCORING when its
+ * direction bit says GAP_OPEN — and stops like LinearSmithWaterman when the cell it arrives at in SCORING has H == 0 (:222). */
+#define ORC_NEG (-(1 << 29))
+static int64_t absw_pair(const orc_params* p, int band, const char* r, int R, const char* q, int Q,
+                         int32_t* score, int32_t* end_row, int32_t* end_col,
+                         char* o_ref, char* o_rel, char* o_qry) {
+    size_t W = (size_t)R + 1, N = W * ((size_t)Q + 1);
+    int32_t* H  = (int32_t*)calloc(N, sizeof(int32_t));
+    int32_t* Dm = (int32_t*)malloc(N * sizeof(int32_t));
+    int32_t* Im = (int32_t*)malloc(N * sizeof(int32_t));
+    uint8_t* T  = (uint8_t*)calloc(N, 1);
+    for (size_t k = 0; k < N; ++k) { Dm[k] = ORC_NEG; Im[k] = ORC_NEG; }
+    const int32_t goe = p->gap_open + p->gap_extend, ge = p->gap_extend;
+    for (int i = 1; i <= Q; ++i) {
+        int jlo = 1, jhi = R;
+        if (band >= 0) { jlo = i - band < 1 ? 1 : i - band; jhi = (int64_t)i + band > R ? R : i + band; }
+        for (int j = jlo; j <= jhi; ++j) {
+            int pred; uint8_t t = 0;
+            int32_t dv = vibmax_s32(H[(i - 1) * W + j] + goe, Dm[(i - 1) * W + j] + ge, &pred); if (pred) t |= 4;
+            int32_t iv = vibmax_s32(H[i * W + (j - 1)] + goe, Im[i * W + (j - 1)] + ge, &pred); if (pred) t |= 8;
+            int32_t diag = H[(i - 1) * W + (j - 1)] + (q[i - 1] == r[j - 1] ? p->match : p->mismatch);
+            int32_t m = dv > iv ? dv : iv; m = m > diag ? m : diag;
+            int32_t h = m > 0 ? m : 0;
+            Dm[i * W + j] = dv; Im[i * W + j] = iv; H[i * W + j] = h;
+            if (h > 0) t |= (dv == h) ? D_UP : (iv == h) ? D_LEFT : D_DIAG;
+            T[i * W + j] = t;
+        }
+    }
+    int32_t best = 0; int bi = 0, bj = 0;
+    for (int i = 0; i <= Q; ++i)
+        for (int j = 0; j <= R; ++j)
+            if (H[i * W + j] > best) { best = H[i * W + j]; bi = i; bj = j; }
+    *score = best; if (end_row) *end_row = bi; if (end_col) *end_col = bj;
+    int64_t len = -1;
+    if (o_ref) {
+        sb3 s; sb_init(&s, o_ref, o_rel, o_qry, (int64_t)Q + R);
+        if (best > 0) {
+            int i = bi, j = bj, state = 0;                 /* 0 SCORING, 1 INSERTION, 2 DELETION */
+            for (;;) {
+                const uint8_t t = T[i * W + j];
+                if (state == 0) {
+                    if (H[i * W + j] == 0) break;
+                    switch (t & 3) {
+                        case D_DIAG: sb_push(&s, r[j - 1], q[i - 1] == r[j - 1] ? '*' : '|', q[i - 1]); --i; --j; break;
+                        case D_UP:   state = 2; break;
+                        case D_LEFT: state = 1; break;
+                        default: abort();
+                    }
+                } else if (state == 1) {
+                    state = (t & 8) ? 0 : 1;
+                    sb_push(&s, r[j - 1], ' ', '_'); --j;
+                } else {
+                    state = (t & 4) ? 0 : 2;
+                    sb_push(&s, '_', ' ', q[i - 1]); --i;
+                }
+            }
+        }
+        len = sb_finish(&s);
+    }
+    free(H); free(Dm); free(Im); free(T);
+    return len;
+}
+
 /* Linear-memory score + end-cell restatement of LinearSmithWaterman (a8/a9) for inputs
  * whose full matrix cannot be allocated (the reference needs 8 B/cell).  One rolling row.
  * Same first-strict-max-in-row-major rule (c++/LinearSmithWaterman.cpp:145-157).
@@ -310,6 +390,7 @@ int64_t orc_align_pair(const orc_params* p, const char* ref, int R, const char* 
                       return anw_pair(p, ref, R, qry, Q, score, o_ref, o_rel, o_qry);
         case ORC_LSW: return lsw_pair(p, -1, ref, R, qry, Q, score, end_row, end_col, o_ref, o_rel, o_qry);
         case ORC_BSW: return lsw_pair(p, p->band, ref, R, qry, Q, score, end_row, end_col, o_ref, o_rel, o_qry);
+        case ORC_ABSW: return absw_pair(p, p->band, ref, R, qry, Q, score, end_row, end_col, o_ref, o_rel, o_qry);
         default: return -2;
     }
 }

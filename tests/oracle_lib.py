@@ -15,8 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_ALIGN = os.path.join(ORACLE_DIR, "_ref", "ref_align")
 
-LNW, ANW, LSW, BSW = 0, 1, 2, 3
-ALGO_NAMES = {LNW: "LNW", ANW: "ANW", LSW: "LSW", BSW: "BSW"}
+LNW, ANW, LSW, BSW, ABSW = 0, 1, 2, 3, 4
+ALGO_NAMES = {LNW: "LNW", ANW: "ANW", LSW: "LSW", BSW: "BSW", ABSW: "ABSW"}
 
 
 class OrcParams(C.Structure):

@@ -83,6 +83,25 @@ def test_long_pairs_config4_shape(eng):
     _check(eng, blob, pairs, 64)
 
 
+def test_config4_true_shape(eng):
+    """BASELINE config 4 at its REAL per-pair size: 64 pairs of 10 000 x 10 000 bp, band 64, scores + end cells + strings against
+    the band-memory oracle (orc bsw_pair_bandmem: O(Q * W) memory, itself pinned on the full-matrix restatement)."""
+    img = synth.mutated_fixed_file_bytes(64, 10_000, 10_000, 0x5EED0004, 0.05, 0.01, 0.01)
+    blob, pairs = ol.parse_image(img)
+    s, e, t = ol.align_batch(ol.params(ol.BSW, band=64), blob, pairs, strings=True, threads=8, bandmem=True)
+    for src in ("raw", "sidecar"):
+        if src == "sidecar":
+            inp = api.parse_image_native(img); blob, pairs = inp.sequences, inp.pairs
+        b = eng.upload(blob, pairs)
+        b.run(api.make_params(api.BSW, flags=ALL, band=64)); b.sync()
+        assert b.stats()["kernel_id"] == KERNEL_BAND
+        res = b.fetch()
+        b.free()
+        assert (res.scores == s).all() and (res.end_row_col == e).all(), src
+        assert res.strings == t, src
+        assert min(len(x[0]) for x in res.strings) > 9000                     # the alignments really span the reads
+
+
 def test_rectangular_pairs_leave_the_band(eng):
     rng = synth.Rng(12)
     pp = [(synth.random_seq(rng, 900), synth.random_seq(rng, 300)), (synth.random_seq(rng, 200), synth.random_seq(rng, 1000))]

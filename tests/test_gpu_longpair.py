@@ -70,3 +70,24 @@ def test_long_pair_letters_and_odd_weights(eng):
     r = synth.random_seq(rng, 5000, b"ACGT"); q = synth.mutate(rng, r, 0.03, 0.01, 0.01, b"ACGT")
     for w in (dict(match=1, mismatch=-1, gap_open=-1), dict(match=5, mismatch=-4, gap_open=-7), dict(match=100, mismatch=-100, gap_open=-120)):
         assert eng.align_long_pair(api.make_params(api.LSW, **w), r, q) == ol.lsw_score_only(ol.params(ol.LSW, **w), r, q)
+
+
+def test_config5_full_size_against_the_cpu_pin(eng):
+    """BASELINE config 5 at its REAL size, 1 Mbp x 1 Mbp (1e12 cells), against tests/golden/cfg5_1m.json: the rolling-row CPU
+    oracle run once on the same generated pair (tools/pin_cfg5.py).  Both lane widths the model may choose."""
+    import hashlib
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cfg5_1m.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/cfg5_1m.json not generated yet (tools/pin_cfg5.py)")
+    g = json.load(open(path))
+    R, Q = g["R"], g["Q"]
+    img = synth.mutated_fixed_file_bytes(1, R, Q, int(g["seed"], 16), 0.01, 0.001, 0.001)
+    ref = img[2:2 + R].tobytes(); qry = img[3 + R:3 + R + Q].tobytes()
+    assert hashlib.sha256(ref).hexdigest() == g["ref_sha256"] and hashlib.sha256(qry).hexdigest() == g["qry_sha256"]
+    want = (g["score"], g["end_row"], g["end_col"])
+    p = api.make_params(api.LSW, **g["weights"])
+    assert eng.align_long_pair(p, ref, qry) == want
+    with eng.options(long_k=16):
+        assert eng.align_long_pair(p, ref, qry) == want

@@ -78,10 +78,13 @@ def _worker(rank, world, port, out_path):
 
 
 @pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_two_gpu_modes_match_oracle(tmp_path):
+@pytest.mark.parametrize("world", sorted({2, _ngpu()} - {0, 1}) or [2])
+def test_multi_gpu_modes_match_oracle(tmp_path, world):
+    """Mode A (sharded batch) and mode B (striped long pair) on 2 GPUs and on every GPU of the box: identical bytes at every
+    rank count (test-plan item 4)."""
     import torch.multiprocessing as mp
     out = str(tmp_path / "res.npz")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
     got = np.load(out)
     blob, pairs = _pairs()
     s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False, threads=8)

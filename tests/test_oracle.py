@@ -162,3 +162,66 @@ def test_all_maxima_golden_fixture():
     txt, n = ol.lsw_all_text(ol.params(ol.LSW), blob, pairs)
     assert txt == open(os.path.join(GOLD, "ties.LSW_ALL.out.txt"), "rb").read()
     assert n > len(pairs)
+
+
+# ---- affine banded Smith-Waterman (ORC_ABSW): not a reference algorithm, see oracle/dpx_oracle.c:absw_pair -------------------
+def _np_local_gotoh_score(r, q, match, mismatch, go, ge, band):
+    """Independent restatement (numpy / plain loops, textbook three-state local alignment restricted to |i-j| <= band):
+    best score only.  A k-long gap costs go + k*ge, as in the reference's Gotoh (c++/AffineNeedlemanWunsch.cpp)."""
+    NEG = -10**9
+    Q, R = len(q), len(r)
+    H = np.zeros((Q + 1, R + 1), dtype=np.int64)
+    D = np.full((Q + 1, R + 1), NEG, dtype=np.int64); I = np.full((Q + 1, R + 1), NEG, dtype=np.int64)
+    for i in range(1, Q + 1):
+        for j in range(max(1, i - band), min(R, i + band) + 1):
+            D[i, j] = max(H[i - 1, j] + go + ge, D[i - 1, j] + ge)
+            I[i, j] = max(H[i, j - 1] + go + ge, I[i, j - 1] + ge)
+            H[i, j] = max(0, D[i, j], I[i, j], H[i - 1, j - 1] + (match if q[i - 1] == r[j - 1] else mismatch))
+    return int(H.max())
+
+
+@pytest.mark.parametrize("band", [0, 3, 17, 1000])
+def test_affine_banded_sw_degenerates_to_the_pinned_linear_band(band):
+    """gap_open = 0: a k-long gap costs k * gap_extend and every tie goes to GAP_OPEN, so scores, end cells and strings must be
+    byte-identical to the linear banded restatement (itself pinned on the LinearSmithWaterman golden for full bands)."""
+    for name in ("adversarial", "shapes", "cfg1_small"):
+        blob, pairs = ol.parse_image(open(os.path.join(GOLD, f"{name}.in.txt"), "rb").read())
+        for g in (-2, -1):
+            a = ol.align_batch(ol.params(ol.ABSW, gap_open=0, gap_extend=g, band=band), blob, pairs)
+            b = ol.align_batch(ol.params(ol.BSW, gap_open=g, band=band), blob, pairs)
+            assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and a[2] == b[2]
+    # full band, open = 0: the committed LinearSmithWaterman golden text itself
+    img = open(os.path.join(GOLD, "mid.in.txt"), "rb").read()
+    if band == 1000:
+        assert oracle_text(ol.ABSW, img, gap_open=0, gap_extend=-2, band=5000) == open(os.path.join(GOLD, "mid.LSW.out.txt"), "rb").read()
+
+
+def test_affine_banded_sw_scores_match_an_independent_restatement():
+    rng = synth.Rng(0xAB5)
+    pp = []
+    for k in range(60):
+        alpha = [b"01", b"0123"][k % 2]
+        r = synth.random_seq(rng, 1 + int(rng.below(1, 60)[0]), alpha)
+        q = synth.mutate(rng, r, 0.1, 0.08, 0.08, alpha) if k % 3 else synth.random_seq(rng, 1 + int(rng.below(1, 60)[0]), alpha)
+        pp.append((r, q))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    for w in (dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1), dict(match=2, mismatch=-3, gap_open=-5, gap_extend=-2), dict(match=1, mismatch=-1, gap_open=-1, gap_extend=0)):
+        for band in (2, 9, 100):
+            s, e, t = ol.align_batch(ol.params(ol.ABSW, band=band, **w), blob, pairs)
+            for k, (r, q) in enumerate(pp):
+                assert int(s[k]) == _np_local_gotoh_score(r, q, w["match"], w["mismatch"], w["gap_open"], w["gap_extend"], band)
+                # the printed alignment re-scores to the score and spells substrings ending at the end cell
+                ref_l, rel, qry_l = t[k]
+                if s[k] == 0:
+                    assert ref_l == rel == qry_l == b""
+                    continue
+                sc, in_gap = 0, None
+                for a, m, b in zip(ref_l, rel, qry_l):
+                    if a == ord("_") or b == ord("_"):
+                        kind = "D" if a == ord("_") else "I"
+                        sc += w["gap_extend"] + (w["gap_open"] if in_gap != kind else 0)
+                        in_gap = kind
+                    else:
+                        sc += w["match"] if a == b else w["mismatch"]; in_gap = None
+                assert sc == int(s[k])
+                assert r[: int(e[k][1])].endswith(ref_l.replace(b"_", b"")) and q[: int(e[k][0])].endswith(qry_l.replace(b"_", b""))

@@ -7,6 +7,7 @@
 // pthreads in consecutive blocks (c++/main.cpp:166-232), which is the shape kept here: CONTIGUOUS shards, balanced by
 // cell count.  Contiguous (rather than dealt) shards let every GPU upload one slice of the blob / packed sidecar instead of
 // a gather; length bucketing happens inside each shard on the device (sched_keys_kernel + radix sort).
+#include <algorithm>
 #include <condition_variable>
 #include <cstdlib>
 #include <cstring>
@@ -74,14 +75,30 @@ int dpx_multi_shard_bounds(const dpx_seq_pair* pairs, size_t n_pairs, int n_shar
         const unsigned long long c = (r > 0 && q > 0) ? (unsigned long long)r * (unsigned long long)q : 0ull;
         return c ? c : 1ull;
     };
-    unsigned long long total = 0;
-    for (size_t i = 0; i < n_pairs; ++i) total += weight(i);
+    // prefix sums over a few host threads (millions of pairs: a single-threaded pass would cost as much as the alignment itself):
+    // per-range totals first, then every boundary is located inside the one range its target falls in
+    const int T = n_pairs >= (1u << 18) ? (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+    std::vector<unsigned long long> part((size_t)T + 1, 0);
+    auto range = [&](int t) { return n_pairs * (size_t)t / (size_t)T; };
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < T; ++t) {
+            auto fn = [&, t] { unsigned long long a = 0; for (size_t i = range(t); i < range(t + 1); ++i) a += weight(i); part[(size_t)t + 1] = a; };
+            if (T == 1) fn(); else th.emplace_back(fn);
+        }
+        for (auto& x : th) x.join();
+    }
+    for (int t = 0; t < T; ++t) part[(size_t)t + 1] += part[(size_t)t];
+    const unsigned long long total = part[(size_t)T];
     bounds[0] = 0;
-    unsigned long long acc = 0; size_t i = 0;
     for (int g = 1; g < n_shards; ++g) {
+        // first index i such that the weight before i, plus half of pair i, reaches the target (same rule as a sequential scan)
         const unsigned long long target = (unsigned long long)((long double)total * g / n_shards);
+        int t = 0;
+        while (t + 1 < T && part[(size_t)t + 1] < target) ++t;
+        unsigned long long acc = part[(size_t)t]; size_t i = range(t);
         while (i < n_pairs && acc + weight(i) / 2 < target) acc += weight(i++);
-        bounds[g] = i;
+        bounds[g] = std::max(i, bounds[g - 1]);
     }
     bounds[n_shards] = n_pairs;
     return DPX_OK;

@@ -666,32 +666,37 @@ def bench_multi_abi(C, steps=3):
     if C.rank != 0:
         store.wait(["dpx_multi_abi_done"])
     if C.rank == 0:
-        n = wl["pairs"] * C.world
-        inp = api.parse_image_native(np.tile(synth.uniform_file_bytes(wl["pairs"], wl["R"], wl["Q"], wl["seed"] + 77), C.world))
-        m = api.MultiEngine(n_devices=C.world)
-        params = api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS, **wl["weights"])
-        sc = torch.empty(n, dtype=torch.int32).pin_memory(); rc = torch.empty((n, 2), dtype=torch.int32).pin_memory()
+      try:
+          rec = 2 + wl["R"] + 1 + wl["Q"] + 1
+          per_gpu = min(wl["pairs"], int(0.95 * (1 << 31)) // (rec * C.world))      # the parseInput blob is indexed with ints: < 2 GiB in all
+          n = per_gpu * C.world
+          inp = api.parse_image_native(np.tile(synth.uniform_file_bytes(per_gpu, wl["R"], wl["Q"], wl["seed"] + 77), C.world))
+          m = api.MultiEngine(n_devices=C.world)
+          params = api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS, **wl["weights"])
+          sc = torch.empty(n, dtype=torch.int32).pin_memory(); rc = torch.empty((n, 2), dtype=torch.int32).pin_memory()
 
-        def once():
-            st = m.L.dpx_multi_align_batch(m.h, Ct.byref(params), inp.sequences.ctypes.data, inp.sequences.size, inp.pairs.ctypes.data, n,
-                                           sc.numpy().ctypes.data, rc.numpy().ctypes.data, None, None)
-            if st:
-                raise RuntimeError(m.L.dpx_multi_last_error(m.h))
-        once(); once()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            once()
-        dt = (time.perf_counter() - t0) / steps
-        cells = float(n) * wl["R"] * wl["Q"]
-        side = api.input_sidecar(inp.sequences)
-        # same pairs through one device: identical bytes (multi-GPU invariance)
-        one = C.eng.align_batch(params, inp.sequences, inp.pairs[:200_000])
-        same = bool((one.scores == sc.numpy()[:200_000]).all() and (one.end_row_col == rc.numpy()[:200_000]).all())
-        out = {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "pairs": n, "devices": C.world, "h2d_bytes_per_step": int(side["upload_bytes"]),
-               "d2h_bytes_per_step": 12 * n, "api": "dpx_multi_align_batch (C ABI): one host process, one worker thread + context per GPU, contiguous shards",
-               "identical_to_one_gpu": same}
-        m.close(); inp.free()
-        store.set("dpx_multi_abi_done", "1")
+          def once():
+              st = m.L.dpx_multi_align_batch(m.h, Ct.byref(params), inp.sequences.ctypes.data, inp.sequences.size, inp.pairs.ctypes.data, n,
+                                             sc.numpy().ctypes.data, rc.numpy().ctypes.data, None, None)
+              if st:
+                  raise RuntimeError(m.L.dpx_multi_last_error(m.h))
+          once(); once()
+          t0 = time.perf_counter()
+          for _ in range(steps):
+              once()
+          dt = (time.perf_counter() - t0) / steps
+          cells = float(n) * wl["R"] * wl["Q"]
+          side = api.input_sidecar(inp.sequences)
+          # same pairs through one device: identical bytes (multi-GPU invariance)
+          one = C.eng.align_batch(params, inp.sequences, inp.pairs[:200_000])
+          same = bool((one.scores == sc.numpy()[:200_000]).all() and (one.end_row_col == rc.numpy()[:200_000]).all())
+          out = {"value": cells / dt / 1e9, "unit": "GCUPS", "ms_per_step": dt * 1e3, "pairs": n, "devices": C.world, "h2d_bytes_per_step": int(side["upload_bytes"]),
+                 "d2h_bytes_per_step": 12 * n, "api": "dpx_multi_align_batch (C ABI): one host process, one worker thread + context per GPU, contiguous shards",
+                 "identical_to_one_gpu": same}
+          m.close(); inp.free()
+      except Exception as ex:                                     # never lose the whole line to this leg
+        out = {"error": repr(ex)}
+      store.set("dpx_multi_abi_done", "1")
     C.barrier()
     return out
 

@@ -24,8 +24,10 @@
 // (E, O) slot pair keeps the highest score, then the earliest step (smallest row), then E before O (smaller column);
 // folded into (score, row, col) every 2^(kb-1) steps, lanes merged at the end with the reference's row-major rule.
 //
-// Traceback: one 16-bit field per lane and super-step (2 bits per slot, order E[0..M-1], extra, O[0..M-1], first slot
-// in the highest bits), two steps per 32-bit word, stored [step/2][lane]: one warp store = one 128-byte line.
+// Traceback, densely packed: a lane's 2M regular slots of one super-step are one field of 4M bits (2 bits per slot, order
+// E[0..M-1], O[0..M-1], first slot in the highest bits), SPW = 32 / 4M steps per 32-bit word (band 64: four 8-bit fields),
+// stored [step / SPW][lane]: one warp store = one 128-byte line, 0.25 B per in-band cell with no padding bits.  The 129th
+// diagonal of bands with W == 32M (the extra slot of lane 31) has its own stream after the main one: 16 steps per word.
 // Backtrack: one thread per pair, private shared-memory windows of the traceback refilled warp-synchronously (below).
 #pragma once
 #include "common.cuh"
@@ -41,8 +43,14 @@ struct BandGeom {
         BandGeom g; g.W = W; g.M = W <= 32 ? 1 : (W + 31) / 32; g.extra = (W == 32 * g.M) ? 1 : 0; return g;
     }
     DPX_HD int slots() const { return 2 * M + extra; }
-    DPX_HD int nsteps(int Q, int R) const { const int m = Q < R ? Q : R; return m > 0 ? ((m + W + 1) & ~1) : 0; }   // even
-    DPX_HD unsigned long long words(int Q, int R) const { return (unsigned long long)(nsteps(Q, R) / 2) * 32ull; }
+    DPX_HD int field_bits() const { return 4 * M; }                      // 2 bits x 2M regular slots per lane and step
+    DPX_HD int spw_shift() const { return M == 1 ? 3 : M == 2 ? 2 : 1; } // log2(steps per word): 8 / 4 / 2
+    DPX_HD int spw() const { return 1 << spw_shift(); }
+    DPX_HD int nsteps(int Q, int R) const { const int m = Q < R ? Q : R; return m > 0 ? ((m + W + spw() - 1) & ~(spw() - 1)) : 0; }   // whole words
+    DPX_HD unsigned long long main_words(int Q, int R) const { return (unsigned long long)(nsteps(Q, R) >> spw_shift()) * 32ull; }
+    DPX_HD unsigned long long words(int Q, int R) const {                // + the extra diagonal's stream, 16 steps per word, padded to a 128-byte line
+        return main_words(Q, R) + (extra ? (unsigned long long)((((nsteps(Q, R) + 15) >> 4) + 31) & ~31) : 0ull);
+    }
     DPX_HD int offq() const { return 31 * M; }
     DPX_HD int offr() const { return W; }
     DPX_HD int qs_len(int Qm, int Rm) const { return (nsteps(Qm, Rm) + 31 * M + 2 + 15) & ~15; }
@@ -86,6 +94,8 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr bool PARTIAL = !EXTRA;
     constexpr int Z = 3;
+    constexpr int SPW = M == 1 ? 8 : M == 2 ? 4 : 2;      // super-steps per traceback word
+    constexpr int FB = 4 * M;                             // bits per field
     const int lane = threadIdx.x & 31;
     const int W = a.W;
     const int gadd = a.gadd, zerog = a.zerog, kb = a.kb;
@@ -127,6 +137,8 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
         rw = (rw >> 4) | (nr << (4 * M));                    // window of step 0
         const uint8_t* __restrict__ qp = qsp; const uint8_t* __restrict__ rp = rsp;
         uint32_t* __restrict__ tbw = tbp;
+        uint32_t* __restrict__ tbx = (TB && EXTRA) ? (a.tb + (unsigned long long)pos * a.tb_stride + geo.main_words(Q, R)) : nullptr;   // lane 31's extra diagonal
+        uint32_t accX = 0;
         const uint32_t rsh = 1u << (4 * M);
 
 // After h' is known: Hg = clean(h') + 4g - 2, key = clean(h') * 2^kb + code, and the 2-bit direction joins the step's field.
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
                 const int m1 = __viaddmax_s32(HgX, (int)prmt_b32(scE, 0u, 0x8880u | (M * 0x1111u)), oldOlast);                       \
                 const int h = __vimax3_s32(m1, zerog + 1, Z);                                                        \
                 uint32_t keyX;                                                                                       \
-                DPX_BAND_TAIL(h, HgX, keyX, cE, ACC)                                                                 \
+                DPX_BAND_TAIL(h, HgX, keyX, cE, accX)                                                                \
                 bestX = max(bestX, keyX);                                                                            \
             }                                                                                                        \
             int Urecv = __shfl_down_sync(FULL, HgE[0], 1);                                                           \
@@ -190,13 +202,21 @@ __global__ void __launch_bounds__(128) band_sw_kernel(const BandArgs a) {
         for (int blk0 = 0; blk0 < nsteps; blk0 += SB) {
             const int u_end = min(blk0 + SB, nsteps);
             #pragma unroll 1
-            for (int u = blk0; u < u_end; u += 2) {
-                const int ubase = u;                              // qp / rp walk the streams: constant offsets inside the step pair
-                uint32_t acc0, acc1;
-                DPX_BAND_STEP(u, acc0)
-                DPX_BAND_STEP(u + 1, acc1)
-                qp += 2; rp += 2;
-                if (TB) { __stcs(tbw, acc0 | (acc1 << 16)); tbw += 32; }
+            for (int u = blk0; u < u_end; u += SPW) {
+                const int ubase = u;                              // qp / rp walk the streams: constant offsets inside the step group
+                uint32_t word = 0;
+                #pragma unroll
+                for (int q = 0; q < SPW; ++q) {
+                    uint32_t acc;
+                    DPX_BAND_STEP(u + q, acc)
+                    if (TB) word |= acc << (q * FB);
+                }
+                qp += SPW; rp += SPW;
+                if (TB) {
+                    __stcs(tbw, word); tbw += 32;
+                    // the extra diagonal: 16 steps per word, first step in the highest bits (a last partial word keeps its codes in the low bits)
+                    if (EXTRA && (((u + SPW) & 15) == 0 || u + SPW >= nsteps)) { if (lane == 31) tbx[u >> 4] = accX; accX = 0; }
+                }
             }
             // fold the block's keys into the lane's (score, row, col)
             auto fold = [&](uint32_t key, int m) {
@@ -237,20 +257,24 @@ struct BandBtArgs {
     const int32_t* order;
     int first, count;
     int W;
+    int wshift;                          // log2(walkers per warp): 3, 4 or 5
     const int32_t* scores; const int32_t* end_rc;
     const uint32_t* tb; unsigned long long tb_stride;
     char* strings; const unsigned long long* str_off; int32_t* str_start;
 };
 
 constexpr int BAND_BT_MOVES = 32;                         // moves per round (a move lowers the super-step by <= 1)
-constexpr int BAND_BT_NEED = BAND_BT_MOVES / 2 + 2;       // traceback rows (2 super-steps each) one round can touch
-constexpr int BAND_BT_AHEAD = 2 * BAND_BT_NEED;           // rows requested per round: this round's and the next one's
-constexpr int BAND_BT_RING = 64;                          // rows of the per-walker ring (power of two > BAND_BT_AHEAD)
-constexpr int BAND_BT_LANES = 4;                          // words per row: the aligned group of four owner lanes around the walk (one 16-byte copy)
+constexpr int BAND_BT_RING_MAX = 64;                      // rows of the per-walker ring: a power of two > rows requested per round, 2 * (32 / SPW + 2):
+DPX_HD int band_bt_ring(int M) { return M >= 3 ? 64 : 32; }   //   36 for bands 65..96 (2 steps per row), 20 / 12 below
+constexpr int BAND_BT_LANES = 8;                          // words per row: two aligned groups of four owner lanes, placed so that the walk starts >= 2 lanes
+                                                          // from either edge (the main diagonal of a band 32M sits exactly on a group boundary)
 constexpr int BAND_BT_CRING = 32;                         // words of the per-walker sequence-byte rings (128 bytes each, filled 16 bytes at a time)
 constexpr int BAND_BT_OUT_STRIDE = 3 * BAND_BT_MOVES + 4; // bytes per walker of the output staging (odd word stride: no bank conflicts)
-constexpr int BAND_BT_WIN_WORDS = BAND_BT_RING * BAND_BT_LANES * 32;
-constexpr int BAND_BT_SMEM_WORDS = BAND_BT_WIN_WORDS + 2 * BAND_BT_CRING * 32 + 32 * BAND_BT_OUT_STRIDE / 4;
+// wpw = walkers per warp (8, 16 or 32): the walk is a chain of dependent shared-memory reads, so a few thousand walkers finish
+// sooner spread over MORE, emptier warps (more independent instruction streams); very large batches fill every lane.
+DPX_HD int band_bt_win_words(int M, int wpw) { return band_bt_ring(M) * BAND_BT_LANES * wpw; }
+DPX_HD int band_bt_smem_words(int M, int wpw) { return band_bt_win_words(M, wpw) + 2 * BAND_BT_CRING * wpw + wpw * BAND_BT_OUT_STRIDE / 4; }
+DPX_HD int band_bt_wpw_shift(int count, int sms) { (void)count; (void)sms; return 5; }   // measured (config 4, 10k walkers): 8 per warp 3.36 ms, 32 per warp 3.06 ms
 static_assert(BAND_BT_MOVES == 32, "the flush writes one character per lane");
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
@@ -277,27 +301,25 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ uint32_t bt_smem[];
-    __shared__ uint16_t s_lut[2 * 96 + 2];                       // diagonal c -> owner lane | bit position << 8
     const int lane = threadIdx.x;
-    const int t = blockIdx.x * 32 + lane;
-    const bool live = t < a.count;
+    const int wshift = a.wshift, wpw = 1 << wshift;
+    const int t = blockIdx.x * wpw + lane;
+    const bool live = lane < wpw && t < a.count;
     const int W = a.W;
     const BandGeom geo = BandGeom::make(W);
-    const int M = geo.M, S = geo.slots();
-    for (int c = lane; c <= 2 * W; c += 32) {
-        const int k = c >> 1, isO = c & 1;
-        const int owner = min(k / M, 31);
-        const int slot = isO ? (M + geo.extra + (k - owner * M)) : (k - owner * M);      // processing order E.., extra, O..
-        s_lut[c] = (uint16_t)(owner | ((2 * (S - 1 - slot)) << 8));
-    }
-    __syncwarp();
-    uint32_t* win = bt_smem + lane * 4;                          // [row & 63][lane][4 words]: one 16-byte cp.async per row
-    uint32_t* rring = bt_smem + BAND_BT_WIN_WORDS + lane * 4;    // [(16-byte block address) & 7][lane][4 words]
-    uint32_t* qring = rring + BAND_BT_CRING * 32;
-    char* outw = reinterpret_cast<char*>(bt_smem + BAND_BT_WIN_WORDS + 2 * BAND_BT_CRING * 32);
-    char* out = outw + lane * BAND_BT_OUT_STRIDE;                // this walker's 3 x MOVES characters, filled from the back
+    const int M = geo.M;
+    const int rsh = geo.spw_shift(), FB = geo.field_bits(), spw_mask = geo.spw() - 1;
+    const int need_rows = (BAND_BT_MOVES >> rsh) + 2;            // traceback rows (SPW super-steps each) one round can touch
+    const int ahead_rows = 2 * need_rows;                        // rows requested per round: this round's and the next one's
+    const int ring_mask = band_bt_ring(geo.M) - 1, win_words = band_bt_win_words(geo.M, wpw);
+    const int wl_ = lane & (wpw - 1);                            // idle lanes (>= wpw) alias a live walker's slots but never touch them
+    uint32_t* win = bt_smem + wl_ * BAND_BT_LANES;               // [row & ring_mask][walker][8 words]: two 16-byte cp.async per row
+    uint32_t* rring = bt_smem + win_words + wl_ * 4;             // [(16-byte block address) & 7][walker][4 words]
+    uint32_t* qring = rring + BAND_BT_CRING * wpw;
+    char* outw = reinterpret_cast<char*>(bt_smem + win_words + 2 * BAND_BT_CRING * wpw);
+    char* out = outw + wl_ * BAND_BT_OUT_STRIDE;                 // this walker's 3 x MOVES characters, filled from the back
     const uintptr_t blob_lo = (uintptr_t)a.blob_lo;
-    const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(s_lut), win_s = (uint32_t)__cvta_generic_to_shared(win);
+    const uint32_t win_s = (uint32_t)__cvta_generic_to_shared(win);
     const uint32_t rring_s = (uint32_t)__cvta_generic_to_shared(rring), qring_s = (uint32_t)__cvta_generic_to_shared(qring);
     const uint32_t out_s = (uint32_t)__cvta_generic_to_shared(out);
 
@@ -320,28 +342,35 @@ __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
     // walk state: diagonal c = j - i + W and super-step u = i + (c >> 1) - 1 move incrementally:
     //   DIAG: u-1;   UP: c+1, u-1 if c is even;   LEFT: c-1, u-1 if c is even
     int c = j - i + W, u = i + (c >> 1) - 1;
+    int nsteps_w = 0;
+    const uint32_t* tbx = nullptr;                               // the extra diagonal's stream of this pair
+    if (live) { const dpx_seq_pair pr = a.pairs[pid]; nsteps_w = geo.nsteps(pr.querySize, pr.referenceSize); tbx = tb + geo.main_words(pr.querySize, pr.referenceSize); }
     int lane_lo = -100, row_loaded = 0;                          // rows [row_loaded, ...) of lanes lane_lo..lane_lo+2 are requested
     uintptr_t r_loaded = 0, q_loaded = 0;                        // word addresses [x_loaded, ...) are requested
 
     while (__any_sync(FULL, !done)) {
         if (!done) {
             bool fresh = false;
-            const int row_hi = u >> 1;
-            const int owner = (int)(s_lut[c] & 0xff);
-            if ((unsigned)(owner - lane_lo) >= (unsigned)BAND_BT_LANES) {        // first round, or the walk left the window
-                lane_lo = owner & ~3;
-                row_loaded = row_hi + 1; fresh = true;
+            const int row_hi = u >> rsh;
+            const int owner = min((c >> 1) / M, 31);                             // (on the extra diagonal: keep lane 31's group warm)
+            if ((unsigned)(owner - lane_lo - 1) >= (unsigned)(BAND_BT_LANES - 2)) {   // first round, or the walk reached an edge lane of the window
+                const int lo = min(max((owner - 2) & ~3, 0), 32 - BAND_BT_LANES);
+                if (lo != lane_lo) { lane_lo = lo; row_loaded = row_hi + 1; fresh = true; }
             }
-            const int row_to = max(row_hi - (BAND_BT_AHEAD - 1), 0);
-            for (int row = row_loaded - 1; row >= row_to; --row) cp_async16(win + (row & (BAND_BT_RING - 1)) * 128, tb + (size_t)row * 32 + lane_lo);
+            const int row_to = max(row_hi - (ahead_rows - 1), 0);
+            for (int row = row_loaded - 1; row >= row_to; --row) {
+                uint32_t* dst = win + (row & ring_mask) * (wpw * BAND_BT_LANES);
+                cp_async16(dst, tb + (size_t)row * 32 + lane_lo);
+                cp_async16(dst + 4, tb + (size_t)row * 32 + lane_lo + 4);
+            }
             row_loaded = min(row_loaded, row_to);
             // sequence bytes [j - 2*MOVES, j) and [i - 2*MOVES, i) as aligned words, never below the start of the blob allocation
             const uintptr_t r_hi = ((uintptr_t)(ref + j - 1)) & ~(uintptr_t)15, q_hi = ((uintptr_t)(qry + i - 1)) & ~(uintptr_t)15;
             const uintptr_t r_to = max(((uintptr_t)(ref + j) - 2 * BAND_BT_MOVES) & ~(uintptr_t)15, blob_lo);
             const uintptr_t q_to = max(((uintptr_t)(qry + i) - 2 * BAND_BT_MOVES) & ~(uintptr_t)15, blob_lo);
             if (r_loaded == 0) { r_loaded = r_hi + 16; q_loaded = q_hi + 16; fresh = true; }
-            for (uintptr_t x = r_loaded; x > r_to; ) { x -= 16; cp_async16(rring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * 128, (const void*)x); }
-            for (uintptr_t x = q_loaded; x > q_to; ) { x -= 16; cp_async16(qring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * 128, (const void*)x); }
+            for (uintptr_t x = r_loaded; x > r_to; ) { x -= 16; cp_async16(rring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * (4 * wpw), (const void*)x); }
+            for (uintptr_t x = q_loaded; x > q_to; ) { x -= 16; cp_async16(qring + ((x >> 4) & (BAND_BT_CRING / 4 - 1)) * (4 * wpw), (const void*)x); }
             r_loaded = min(r_loaded, r_to); q_loaded = min(q_loaded, q_to);
             cp_async_commit();
             if (fresh) cp_async_wait<0>(); else cp_async_wait<1>();
@@ -351,18 +380,32 @@ __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
         //   lut -> window word -> code -> next (c, u);  the two sequence bytes and the three stores hang off the side
         int cnt = 0;
         uint32_t rpos = (uint32_t)(uintptr_t)(ref + j - 1), qpos = (uint32_t)(uintptr_t)(qry + i - 1);   // low address bits index the rings
+        // The traceback word of (row, owner lane) serves SPW consecutive diagonal moves: it is kept in a register and re-read from the
+        // window only when the walk changes row or owner (key_cached); owner and bit position come from arithmetic on c, not a table.
+        uint32_t w_cached = 0, key_cached = 0xffffffffu;
         #pragma unroll 1
         for (int mv = 0; mv < BAND_BT_MOVES; ++mv) {
-            if (__all_sync(FULL, done)) break;
             if (done) continue;
-            const uint32_t e = lds_u16(lut_s + 2u * (uint32_t)c);
-            const uint32_t wl = (e & 0xffu) - (uint32_t)lane_lo;
-            const uint32_t w = (wl < (uint32_t)BAND_BT_LANES) ? lds_u32(win_s + ((((uint32_t)u >> 1) & (BAND_BT_RING - 1)) << 9) + 4u * wl)
-                                                              : __ldg(tb + (size_t)(u >> 1) * 32 + (e & 0xffu));
-            const uint32_t code = (w >> (((uint32_t)u & 1u) * 16u + (e >> 8))) & 3u;
+            const uint32_t k = (uint32_t)c >> 1, isO = (uint32_t)c & 1u;
+            const uint32_t owner = (M == 2) ? (k >> 1) : (M == 1) ? k : k / 3u;
+            const uint32_t slot = isO * (uint32_t)M + (k - owner * (uint32_t)M);
+            uint32_t code;
+            if (owner > 31u) {                                                   // the extra diagonal (j - i == W): its own stream, 16 steps per word
+                const int nleft = min(16, nsteps_w - (u & ~15));
+                code = (__ldg(tbx + (u >> 4)) >> (2 * (nleft - 1 - (u & 15)))) & 3u;
+            } else {
+                const uint32_t row = (uint32_t)u >> rsh, key = (row << 5) | owner;
+                if (key != key_cached) {
+                    const uint32_t wl = owner - (uint32_t)lane_lo;
+                    w_cached = (wl < (uint32_t)BAND_BT_LANES) ? lds_u32(win_s + ((row & (uint32_t)ring_mask) << (5 + wshift)) + 4u * wl)
+                                                              : __ldg(tb + (size_t)row * 32 + owner);
+                    key_cached = key;
+                }
+                code = (w_cached >> (((uint32_t)u & (uint32_t)spw_mask) * (uint32_t)FB + 2u * (2u * (uint32_t)M - 1u - slot))) & 3u;
+            }
             if (code == BD_STOP) { done = 1; continue; }
-            const uint32_t rc = lds_u8(rring_s + ((rpos & 0x70u) << 5) + (rpos & 15u));
-            const uint32_t qc = lds_u8(qring_s + ((qpos & 0x70u) << 5) + (qpos & 15u));
+            const uint32_t rc = lds_u8(rring_s + ((rpos & 0x70u) << wshift) + (rpos & 15u));
+            const uint32_t qc = lds_u8(qring_s + ((qpos & 0x70u) << wshift) + (qpos & 15u));
             ++cnt;
             const uint32_t o = out_s + (uint32_t)(BAND_BT_MOVES - cnt);
             sts_u8(o, (code == BD_UP) ? (uint32_t)'_' : rc);
@@ -378,7 +421,7 @@ __global__ void __launch_bounds__(32) band_bt_kernel(const BandBtArgs a) {
         // flush: the warp writes every walker's new characters with coalesced byte stores (positions [p - cnt, p) of each field)
         p -= cnt;
         #pragma unroll 4
-        for (int w = 0; w < 32; ++w) {
+        for (int w = 0; w < wpw; ++w) {
             const int n = __shfl_sync(FULL, cnt, w);
             if (n == 0) continue;
             const char* src = outw + w * BAND_BT_OUT_STRIDE + (BAND_BT_MOVES - n);

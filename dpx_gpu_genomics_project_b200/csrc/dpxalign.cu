@@ -136,7 +136,13 @@ struct dpx_ctx {
     int32_t* boundary[4] = {nullptr, nullptr, nullptr, nullptr}; size_t boundary_ints[4] = {0, 0, 0, 0};
     unsigned int* counters = nullptr;              // 64 dynamic-work counters per lane
     size_t tb_budget_bytes = (size_t)16 << 30;     // traceback chunk budget
+    // recycled CUDA events (creating / destroying ~10 events per chunk of the one-call pipeline was a measurable share of its
+    // host time, and with several contexts in one process those calls serialise on the driver's lock)
+    std::vector<cudaEvent_t> ev_pool_timing, ev_pool_plain;
+    // per kernel: shared-memory attribute already raised, and occupancy per dynamic shared-memory size
+    std::unordered_map<const void*, std::map<size_t, int>> occ_cache;
     int chunks = 12;                               // one-call pipeline: equal middle chunks (dpx_set_option "chunks")
+    int chunks_packed = 12;                        // ... when the input comes from the packed sidecar (kernel-bound: fewer, larger chunks)
     bool counted = false;                          // registered in g_live_ctx (dpx_create succeeded)
 };
 
@@ -187,12 +193,36 @@ struct dpx_batch {
 };
 
 // Kernels always get the opt-in ceiling (minus their static shared memory) as MaxDynamicSharedMemorySize: see dpx_ctx::smem_optin.
+// Done once per kernel and context (the attribute never changes afterwards).
 template <typename F>
-static cudaError_t max_dyn_smem(const dpx_ctx* ctx, F kern) {
+static cudaError_t max_dyn_smem(dpx_ctx* ctx, F kern) {
+    if (ctx->occ_cache.count((const void*)kern)) return cudaSuccess;
     cudaFuncAttributes fa;
-    const cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+    cudaError_t e = cudaFuncGetAttributes(&fa, kern);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - (int)fa.sharedSizeBytes);
+    if (e == cudaSuccess) ctx->occ_cache[(const void*)kern];
+    return e;
+}
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor, remembered per (kernel, dynamic shared memory)
+template <typename F>
+static cudaError_t occupancy(dpx_ctx* ctx, int* per_sm, F kern, int threads, size_t smem) {
+    auto& m = ctx->occ_cache[(const void*)kern];
+    auto it = m.find(smem);
+    if (it != m.end()) { *per_sm = it->second; return cudaSuccess; }
+    const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, threads, smem);
+    if (e == cudaSuccess) m[smem] = *per_sm;
+    return e;
+}
+static cudaError_t ev_get(dpx_ctx* ctx, cudaEvent_t* ev, bool timing) {
+    auto& pool = timing ? ctx->ev_pool_timing : ctx->ev_pool_plain;
+    if (!pool.empty()) { *ev = pool.back(); pool.pop_back(); return cudaSuccess; }
+    return timing ? cudaEventCreate(ev) : cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+}
+static void ev_put(dpx_ctx* ctx, cudaEvent_t ev, bool timing) {
+    if (!ev) return;
+    auto& pool = timing ? ctx->ev_pool_timing : ctx->ev_pool_plain;
+    if (pool.size() < 256) pool.push_back(ev); else cudaEventDestroy(ev);
 }
 
 #define CU(call)                                                                                   \
@@ -266,6 +296,8 @@ void dpx_destroy(dpx_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->pool.clear_all();
+    for (auto e : ctx->ev_pool_timing) cudaEventDestroy(e);
+    for (auto e : ctx->ev_pool_plain) cudaEventDestroy(e);
     for (int l = 0; l < 4; ++l) { if (ctx->boundary[l]) cudaFree(ctx->boundary[l]); if (ctx->h_info[l]) cudaFreeHost(ctx->h_info[l]); }
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -299,6 +331,7 @@ int dpx_set_option(dpx_ctx* ctx, const char* name, long long value) {
     else if (k == "trace") o.trace = value != 0;
     else if (k == "no_sidecar") o.no_sidecar = value != 0;
     else if (k == "chunks") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks = (int)value; }
+    else if (k == "chunks_packed") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks_packed = (int)value; }
     else if (k == "tb_budget_bytes") { if (value < (1 << 16)) return DPX_ERR_INVALID; ctx->tb_budget_bytes = (size_t)value; }
     else { ctx->err = "unknown option: " + k; return DPX_ERR_INVALID; }
     return DPX_OK;
@@ -473,11 +506,9 @@ static void batch_release(dpx_batch* b) {
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
     P.release(b->d_stage[0]); P.release(b->d_stage[1]);
     P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
-    for (auto e : b->ev) cudaEventDestroy(e);
-    for (auto e : b->ev_sync) cudaEventDestroy(e);
-    if (b->ev_begin) cudaEventDestroy(b->ev_begin);
-    if (b->ev_end) cudaEventDestroy(b->ev_end);
-    if (b->ev_h2d) cudaEventDestroy(b->ev_h2d);
+    for (auto e : b->ev) ev_put(b->ctx, e, true);
+    for (auto e : b->ev_sync) ev_put(b->ctx, e, false);
+    ev_put(b->ctx, b->ev_begin, true); ev_put(b->ctx, b->ev_end, true); ev_put(b->ctx, b->ev_h2d, false);
     delete b;
 }
 
@@ -499,10 +530,10 @@ static int batch_begin(dpx_ctx* ctx, cudaStream_t st, int lane, const char* sequ
     if (!pool_alloc(ctx, &b->d_blob_alloc, nb + 16) || !pool_alloc(ctx, &b->d_pairs, n_pairs) ||
         !pool_alloc(ctx, &b->d_scores, n_pairs) || !pool_alloc(ctx, &b->d_end_rc, 2 * n_pairs)) return fail(DPX_ERR_NOMEM);
     b->d_blob = b->d_blob_alloc - byte_lo;
-    CUB_(cudaEventCreate(&b->ev_begin)); CUB_(cudaEventCreate(&b->ev_end));
+    CUB_(ev_get(ctx, &b->ev_begin, true)); CUB_(ev_get(ctx, &b->ev_end, true));
     if (n_pairs == 0) { *out = b; return DPX_OK; }
     // inputs cross PCIe on the context's single copy stream (chunks arrive in issue order); the lane waits on the event
-    CUB_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    CUB_(ev_get(ctx, &b->ev_h2d, false));
     if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
     CUB_(cudaMemcpyAsync(b->d_pairs, pairs, n_pairs * sizeof(dpx_seq_pair), cudaMemcpyHostToDevice, ctx->copy_stream));
     CUB_(cudaEventRecord(b->ev_h2d, ctx->copy_stream));
@@ -591,8 +622,8 @@ static int batch_known_copy(dpx_ctx* ctx, cudaStream_t st, int lane, const char*
         !pool_alloc(ctx, &b->d_scores, n_pairs) || !pool_alloc(ctx, &b->d_end_rc, 2 * n_pairs) ||
         !pool_alloc(ctx, &b->d_packed, (size_t)b->info.packed_words + 1)) return fail(DPX_ERR_NOMEM);
     b->d_blob = b->d_blob_alloc - byte_lo;
-    CUB_(cudaEventCreate(&b->ev_begin)); CUB_(cudaEventCreate(&b->ev_end));
-    CUB_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    CUB_(ev_get(ctx, &b->ev_begin, true)); CUB_(ev_get(ctx, &b->ev_end, true));
+    CUB_(ev_get(ctx, &b->ev_h2d, false));
     if (nb) CUB_(cudaMemcpyAsync(b->d_blob_alloc, sequences + byte_lo, nb, cudaMemcpyHostToDevice, ctx->copy_stream));
     if (stride > 0) {
         regular_pairs_kernel<<<(int)((n_pairs + 255) / 256), 256, 0, st>>>(b->d_pairs, (int)n_pairs, pairs[0], (int)stride);
@@ -671,8 +702,8 @@ static int batch_from_sidecar(dpx_ctx* ctx, cudaStream_t st, int lane, const dpx
         (ragged && (!pool_alloc(ctx, &d_sizes, sz_words) || !pool_alloc(ctx, &d_woff, n + 1)))) { ctx->pool.release(d_sizes); ctx->pool.release(d_woff); return fail(DPX_ERR_NOMEM); }
     auto fail2 = [&](int s) { cudaStreamSynchronize(st); cudaStreamSynchronize(ctx->copy_stream); ctx->pool.release(d_sizes); ctx->pool.release(d_woff); batch_release(b); return s; };
 #define CUS_(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail2(e__ == cudaErrorMemoryAllocation ? DPX_ERR_NOMEM : DPX_ERR_CUDA); } } while (0)
-    CUS_(cudaEventCreate(&b->ev_begin)); CUS_(cudaEventCreate(&b->ev_end));
-    CUS_(cudaEventCreateWithFlags(&b->ev_h2d, cudaEventDisableTiming));
+    CUS_(ev_get(ctx, &b->ev_begin, true)); CUS_(ev_get(ctx, &b->ev_end, true));
+    CUS_(ev_get(ctx, &b->ev_h2d, false));
     if (nw) CUS_(cudaMemcpyAsync(b->d_packed, sc->words + w0, nw * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
     if (ragged) {
         CUS_(cudaMemcpyAsync(d_sizes, sc->sizes + p0 * (sc->small ? 1 : 2), sz_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -764,7 +795,7 @@ int dpx_batch_upload_image(dpx_ctx* ctx, const char* image, size_t n_bytes, dpx_
 #define CUI_(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__); return fail(e__ == cudaErrorMemoryAllocation ? DPX_ERR_NOMEM : DPX_ERR_CUDA); } } while (0)
     if (!pool_alloc(ctx, &b->d_blob_alloc, n_bytes + 16)) return fail(DPX_ERR_NOMEM);
     b->d_blob = b->d_blob_alloc;
-    CUI_(cudaEventCreate(&b->ev_begin)); CUI_(cudaEventCreate(&b->ev_end));
+    CUI_(ev_get(ctx, &b->ev_begin, true)); CUI_(ev_get(ctx, &b->ev_end, true));
     int n_lines = 0;
     if (n_bytes) {
         CUI_(cudaMemcpyAsync(b->d_blob_alloc, image, n_bytes, cudaMemcpyHostToDevice, st));
@@ -991,7 +1022,11 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     CU(cudaSetDevice(ctx->device));
     const bool want_strings = (params->flags & DPX_OUT_STRINGS) != 0;
     const size_t min_chunk = 32768;
-    size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)ctx->chunks, n_pairs / min_chunk);
+    // Registered input (parser output / dpx_register_input): every chunk uploads its slice of the host-side 2-bit sidecar --
+    // a quarter of the bytes, no device pass, no alphabet handshake with chunk 0.
+    size_t sc_first = 0;
+    const dpxhost_pack::Sidecar* sc = (ctx->opt.no_sidecar || want_strings || n_pairs == 0) ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
+    size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)(sc ? ctx->chunks_packed : ctx->chunks), n_pairs / min_chunk);
     if (nbase <= 1) {
         dpx_batch* b = nullptr;
         int st = dpx_batch_upload(ctx, sequences, n_bytes, pairs, n_pairs, &b);
@@ -1034,10 +1069,6 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     if (!pool_alloc(ctx, &d_unknown, 1)) return DPX_ERR_NOMEM;
     CU(cudaMemsetAsync(d_unknown, 0, sizeof(int), ctx->copy_stream));
 
-    // Registered input (parser output / dpx_register_input): every chunk uploads its slice of the host-side 2-bit sidecar --
-    // a quarter of the bytes, no device pass, no alphabet handshake with chunk 0.
-    size_t sc_first = 0;
-    const dpxhost_pack::Sidecar* sc = ctx->opt.no_sidecar ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
     for (size_t c = 0; sc && c < nchunks; ++c)
         if (16ull * (unsigned long long)(sc->woff[sc_first + bound[c + 1]] - sc->woff[sc_first + bound[c]]) + 16ull > 0x7fffffffull) sc = nullptr;
 

@@ -6,7 +6,7 @@
 template <int ALGO, bool TB, int K>
 static int query_wf(dpx_ctx* ctx, int slots_wanted, int* blocks_out) {
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_fill_kernel<ALGO, TB, K>, 128, 0));
+    CU(occupancy(ctx, &per_sm, wf_fill_kernel<ALGO, TB, K>, 128, 0));
     if (per_sm < 1) per_sm = 1;
     int blocks = std::min(ctx->sm_count * per_sm, (slots_wanted + 3) / 4);
     *blocks_out = std::max(blocks, 1);
@@ -40,7 +40,7 @@ static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xorm
     auto launch = [&](auto kern) -> int {
         CU(max_dyn_smem(ctx, kern));
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+        CU(occupancy(ctx, &per_sm, kern, 128, smem));
         if (per_sm < 1) { ctx->err = "short-read kernel does not fit on an SM"; return DPX_ERR_RANGE; }
         const int warps_needed = (a.n_slots + (32 / G) - 1) / (32 / G);
         int blocks = std::min(ctx->sm_count * per_sm, (warps_needed + 3) / 4);
@@ -158,7 +158,7 @@ static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_
     auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND, WIDE>;
     CU(max_dyn_smem(ctx, kern));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    CU(occupancy(ctx, &per_sm, kern, 128, smem));
     if (per_sm < 1) { ctx->err = "pair-wavefront kernel does not fit on an SM"; return DPX_ERR_RANGE; }
     const int blocks = std::max(1, std::min(ctx->sm_count * per_sm, (n_slots + 3) / 4));
     kern<<<blocks, 128, smem, st>>>(a);
@@ -199,7 +199,7 @@ template <int M, bool EXTRA>
 static int launch_band(dpx_ctx* ctx, cudaStream_t st, const BandArgs& a, bool tb) {
     auto go = [&](auto kern) -> int {
         int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0));
+        CU(occupancy(ctx, &per_sm, kern, 128, 0));
         const int blocks = std::max(1, std::min(ctx->sm_count * std::max(per_sm, 1), (a.count + 3) / 4));
         kern<<<blocks, 128, 0, st>>>(a);
         CU(cudaGetLastError());
@@ -229,8 +229,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     const size_t n = b->n_pairs;
     b->params = *p; b->ran = true;
     b->stats = dpx_run_stats{};
-    for (auto e : b->ev) cudaEventDestroy(e);
-    for (auto e : b->ev_sync) cudaEventDestroy(e);
+    for (auto e : b->ev) ev_put(ctx, e, true);
+    for (auto e : b->ev_sync) ev_put(ctx, e, false);
     b->ev.clear(); b->ev_kind.clear(); b->ev_sync.clear();
     const bool want_strings = (p->flags & DPX_OUT_STRINGS) != 0;
     const int algo = p->algo;
@@ -254,7 +254,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
     CU(cudaEventRecord(b->ev_begin, st));
 
     auto add_event_pair = [&](int kind, cudaEvent_t* s, cudaEvent_t* e) -> int {
-        CU(cudaEventCreate(s)); CU(cudaEventCreate(e));
+        CU(ev_get(ctx, s, true)); CU(ev_get(ctx, e, true));
         b->ev.push_back(*s); b->ev.push_back(*e); b->ev_kind.push_back(kind);
         return DPX_OK;
     };
@@ -325,7 +325,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             // overlaps the head of the next), walks run on a third
             cudaStream_t bt_st = nbuf > 1 ? ctx->aux_stream[0] : st;
             cudaStream_t fill2_st = nbuf > 1 ? ctx->aux_stream[1] : st;
-            auto sync_event = [&](cudaEvent_t* ev) -> int { CU(cudaEventCreateWithFlags(ev, cudaEventDisableTiming)); b->ev_sync.push_back(*ev); return DPX_OK; };
+            auto sync_event = [&](cudaEvent_t* ev) -> int { CU(ev_get(ctx, ev, false)); b->ev_sync.push_back(*ev); return DPX_OK; };
             std::vector<cudaEvent_t> bt_done, fill_done;
             if (nbuf > 1) {
                 b->used_aux = true;
@@ -465,9 +465,11 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     t.strings = b->d_strings; t.str_off = b->d_str_off; t.str_start = b->d_str_start;
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, st));
-                    const size_t bt_smem = (size_t)BAND_BT_SMEM_WORDS * sizeof(uint32_t);
+                    t.wshift = band_bt_wpw_shift(a.count, ctx->sm_count);
+                    const int wpw = 1 << t.wshift;
+                    const size_t bt_smem = (size_t)band_bt_smem_words(geo.M, wpw) * sizeof(uint32_t);
                     CU(max_dyn_smem(ctx, band_bt_kernel));
-                    band_bt_kernel<<<(a.count + 31) / 32, 32, bt_smem, st>>>(t);
+                    band_bt_kernel<<<(a.count + wpw - 1) / wpw, 32, bt_smem, st>>>(t);
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, st));
                     b->stats.kernel_launches++;

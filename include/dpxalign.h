@@ -112,7 +112,7 @@ const char* dpx_last_error(const dpx_ctx* ctx);
 int         dpx_set_stream(dpx_ctx* ctx, void* cuda_stream);
 
 /* Debug / test knobs (the library never reads the environment).  Unknown names return DPX_ERR_INVALID.
- *   "chunks" (1..64)         equal middle chunks of the one-call pipeline          "tb_budget_bytes"  traceback slab budget
+ *   "chunks" / "chunks_packed" (1..64)  middle chunks of the one-call pipeline (raw / sidecar input)   "tb_budget_bytes"  traceback slab budget
  *   "serial_chunks" 0/1      traceback chunks in series on one buffer              "trace" 0/1        chunk timeline on stderr
  *   "no_sidecar" 0/1         ignore the parser's packed copy, upload raw bytes     "no_shortread" / "no_pairwf" / "no_bandkernel" /
  *   "pairwf_int32" 0/1       kernel selection overrides (fall back to the next kernel family; still CUDA, never the CPU)

@@ -59,7 +59,7 @@ WORKLOADS = {
             title="LinearNeedlemanWunsch batch (substitute for the missing bundled pairs): {pairs} pairs, R ~ U[100,300], query = reference mutated "
                   "5 % / 2 % / 2 %, 2-bit traceback + alignment strings, match 3 / mismatch -1 / gap -2", cpu_per_core=0.05e9, tb_bytes_per_cell=0.25),
     2: dict(algo="LSW", R=150, Q=150, pairs=1_000_000, weights=dict(match=3, mismatch=-1, gap_open=-2), strings=False, seed=0x5EED0002,
-            gen="uniform", dtype="int16x2", kernel="sr_lsw_kernel<G=8,K=19>", sass="shortread_s16x2:G=8,K=19,track={track},xormode=False",
+            gen="uniform", dtype="int16x2", kernel="sr_lsw_kernel<G=8,K=19>", sass="shortread_s16x2:G=8,K=19,track={track},wide=False",
             title="LinearSmithWaterman batch: {pairs} pairs x (150x150) bp per GPU, score{ends}, match 3 / mismatch -1 / gap -2",
             cpu_per_core=0.045e9),
     3: dict(algo="ANW", R=1000, Q=1000, pairs=100_000, weights=dict(match=3, mismatch=-1, gap_open=-3, gap_extend=-1), strings=True, seed=0x5EED0003,

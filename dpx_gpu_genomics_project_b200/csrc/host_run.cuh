@@ -32,7 +32,7 @@ static int dispatch_wf(dpx_ctx* ctx, cudaStream_t st, int algo, bool tb, int K, 
 }
 
 template <int G, int K>
-static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xormode) {
+static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool wide) {
     const int gpb = 128 / G;
     a.bnd_stride = b->max_r + G + 2;
     a.rsel_stride = (b->max_r + 2 * G + 18 + 1) & ~1;          // the table is written 16 entries (one packed word) at a time
@@ -42,20 +42,22 @@ static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool xorm
         int per_sm = 0;
         CU(occupancy(ctx, &per_sm, kern, 128, smem));
         if (per_sm < 1) { ctx->err = "short-read kernel does not fit on an SM"; return DPX_ERR_RANGE; }
-        const int warps_needed = (a.n_slots + (32 / G) - 1) / (32 / G);
+        const int warps_needed = (a.n_slots + (32 / G) - 1) / (32 / G);   // (n_slots: pair duos, or single pairs in WIDE mode)
         int blocks = std::min(ctx->sm_count * per_sm, (warps_needed + 3) / 4);
         if (blocks < 1) blocks = 1;
         kern<<<blocks, 128, smem, b->stream>>>(a);
         CU(cudaGetLastError());
         return DPX_OK;
     };
-    if (track) return xormode ? launch(sr_lsw_kernel<G, K, true, true>) : launch(sr_lsw_kernel<G, K, true, false>);
-    return xormode ? launch(sr_lsw_kernel<G, K, false, true>) : launch(sr_lsw_kernel<G, K, false, false>);
+    if (track) return wide ? launch(sr_lsw_kernel<G, K, true, true>) : launch(sr_lsw_kernel<G, K, true, false>);
+    return wide ? launch(sr_lsw_kernel<G, K, false, true>) : launch(sr_lsw_kernel<G, K, false, false>);
 }
 
 // Eligibility of the packed int16x2 short-read kernel (shortread.cuh).
-static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, bool* xormode, int* kbits_out) {
-    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || !b->packed2 || b->ctx->opt.no_shortread) return false;
+static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, bool* wide, int* kbits_out) {
+    // <= 4 symbols: the 2-bit packed batch, two pairs per lane group; 5..8 symbols (byte codes present): one pair per group (WIDE)
+    const bool w = !b->packed2 && b->d_codes != nullptr;
+    if (p->algo != DPX_ALGO_LSW || (p->flags & DPX_OUT_STRINGS) || (!b->packed2 && !w) || b->ctx->opt.no_shortread) return false;
     const int m = p->match, x = p->mismatch, g = p->gap_open;
     if (!(m > 0 && x < 0 && g < 0)) return false;                 // pads must stay strictly below real cells
     if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
@@ -70,7 +72,7 @@ static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, 
     while (k < 8 && (top << (k + 1)) < 32768) ++k;
     if (k < 3) return false;                  // below that the fold every 2^(k-1) steps costs more than it saves
     if (((long long)b->max_r + 16) >> (k - 1) >= 255) return false;
-    *B_out = B; *xormode = (x - g < 0); *kbits_out = k;
+    *B_out = B; *wide = w; *kbits_out = k;
     return true;
 }
 
@@ -261,19 +263,15 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
 
     // ---- short-read path: packed int16x2 DPX kernel (score / end cell only) -------------------------
     {
-        int B = 0, kbits = 0; bool xormode = false;
-        if (short_eligible(b, p, &B, &xormode, &kbits)) {
+        int B = 0, kbits = 0; bool wide = false;
+        if (short_eligible(b, p, &B, &wide, &kbits)) {
             const int g = p->gap_open;
             SrArgs sa{};
             sa.packed = b->d_packed; sa.pk_off = b->d_pk_off; sa.pk_stride = b->pk_stride;
             sa.pairs = b->d_pairs; sa.order = b->d_order;
-            sa.n_pairs = (int)n; sa.n_slots = (int)((n + 1) / 2);
+            sa.codes = wide ? b->d_codes : nullptr;
+            sa.n_pairs = (int)n; sa.n_slots = wide ? (int)n : (int)((n + 1) / 2);
             const int ms = p->match - g, xs = p->mismatch - g;
-            uint8_t tab[8];
-            for (int k = 0; k < 8; ++k) tab[k] = (uint8_t)(int8_t)xs;
-            tab[xormode ? 0 : 3] = (uint8_t)(int8_t)ms;
-            sa.lut_lo = tab[0] | tab[1] << 8 | tab[2] << 16 | (uint32_t)tab[3] << 24;
-            sa.lut_hi = tab[4] | tab[5] << 8 | tab[6] << 16 | (uint32_t)tab[7] << 24;
             sa.ms_byte = (uint32_t)(ms & 0xff); sa.xs_byte = (uint32_t)(xs & 0xff);
             auto pk = [](int v) { return (uint32_t)(v & 0xffff) | ((uint32_t)(v & 0xffff) << 16); };
             sa.one = 1u; sa.kbits = kbits; sa.kmul = 1u << kbits; sa.B = B; sa.B2 = pk(B); sa.Bg2 = pk(B + g);
@@ -286,8 +284,8 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             { int r = add_event_pair(0, &s, &e); if (r) return r; }
             CU(cudaEventRecord(s, st));
             int r;
-            if (b->max_q <= 64) r = run_short<8, 8>(ctx, b, sa, track, xormode);
-            else                r = run_short<8, 19>(ctx, b, sa, track, xormode);
+            if (b->max_q <= 64) r = run_short<8, 8>(ctx, b, sa, track, wide);
+            else                r = run_short<8, 19>(ctx, b, sa, track, wide);
             if (r) return r;
             CU(cudaEventRecord(e, st));
             b->stats.kernel_launches = 1;

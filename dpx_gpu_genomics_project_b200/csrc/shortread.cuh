@@ -11,10 +11,10 @@
 // take several passes with the last lane's row handed over through a per-group shared-memory row.
 //
 // Arithmetic (per cell-pair; measured pipe model in profiles/: ALU/DPX 64 lanes/clk/SM, FMA pipe another 64):
-//   x   = qsel + rsel                  nibble-wise q + (3 - r): equals 3 iff the bases match   (IADD, either pipe)
-//                                      [XORMODE: x = qsel ^ rsel, 0 iff match — LOP3, ALU only; used when
-//                                       mismatch - gap < 0 so the table needs the sign-replicating selector]
-//   s   = prmt(LUT, x)                 8-entry byte table -> packed (score - gap) per int16 half (ALU)
+//   s   = prmt(ta[r], tb[r], rsel)     per-row tables: byte c of ta / tb = (score - gap) of this row's base against reference code c
+//                                      for pair A / pair B; the column's selector picks both and sign-extends them (ALU)
+//   [WIDE: alphabets of 5..8 symbols -- the reference's data sets use '0'..'4' -- need all eight bytes of (ta, tb) for ONE pair:
+//    a slot then holds one pair (its scores ride in the low halves, the high halves idle) and sequences are read as byte codes]
 //   e   = __viaddmax_s16x2(diag, s, left) max(diag + s, left)   — independent of the row above (VIADDMNMX.S16x2)
 //   h   = __vimax3_s16x2(e, up, B2)       ReLU against the bias B (= zero)                     (VIMNMX3.S16x2)
 //   hg  = h + G2                       plain 32-bit add: all values carry a bias B >= -gap, so the low half
@@ -37,12 +37,12 @@ namespace dpx {
 
 struct SrArgs {
     const uint32_t* packed;              // 2-bit packed sequences (pack.cuh)
+    const uint8_t* codes;                // WIDE: byte codes 0..7, indexed like the blob (referenceIdx / queryIdx)
     const unsigned long long* pk_off;    // [n_pairs] word offsets, or null: pair p starts at p * pk_stride
     unsigned long long pk_stride;
     const dpx_seq_pair* pairs;
     const int32_t* order;                // schedule (nullable = identity); slot s = schedule positions 2s, 2s+1
     int n_pairs, n_slots;
-    uint32_t lut_lo, lut_hi;             // (unused by the per-row tables; kept for the ABI of the launcher)
     uint32_t ms_byte, xs_byte;           // (match - gap) & 0xff, (mismatch - gap) & 0xff
     uint32_t B2, Bg2, G2;                // packed bias, bias + gap, and the add constant ((gap-1)<<16 | gap&0xffff)
     int B;
@@ -78,7 +78,7 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {       //
 
 __device__ __forceinline__ uint32_t get2(const uint32_t* __restrict__ w, int k) { return (w[k >> 4] >> (2 * (k & 15))) & 3u; }
 
-template <int G, int K, bool TRACK, bool XORMODE>
+template <int G, int K, bool TRACK, bool WIDE>
 __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
     extern __shared__ uint32_t sr_smem[];
     constexpr unsigned FULL = 0xffffffffu;
@@ -102,7 +102,14 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
         const int slot = base + gw;
         int pa = -1, pb = -1, RA = 0, QA = 0, RB = 0, QB = 0;
         const uint32_t *refA = a.packed, *qryA = a.packed, *refB = a.packed, *qryB = a.packed;
-        if (slot < a.n_slots) {
+        const uint8_t *crefA = a.codes, *cqryA = a.codes;            // WIDE
+        if (WIDE && slot < a.n_slots) {
+            pa = a.order ? a.order[slot] : slot;                      // one pair per slot
+            const dpx_seq_pair p = a.pairs[pa];
+            RA = p.referenceSize; QA = p.querySize;
+            crefA = a.codes + p.referenceIdx; cqryA = a.codes + p.queryIdx;
+        }
+        if (!WIDE && slot < a.n_slots) {
             pa = a.order ? a.order[2 * slot] : 2 * slot;
             const dpx_seq_pair p = a.pairs[pa];
             RA = p.referenceSize; QA = p.querySize;
@@ -126,7 +133,15 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
         // int16 sign extension.  Pad columns select the sign of byte 0 / 4: 0 or -1, below any real score.
         // Built one packed word (16 bases) per lane at a time: base k of the reference is entry e = k + G.
         for (int e = gl; e < G; e += G) rsel[e] = (uint16_t)0xcc88u;                       // columns j <= 0
-        for (int c = gl; 16 * c < Rw + G + 2; c += G) {
+        if (WIDE) {
+            // one pair, codes 0..7: nibble 0 = code (byte of the row's 8-byte table ta:tb), nibble 1 = code | 8 (its sign); the high
+            // half repeats a pad (sign of byte 4 -- an entry >= 0 would do as well: the high halves carry nothing)
+            for (int k = gl; k < Rw + G + 2; k += G) {               // lane 0 runs G - 1 pad columns past the last real one
+                const uint32_t nA = (k < RA) ? (uint32_t)(crefA[k] & 7u) : 8u;
+                rsel[k + G] = (uint16_t)((k < RA) ? (nA | ((nA | 8u) << 4) | 0xcc00u) : 0xcc88u);
+            }
+        }
+        for (int c = gl; !WIDE && 16 * c < Rw + G + 2; c += G) {
             const int k0 = 16 * c;
             const uint32_t wA = (k0 < RA) ? refA[c] : 0u, wB = (k0 < RB) ? refB[c] : 0u;
             const int nvA = RA - k0, nvB = RB - k0;                                         // bases of this word that exist
@@ -150,10 +165,16 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
             #pragma unroll
             for (int r = 0; r < K; ++r) {
                 const int i = i0 + r;                            // 0-based query index
-                const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
-                const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
-                ta[r] = xs4 ^ shl_clamp(dms, (qa < 4u) ? 8u * qa : 32u);
-                tb[r] = xs4 ^ shl_clamp(dms, (qb < 4u) ? 8u * qb : 32u);
+                if (WIDE) {
+                    const uint32_t qa = (i < QA) ? (uint32_t)(cqryA[i] & 7u) : 8u;           // 8: a pad row matches nothing
+                    ta[r] = xs4 ^ shl_clamp(dms, (qa < 4u) ? 8u * qa : 32u);
+                    tb[r] = xs4 ^ shl_clamp(dms, (qa >= 4u && qa < 8u) ? 8u * (qa - 4u) : 32u);
+                } else {
+                    const uint32_t qa = (i < QA) ? get2(qryA, i) : 4u;
+                    const uint32_t qb = (i < QB) ? get2(qryB, i) : 4u;
+                    ta[r] = xs4 ^ shl_clamp(dms, (qa < 4u) ? 8u * qa : 32u);
+                    tb[r] = xs4 ^ shl_clamp(dms, (qb < 4u) ? 8u * qb : 32u);
+                }
                 hgA[r] = Bg2; hgB[r] = Bg2;
             }
             #pragma unroll

@@ -251,6 +251,43 @@ def test_short_read_kernel_uniform(eng, shape, w):
             assert len(bad) == 0, f"{len(bad)} end cells differ, first {bad[:5]}: gpu {res.end_row_col[bad[:3]]} oracle {e[bad[:3]]}"
 
 
+@pytest.mark.parametrize("alphabet", [b"01234", b"ACGTN", b"01234567", b"ACGTNRYK"])
+def test_short_read_kernel_wide_alphabets(eng, alphabet):
+    """5..8 symbols (the reference's data sets use '0'..'4'): the WIDE instantiation of the short-read kernel -- one pair per lane
+    group, byte codes, all eight table bytes of a row for that pair -- instead of the byte-compare wavefront kernel."""
+    rng = synth.Rng(len(alphabet) * 101 + alphabet[0])
+    pp = [(b"", b""), (alphabet[:1], alphabet[-1:]), (alphabet, alphabet), (alphabet[::-1] * 3, alphabet * 2)]
+    for k in range(900):
+        R = 1 + int(rng.below(1, 330)[0])
+        r = synth.random_seq(rng, R, alphabet)
+        q = synth.mutate(rng, r, 0.05, 0.03, 0.03, alphabet) if k % 3 else synth.random_seq(rng, 1 + int(rng.below(1, 330)[0]), alphabet)
+        pp.append((r, q))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    for w in (dict(match=3, mismatch=-1, gap_open=-2), dict(match=2, mismatch=-3, gap_open=-1), dict(match=5, mismatch=-4, gap_open=-7)):
+        for flags in (api.OUT_SCORE | api.OUT_END_COORDS, api.OUT_SCORE):
+            res, st = _staged(eng, blob, pairs, api.make_params(api.LSW, flags=flags, **w))
+            assert st["kernel_id"] == 2, "5..8 symbols must stay on the short-read kernel"
+            s, e, _ = ol.align_batch(ol.params(ol.LSW, **w), blob, pairs, strings=False, threads=8)
+            assert (res.scores == s).all()
+            if flags & api.OUT_END_COORDS:
+                assert (res.end_row_col == e).all()
+    # uniform 150 x 150 (config 2's shape) over '0'..'4', several passes for longer queries
+    for R, Q, n in ((150, 150, 3000), (400, 333, 200)):
+        img = synth.uniform_file_bytes(n, R, Q, 99 + R, alphabet)
+        blob, pairs = ol.parse_image(img)
+        blob[pairs["queryIdx"][0]: pairs["queryIdx"][0] + min(R, Q)] = blob[pairs["referenceIdx"][0]: pairs["referenceIdx"][0] + min(R, Q)]
+        res, st = _staged(eng, blob, pairs, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
+        assert st["kernel_id"] == 2
+        s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False, threads=8)
+        assert (res.scores == s).all() and (res.end_row_col == e).all()
+    # a ninth symbol leaves the table kernels
+    nine = ol.parse_image(synth.pairs_to_file_bytes([(b"012345678", b"876543210"), (b"0123", b"0123")]))
+    res, st = _staged(eng, nine[0], nine[1], api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
+    assert st["kernel_id"] == 1
+    s, e, _ = ol.align_batch(ol.params(ol.LSW), nine[0], nine[1], strings=False)
+    assert (res.scores == s).all() and (res.end_row_col == e).all()
+
+
 def test_short_read_kernel_ragged_lengths(eng):
     rng = synth.Rng(0x5EED0000 + 77)
     pairs = []
@@ -267,10 +304,16 @@ def test_short_read_kernel_ragged_lengths(eng):
     assert (res.scores == s).all() and (res.end_row_col == e).all()
 
 
-def test_five_symbol_alphabet_escapes_to_byte_kernels(eng):
+def test_five_symbol_alphabet_uses_the_wide_tables(eng):
+    """'0'..'4' (the reference's data sets): score requests stay on the short-read kernel (WIDE); with the kernel switched off
+    the byte-compare wavefront kernel gives the same bytes."""
     blob, idx = random_pairs(0x44, 200, 120, alphabets=(b"01234",))
+    with eng.options(no_shortread=1):
+        res0, st0 = _staged(eng, blob, idx, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
+    assert st0["kernel_id"] == 1
     res, st = _staged(eng, blob, idx, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS))
-    assert st["kernel_id"] == 1
+    assert st["kernel_id"] == 2
+    assert (res0.scores == res.scores).all() and (res0.end_row_col == res.end_row_col).all()
     s, e, _ = ol.align_batch(ol.params(ol.LSW), blob, idx, strings=False)
     assert (res.scores == s).all() and (res.end_row_col == e).all()
 

@@ -31,7 +31,7 @@ def pipe(op):
 # kernel-name regex -> (label, cells per inner-loop trip as a function of template ints)
 SPECS = [
     (r"sr_lsw_kernelILi(\d+)ELi(\d+)ELb([01])ELb([01])E", "shortread_s16x2",
-     lambda g: dict(G=int(g[0]), K=int(g[1]), track=bool(int(g[2])), xormode=bool(int(g[3])), cells=2 * 2 * int(g[1]))),
+     lambda g: dict(G=int(g[0]), K=int(g[1]), track=bool(int(g[2])), wide=bool(int(g[3])), cells=2 * 2 * int(g[1]))),
     (r"pw_nw_kernelILi(\d+)ELb([01])ELi(\d+)ELb1ELb0ELb0E", "pairwf_s16x2",
      lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=2 * 2 * int(g[2]))),
     (r"pw_nw_kernelILi(\d+)ELb([01])ELi(\d+)ELb0ELb0ELb0E", "pairwf_s32",

@@ -31,13 +31,15 @@ def pipe(op):
 # kernel-name regex -> (label, cells per inner-loop trip as a function of template ints)
 SPECS = [
     (r"sr_lsw_kernelILi(\d+)ELi(\d+)ELb([01])ELb([01])E", "shortread_s16x2",
-     lambda g: dict(G=int(g[0]), K=int(g[1]), track=bool(int(g[2])), wide=bool(int(g[3])), cells=2 * 2 * int(g[1]))),
+     # one loop trip = two column steps of K rows, two pairs per slot (WIDE: one pair)
+     lambda g: dict(G=int(g[0]), K=int(g[1]), track=bool(int(g[2])), wide=bool(int(g[3])), cells=(1 if int(g[3]) else 2) * 2 * int(g[1]))),
     (r"pw_nw_kernelILi(\d+)ELb([01])ELi(\d+)ELb1ELb0ELb0E", "pairwf_s16x2",
      lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=2 * 2 * int(g[2]))),
     (r"pw_nw_kernelILi(\d+)ELb([01])ELi(\d+)ELb0ELb0ELb0E", "pairwf_s32",
      lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=2 * int(g[2]))),
     (r"band_sw_kernelILi(\d+)ELb([01])ELb([01])E", "band_s32",
-     lambda g: dict(M=int(g[0]), extra=bool(int(g[1])), traceback=bool(int(g[2])), cells=2 * (2 * int(g[0]) + int(g[1])))),
+     # one loop trip = one traceback word = SPW super-steps (8 / 4 / 2 for M = 1 / 2 / 3) of 2M (+1) slots
+     lambda g: dict(M=int(g[0]), extra=bool(int(g[1])), traceback=bool(int(g[2])), cells={1: 8, 2: 4, 3: 2}[int(g[0])] * (2 * int(g[0]) + int(g[1])))),
     (r"wf_fill_kernelILi(\d+)ELb([01])ELi(\d+)E", "wavefront_s32",
      lambda g: dict(algo=int(g[0]), traceback=bool(int(g[1])), K=int(g[2]), cells=int(g[2]))),
     # long-pair chain: the steady row loop is unrolled 4 row steps of K cells (several overlapping back-edges: pick the densest loop)

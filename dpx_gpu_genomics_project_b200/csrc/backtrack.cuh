@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(256) str_len_kernel(const dpx_seq_pair* __rest
 __global__ void __launch_bounds__(256) str_compact_kernel(const dpx_seq_pair* __restrict__ pairs, int n, const char* __restrict__ slab,
                                                           const unsigned long long* __restrict__ str_off, const int32_t* __restrict__ str_start,
                                                           const unsigned long long* __restrict__ coff, char* __restrict__ out,
-                                                          unsigned long long* __restrict__ offs) {
+                                                          unsigned long long* __restrict__ offs, unsigned long long base = 0ull) {   // base: added to the offsets only
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     for (int i = warp; i < n; i += nwarps) {
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) str_compact_kernel(const dpx_seq_pair* __
         char* __restrict__ dst = out + coff[i];
         for (int k = 0; k < 3; ++k)
             for (unsigned long long x = lane; x < L; x += 32) dst[k * L + x] = src[k * F + x];
-        if (lane < 3) offs[3 * i + lane] = coff[i] + lane * L;
+        if (lane < 3) offs[3 * i + lane] = base + coff[i] + lane * L;
     }
 }
 

@@ -116,6 +116,7 @@ struct DpxOptions {
     int serial_chunks = 0;     // traceback chunk pipeline: one buffer, chunks in series (times the fill kernel alone)
     int trace = 0;             // one-call pipeline: per-chunk timeline on stderr
     int no_sidecar = 0;        // dpx_align_batch: ignore the parser's packed sidecar (upload the raw blob)
+    int serial_strings = 0;    // dpx_align_batch with strings: one batch, upload -> kernels -> compaction -> download in series
 };
 
 struct dpx_ctx {
@@ -142,6 +143,7 @@ struct dpx_ctx {
     // per kernel: shared-memory attribute already raised, and occupancy per dynamic shared-memory size
     std::unordered_map<const void*, std::map<size_t, int>> occ_cache;
     int chunks = 12;                               // one-call pipeline: equal middle chunks (dpx_set_option "chunks")
+    int chunks_strings = 8;                        // ... upper limit of chunks when alignment strings are requested
     int chunks_packed = 12;                        // ... when the input comes from the packed sidecar (kernel-bound: fewer, larger chunks)
     bool counted = false;                          // registered in g_live_ctx (dpx_create succeeded)
 };
@@ -166,6 +168,7 @@ struct dpx_batch {
     uint32_t inv4 = 0;                             // sidecar batches: code -> byte (4 bytes), for ensure_blob
     bool from_sidecar = false;
     uint32_t* d_stage[2] = {nullptr, nullptr};     // sidecar batches: staged sizes / word offsets (released with the batch)
+    std::vector<void*> d_scratch;                  // scratch of the batch's CUB passes (sort keys, scan temporaries): released with the batch
     size_t h2d_bytes = 0;                          // bytes this batch's upload moved over PCIe
     uint8_t* d_codes = nullptr;                    // 5..8 symbols: byte codes, same indexing as d_blob (allocated at d_codes_alloc - byte_lo)
     uint8_t* d_codes_alloc = nullptr;
@@ -330,7 +333,9 @@ int dpx_set_option(dpx_ctx* ctx, const char* name, long long value) {
     else if (k == "serial_chunks") o.serial_chunks = value != 0;
     else if (k == "trace") o.trace = value != 0;
     else if (k == "no_sidecar") o.no_sidecar = value != 0;
+    else if (k == "serial_strings") o.serial_strings = value != 0;
     else if (k == "chunks") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks = (int)value; }
+    else if (k == "chunks_strings") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks_strings = (int)value; }
     else if (k == "chunks_packed") { if (value < 1 || value > 64) return DPX_ERR_INVALID; ctx->chunks_packed = (int)value; }
     else if (k == "tb_budget_bytes") { if (value < (1 << 16)) return DPX_ERR_INVALID; ctx->tb_budget_bytes = (size_t)value; }
     else { ctx->err = "unknown option: " + k; return DPX_ERR_INVALID; }
@@ -505,6 +510,7 @@ static void batch_release(dpx_batch* b) {
     P.release(b->d_blob_alloc); P.release(b->d_pairs); P.release(b->d_packed); P.release(b->d_codes_alloc); P.release(b->d_pk_off); P.release(b->d_str_len);
     P.release(b->d_order); P.release(b->d_scores); P.release(b->d_end_rc); P.release(b->d_tb); P.release(b->d_strings);
     P.release(b->d_stage[0]); P.release(b->d_stage[1]);
+    for (void* x : b->d_scratch) P.release(x);
     P.release(b->d_str_off); P.release(b->d_str_start); P.release(b->d_band_cells); P.release(b->d_info); P.release(b->d_band_qs); P.release(b->d_band_rs);
     for (auto e : b->ev) ev_put(b->ctx, e, true);
     for (auto e : b->ev_sync) ev_put(b->ctx, e, false);
@@ -1012,6 +1018,132 @@ int dpx_align_batch_text(dpx_ctx* ctx, const dpx_params* params, const char* seq
     return st;
 }
 
+// ---- strings of one chunk of the one-call pipeline, in two asynchronous halves -------------------------------------------------
+// begin : lengths of the compacted strings + their scan + the chunk's total into the lane's pinned slot (needs a host wait later);
+// finish: (total known) compact into a device buffer and copy it, with offsets already rebased to `base`, into the shared host blob.
+static int batch_strings_begin(dpx_batch* b, unsigned long long* h_total, unsigned long long** d_coff_out) {
+    dpx_ctx* ctx = b->ctx;
+    const size_t n = b->n_pairs;
+    unsigned long long *d_len = nullptr, *d_coff = nullptr;
+    if (!pool_alloc(ctx, &d_len, n + 1) || !pool_alloc(ctx, &d_coff, n + 1)) { ctx->pool.release(d_len); ctx->pool.release(d_coff); return DPX_ERR_NOMEM; }
+    b->d_scratch.push_back(d_len); b->d_scratch.push_back(d_coff);
+    str_len_kernel<<<(int)((n + 1 + 255) / 256), 256, 0, b->stream>>>(b->d_pairs, (int)n, b->d_str_start, d_len);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_len, d_coff, (int)n + 1, b->stream);
+    void* tmp = ctx->pool.alloc(tmp_bytes);
+    if (!tmp) return DPX_ERR_NOMEM;
+    b->d_scratch.push_back(tmp);
+    CU(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_len, d_coff, (int)n + 1, b->stream));
+    CU(cudaMemcpyAsync(h_total, d_coff + n, sizeof(unsigned long long), cudaMemcpyDeviceToHost, b->stream));
+    *d_coff_out = d_coff;
+    return DPX_OK;
+}
+
+static int batch_strings_finish(dpx_batch* b, const unsigned long long* d_coff, unsigned long long total, unsigned long long base,
+                                char* host_blob, size_t* host_offs /* [3 * n] of this chunk */) {
+    dpx_ctx* ctx = b->ctx;
+    const size_t n = b->n_pairs;
+    char* d_compact = nullptr; unsigned long long* d_offs = nullptr;
+    if (!pool_alloc(ctx, &d_compact, (size_t)total + 16) || !pool_alloc(ctx, &d_offs, 3 * n)) { ctx->pool.release(d_compact); ctx->pool.release(d_offs); return DPX_ERR_NOMEM; }
+    b->d_scratch.push_back(d_compact); b->d_scratch.push_back(d_offs);
+    str_compact_kernel<<<(int)std::min<size_t>((n + 7) / 8, (size_t)ctx->sm_count * 16), 256, 0, b->stream>>>(
+        b->d_pairs, (int)n, b->d_strings, b->d_str_off, b->d_str_start, d_coff, d_compact, d_offs, base);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host_offs, d_offs, 3 * n * sizeof(size_t), cudaMemcpyDeviceToHost, b->stream));
+    if (total) CU(cudaMemcpyAsync(host_blob + base, d_compact, (size_t)total, cudaMemcpyDeviceToHost, b->stream));
+    return DPX_OK;
+}
+
+// Alignment strings for a large batch: the pairs are cut into chunks that run on the four lanes (streams) like the score chunks
+// below; a chunk's fill overlaps the previous chunk's walk, and its compaction + download overlap the next chunks' kernels, so the
+// PCIe time of the strings (the largest part of the serial route's overhead) disappears behind the kernels.  The host blob is one
+// page-locked allocation sized by the upper bound 3 (Q + R + 1) per pair; chunks land back to back at their exact sizes.
+static int align_batch_strings_pipelined(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
+                                         const dpx_seq_pair* pairs, size_t n_pairs, int32_t* scores, int32_t* end_row_col,
+                                         char** strings_blob, size_t** string_offsets, size_t nchunks) {
+    constexpr int NL = 4;
+    cudaStream_t lanes[NL] = {ctx->stream, ctx->aux_stream[0], ctx->aux_stream[1], ctx->aux_stream[2]};
+    size_t sc_first = 0;
+    const dpxhost_pack::Sidecar* sc = ctx->opt.no_sidecar ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
+    std::vector<size_t> bound(nchunks + 1);
+    for (size_t c = 0; c <= nchunks; ++c) bound[c] = n_pairs * c / nchunks;
+    for (size_t c = 0; sc && c < nchunks; ++c)
+        if (16ull * (unsigned long long)(sc->woff[sc_first + bound[c + 1]] - sc->woff[sc_first + bound[c]]) + 16ull > 0x7fffffffull) sc = nullptr;
+    // upper bound of the compacted strings
+    unsigned long long cap = 0;
+    if (sc && n_pairs == sc->n_pairs) cap = 3ull * (sc->sum_r + sc->sum_q + (unsigned long long)n_pairs);
+    else for (size_t i = 0; i < n_pairs; ++i) cap += 3ull * ((unsigned long long)std::max(pairs[i].referenceSize, 0) + (unsigned long long)std::max(pairs[i].querySize, 0) + 1ull);
+    char* blob = (char*)g_host.take(std::max<size_t>((size_t)cap, 1));
+    size_t* offs = (size_t*)g_host.take(std::max<size_t>(3 * n_pairs, 1) * sizeof(size_t));
+    unsigned long long* h_total = nullptr;
+    auto drop = [&]() { if (blob) dpx_free(blob); if (offs) dpx_free(offs); if (h_total) cudaFreeHost(h_total); };
+    if (!blob || !offs || cudaHostAlloc(&h_total, NL * sizeof(unsigned long long), cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); drop(); return DPX_ERR_NOMEM; }
+    dpx_batch* inflight[NL] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<dpx_batch*> chunk_batch(nchunks, nullptr);
+    std::vector<unsigned long long*> chunk_coff(nchunks, nullptr);
+    std::vector<cudaEvent_t> chunk_ev(nchunks, nullptr);
+    unsigned long long base = 0;
+    int status = DPX_OK;
+    auto stage_a = [&](size_t c) -> int {                    // upload (previous tenant of the lane is finished and released first)
+        const int lane = (int)(c % NL);
+        if (inflight[lane]) { cudaStreamSynchronize(lanes[lane]); batch_release(inflight[lane]); inflight[lane] = nullptr; }
+        const size_t p0 = bound[c], n = bound[c + 1] - p0;
+        dpx_batch* b = nullptr;
+        int s = DPX_ERR_UNSUPPORTED;
+        if (sc) s = batch_from_sidecar(ctx, lanes[lane], lane, sc, sc_first + p0, n, &b);
+        if (s == DPX_ERR_UNSUPPORTED) {
+            long long lo = (long long)n_bytes, hi = 0;
+            for (size_t i = p0; i < p0 + n; ++i) {
+                const dpx_seq_pair& q = pairs[i];
+                lo = std::min<long long>(lo, std::min(q.referenceIdx, q.queryIdx));
+                hi = std::max<long long>(hi, std::max((long long)q.referenceIdx + q.referenceSize, (long long)q.queryIdx + q.querySize));
+            }
+            if (lo < 0 || hi > (long long)n_bytes || hi < lo) { ctx->err = "a seqPair entry points outside the sequence blob"; return DPX_ERR_INVALID; }
+            s = batch_create(ctx, lanes[lane], lane, sequences, lo, hi, pairs + p0, n, &b);
+        }
+        if (s) return s;
+        inflight[lane] = b; chunk_batch[c] = b;
+        return DPX_OK;
+    };
+    auto stage_b = [&](size_t c) -> int {                    // kernels + the first half of the strings
+        dpx_batch* b = chunk_batch[c];
+        const size_t p0 = bound[c];
+        int s = batch_run(b, params);
+        if (!s) s = batch_fetch_async(b, scores + p0, end_row_col ? end_row_col + 2 * p0 : nullptr);
+        if (!s) s = batch_strings_begin(b, h_total + (c % NL), &chunk_coff[c]);
+        if (!s) { cudaEvent_t e; if (ev_get(ctx, &e, false) != cudaSuccess || cudaEventRecord(e, b->stream) != cudaSuccess) s = DPX_ERR_CUDA; else chunk_ev[c] = e; }
+        return s;
+    };
+    auto stage_c = [&](size_t c) -> int {                    // total known: compact + download at the running offset
+        dpx_batch* b = chunk_batch[c];
+        if (cudaEventSynchronize(chunk_ev[c]) != cudaSuccess) return DPX_ERR_CUDA;
+        ev_put(ctx, chunk_ev[c], false); chunk_ev[c] = nullptr;
+        const unsigned long long total = h_total[c % NL];
+        if (base + total > cap) { ctx->err = "string blob overflow"; return DPX_ERR_CUDA; }
+        const int s = batch_strings_finish(b, chunk_coff[c], total, base, blob, offs + 3 * bound[c]);
+        base += total;
+        return s;
+    };
+    status = stage_a(0);
+    if (status == DPX_OK && nchunks > 1) status = stage_a(1);
+    for (size_t c = 0; c < nchunks && status == DPX_OK; ++c) {
+        status = stage_b(c);
+        if (status == DPX_OK && c >= 1) status = stage_c(c - 1);           // (waits for chunk c-1 while chunk c's kernels are queued)
+        if (status == DPX_OK && c + 2 < nchunks) status = stage_a(c + 2);
+    }
+    if (status == DPX_OK) status = stage_c(nchunks - 1);
+    for (int lane = 0; lane < NL; ++lane) {
+        cudaError_t e = cudaStreamSynchronize(lanes[lane]);
+        if (e != cudaSuccess && status == DPX_OK) { ctx->err = std::string("stream sync: ") + cudaGetErrorString(e); status = DPX_ERR_CUDA; }
+        if (inflight[lane]) batch_release(inflight[lane]);
+    }
+    for (auto e : chunk_ev) if (e) ev_put(ctx, e, false);
+    cudaFreeHost(h_total); h_total = nullptr;
+    if (status != DPX_OK) { drop(); return status; }
+    *strings_blob = blob; *string_offsets = offs;
+    return DPX_OK;
+}
+
 // One call, host buffers in and out.  Score / end-cell requests on large batches are cut into chunks of
 // consecutive pairs that alternate between two streams, so the H2D copy of chunk k+1 (and the host's scan of
 // its byte range) overlaps the kernels of chunk k; everything else takes the single-batch route.
@@ -1027,6 +1159,12 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     size_t sc_first = 0;
     const dpxhost_pack::Sidecar* sc = (ctx->opt.no_sidecar || want_strings || n_pairs == 0) ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
     size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)(sc ? ctx->chunks_packed : ctx->chunks), n_pairs / min_chunk);
+    if (want_strings && strings_blob && string_offsets && !ctx->opt.serial_strings && n_pairs >= 4096) {
+        // >= 2048 pairs per chunk, at most 8 chunks (each chunk is a batch of its own: fewer, larger chunks keep the kernels' waves full)
+        const size_t nstr = std::max<size_t>(1, std::min<size_t>((size_t)ctx->chunks_strings, n_pairs / 2048));
+        *strings_blob = nullptr; *string_offsets = nullptr;
+        return align_batch_strings_pipelined(ctx, params, sequences, n_bytes, pairs, n_pairs, scores, end_row_col, strings_blob, string_offsets, nstr);
+    }
     if (nbase <= 1) {
         dpx_batch* b = nullptr;
         int st = dpx_batch_upload(ctx, sequences, n_bytes, pairs, n_pairs, &b);

@@ -76,20 +76,23 @@ static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, 
     return true;
 }
 
+// Scratch of the per-batch CUB passes stays with the batch until it is released (batch_release runs after the stream has
+// drained): no host sync here, so the chunks of the one-call pipeline keep streaming when the lengths are ragged.
 static int ensure_order(dpx_batch* b) {
     dpx_ctx* ctx = b->ctx;
     if (b->uniform || b->d_order) return DPX_OK;
     const int n = (int)b->n_pairs;
     unsigned long long *k_in = nullptr, *k_out = nullptr; int32_t* v_in = nullptr;
-    if (!pool_alloc(ctx, &k_in, n) || !pool_alloc(ctx, &k_out, n) || !pool_alloc(ctx, &v_in, n) || !pool_alloc(ctx, &b->d_order, n)) return DPX_ERR_NOMEM;
+    if (!pool_alloc(ctx, &k_in, n) || !pool_alloc(ctx, &k_out, n) || !pool_alloc(ctx, &v_in, n)) { ctx->pool.release(k_in); ctx->pool.release(k_out); ctx->pool.release(v_in); return DPX_ERR_NOMEM; }
+    b->d_scratch.push_back(k_in); b->d_scratch.push_back(k_out); b->d_scratch.push_back(v_in);
+    if (!pool_alloc(ctx, &b->d_order, n)) return DPX_ERR_NOMEM;
     sched_keys_kernel<<<(n + 255) / 256, 256, 0, b->stream>>>(b->d_pairs, n, k_in, v_in);
     size_t tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, v_in, b->d_order, n, 0, 64, b->stream);
     void* tmp = ctx->pool.alloc(tmp_bytes);
     if (!tmp) return DPX_ERR_NOMEM;
+    b->d_scratch.push_back(tmp);
     CU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, v_in, b->d_order, n, 0, 64, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
-    ctx->pool.release(tmp); ctx->pool.release(k_in); ctx->pool.release(k_out); ctx->pool.release(v_in);
     return DPX_OK;
 }
 
@@ -102,9 +105,8 @@ static int ensure_str_off(dpx_batch* b) {
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, b->d_str_len, b->d_str_off, n, b->stream);
     void* tmp = ctx->pool.alloc(tmp_bytes);
     if (!tmp) return DPX_ERR_NOMEM;
+    b->d_scratch.push_back(tmp);
     CU(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, b->d_str_len, b->d_str_off, n, b->stream));
-    CU(cudaStreamSynchronize(b->stream));
-    ctx->pool.release(tmp);
     if (!pool_alloc(ctx, &b->d_strings, (size_t)b->info.str_bytes + 1)) return DPX_ERR_NOMEM;
     return DPX_OK;
 }

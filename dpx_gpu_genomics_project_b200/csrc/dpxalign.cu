@@ -1147,11 +1147,49 @@ static int align_batch_strings_pipelined(dpx_ctx* ctx, const dpx_params* params,
 // One call, host buffers in and out.  Score / end-cell requests on large batches are cut into chunks of
 // consecutive pairs that alternate between two streams, so the H2D copy of chunk k+1 (and the host's scan of
 // its byte range) overlaps the kernels of chunk k; everything else takes the single-batch route.
+static int align_batch_impl(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
+                            const dpx_seq_pair* pairs, size_t n_pairs, int32_t* scores, int32_t* end_row_col,
+                            char** strings_blob, size_t** string_offsets);
+
+static bool is_device_accessible_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
 int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
                     const dpx_seq_pair* pairs, size_t n_pairs, int32_t* scores, int32_t* end_row_col,
                     char** strings_blob, size_t** string_offsets) {
     if (!ctx || !params || !scores || (!sequences && n_bytes) || (!pairs && n_pairs) || n_pairs > 0x7fffffffu) return DPX_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
+    // The chunk pipelines below copy results out asynchronously; a copy into PAGEABLE memory blocks the host thread and would
+    // serialise the chunks (measured: config 3, 38 -> 51 ms).  Callers with ordinary malloc'ed result arrays (the reference's
+    // driver style) therefore get page-locked bounce buffers and one memcpy at the end.
+    if (n_pairs >= 65536 || ((params->flags & DPX_OUT_STRINGS) && n_pairs >= 16384)) {
+        const bool bs = !is_device_accessible_host(scores), be = end_row_col && !is_device_accessible_host(end_row_col);
+        if (bs || be) {
+            int32_t* ts = bs ? (int32_t*)g_host.take(n_pairs * sizeof(int32_t)) : scores;
+            int32_t* te = be ? (int32_t*)g_host.take(2 * n_pairs * sizeof(int32_t)) : end_row_col;
+            if (ts && (te || !end_row_col)) {
+                const int st = align_batch_impl(ctx, params, sequences, n_bytes, pairs, n_pairs, ts, te, strings_blob, string_offsets);
+                if (st == DPX_OK) {
+                    if (bs) memcpy(scores, ts, n_pairs * sizeof(int32_t));
+                    if (be) memcpy(end_row_col, te, 2 * n_pairs * sizeof(int32_t));
+                }
+                if (bs) dpx_free(ts);
+                if (be) dpx_free(te);
+                return st;
+            }
+            if (bs && ts) dpx_free(ts);
+            if (be && te) dpx_free(te);
+        }
+    }
+    return align_batch_impl(ctx, params, sequences, n_bytes, pairs, n_pairs, scores, end_row_col, strings_blob, string_offsets);
+}
+
+static int align_batch_impl(dpx_ctx* ctx, const dpx_params* params, const char* sequences, size_t n_bytes,
+                            const dpx_seq_pair* pairs, size_t n_pairs, int32_t* scores, int32_t* end_row_col,
+                            char** strings_blob, size_t** string_offsets) {
     const bool want_strings = (params->flags & DPX_OUT_STRINGS) != 0;
     const size_t min_chunk = 32768;
     // Registered input (parser output / dpx_register_input): every chunk uploads its slice of the host-side 2-bit sidecar --
@@ -1159,8 +1197,9 @@ int dpx_align_batch(dpx_ctx* ctx, const dpx_params* params, const char* sequence
     size_t sc_first = 0;
     const dpxhost_pack::Sidecar* sc = (ctx->opt.no_sidecar || want_strings || n_pairs == 0) ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
     size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)(sc ? ctx->chunks_packed : ctx->chunks), n_pairs / min_chunk);
-    if (want_strings && strings_blob && string_offsets && !ctx->opt.serial_strings && n_pairs >= 4096) {
-        // >= 2048 pairs per chunk, at most 8 chunks (each chunk is a batch of its own: fewer, larger chunks keep the kernels' waves full)
+    if (want_strings && strings_blob && string_offsets && !ctx->opt.serial_strings && n_pairs >= 16384) {
+        // >= 2048 pairs per chunk, at most 8 chunks.  Measured (tools/e2e_strings.py): config 3 (100 k pairs) 43.5 ms serial, 38.1 ms in 8
+        // chunks; config 4 (10 k long pairs) 18.5 ms serial, 20 ms in 4 chunks of 2500 walkers -- hence the floor of 16 k pairs.
         const size_t nstr = std::max<size_t>(1, std::min<size_t>((size_t)ctx->chunks_strings, n_pairs / 2048));
         *strings_blob = nullptr; *string_offsets = nullptr;
         return align_batch_strings_pipelined(ctx, params, sequences, n_bytes, pairs, n_pairs, scores, end_row_col, strings_blob, string_offsets, nstr);

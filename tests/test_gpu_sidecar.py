@@ -164,9 +164,9 @@ def test_multi_device_call_returns_pair_order_results(eng, devices):
 
 @pytest.mark.parametrize("algo,w", CASES[:4])
 def test_pipelined_strings_route_matches_the_serial_one(eng, algo, w):
-    """>= 4096 pairs with alignment strings: the one-call ABI cuts the batch into chunks over four streams and downloads each
+    """>= 16 384 pairs with alignment strings: the one-call ABI cuts the batch into chunks over four streams and downloads each
     chunk's strings while the next chunks compute; blob + offsets must spell the same strings as the serial route and the oracle."""
-    n = 9000
+    n = 20000
     blob, pairs = synth.ragged_mutated_blob_pairs(n, 30, 140, 77 + algo, 0.05, 0.02, 0.02)
     inp = api.parse_image_native(synth.blob_to_file_bytes(blob))
     s, e, t = ol.align_batch(ol.params(algo, **w), inp.sequences, inp.pairs, threads=8)
@@ -178,9 +178,9 @@ def test_pipelined_strings_route_matches_the_serial_one(eng, algo, w):
         _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs), s, e, t, algo)
     inp.free()
     # uniform lengths (no schedule), sub-range of a registered input
-    img = synth.mutated_fixed_file_bytes(6000, 120, 110, 5, 0.04, 0.01, 0.01)
+    img = synth.mutated_fixed_file_bytes(18000, 120, 110, 5, 0.04, 0.01, 0.01)
     inp = api.parse_image_native(img)
     s, e, t = ol.align_batch(ol.params(algo, **w), inp.sequences, inp.pairs, threads=8)
     _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs), s, e, t, algo)
-    _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs[700:5700]), s[700:5700], e[700:5700], t[700:5700], algo)
+    _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs[700:17700]), s[700:17700], e[700:17700], t[700:17700], algo)
     inp.free()

@@ -2,7 +2,7 @@
 usage: python tools/e2e_strings.py 3|4 [pairs]"""
 import ctypes as C, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np
+import numpy as np, torch
 from dpx_gpu_genomics_project_b200 import api, synth
 cfg = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 if cfg == 3:
@@ -15,7 +15,7 @@ else:
     p = api.make_params(api.BSW, gap_open=-2, band=64, flags=7)
 inp = api.parse_image_native(img)
 eng = api.Engine(0)
-sc = np.zeros(n, np.int32); rc = np.zeros((n, 2), np.int32)
+sc = torch.empty(n, dtype=torch.int32).pin_memory().numpy(); rc = torch.empty((n, 2), dtype=torch.int32).pin_memory().numpy()    # page-locked, like bench.py (pageable result buffers serialise the chunks)
 def once():
     sb, so = C.c_void_p(), C.c_void_p()
     st = eng.L.dpx_align_batch(eng.ctx, C.byref(p), inp.sequences.ctypes.data, inp.sequences.size, inp.pairs.ctypes.data, n, sc.ctypes.data, rc.ctypes.data, C.byref(sb), C.byref(so))

@@ -284,6 +284,13 @@ def golden_cfg5():
         return None
 
 
+def long_config(R, Q, n_gpus):
+    return {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp (query = reference mutated 1 % / 0.1 % / 0.1 %), score + end cell, "
+                        "match 3 / mismatch -1 / gap -2", "baseline_config": 5, "R": R, "Q": Q,
+            "sharding": f"{n_gpus} column stripe(s), right edges streamed GPU to GPU over NVLink P2P (no NCCL on the data path)",
+            "l2": "256 MiB memset between timed steps", "seed": f"{LONG['seed']:#x}"}
+
+
 def bench_long(C, steps, warmup, with_cpu):
     """config 5: one step = one alignment of the 1 Mbp x 1 Mbp pair.  N > 1: the reference columns are split into one stripe per
     GPU (multi-GPU mode B, the right edge of a stripe streams to the next GPU by NVLink P2P stores): total work is fixed, so
@@ -302,10 +309,7 @@ def bench_long(C, steps, warmup, with_cpu):
         img = synth.mutated_fixed_file_bytes(1, r_len, q_len, LONG["seed"], *LONG["mutate"])
         return img[2:2 + r_len].tobytes(), img[3 + r_len:3 + r_len + q_len].tobytes()
 
-    config = {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp (query = reference mutated 1 % / 0.1 % / 0.1 %), score + end cell, "
-                          "match 3 / mismatch -1 / gap -2", "baseline_config": 5, "R": R, "Q": Q,
-              "sharding": f"{world} column stripe(s), right edges streamed GPU to GPU over NVLink P2P (no NCCL on the data path)",
-              "l2": "256 MiB memset between timed steps", "seed": f"{LONG['seed']:#x}"}
+    config = long_config(R, Q, world)
     ref, qry = make_pair(R, Q)
     eng = C.eng
     params = api.make_params(api.LSW, **w)
@@ -385,7 +389,7 @@ def reference_long(args):
     for _ in range(max(1, min(args.steps, 2))):
         t0 = time.perf_counter(); ol.lsw_score_only(ol.params(ol.LSW, **w), ref, qry); secs.append(time.perf_counter() - t0)
     v = n * n / float(np.mean(secs)) / 1e9
-    config = {"workload": f"LinearSmithWaterman, ONE pair of {R} x {Q} bp, score + end cell", "baseline_config": 5, "R": R, "Q": Q}
+    config = long_config(args.pairs or R, args.pairs or Q, max(args.gpus, env_int("WORLD_SIZE", 1)))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "GCUPS", "n_gpus": max(args.gpus, env_int("WORLD_SIZE", 1)), "steps": len(secs), "warmup": 0,
         "ms_per_step": float(np.mean(secs)) * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32",
@@ -394,6 +398,16 @@ def reference_long(args):
                          "sample": f"a {n} x {n} bp pair of the same generator; rolling-row C port of LinearSmithWaterman (the reference's "
                                    "full-matrix class needs 8 B per cell: 8 TB at 1 Mbp x 1 Mbp), 1 thread"},
         "e2e": {"value": v, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+
+
+def batched_config(wl, cfg_no, n_pairs, n_gpus, score_only, label=None):
+    """The `config` object of a batched line: identical for the dpx and the reference arm of the same workload."""
+    want_strings = wl["strings"] and not score_only
+    ends = "" if (cfg_no == 2 and score_only) else (" + end coords" if cfg_no == 2 else "")
+    return {"workload": (label or wl["title"]).format(pairs=n_pairs, ends=ends) + ("" if want_strings or not wl["strings"] else " [score only]"),
+            "baseline_config": cfg_no, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
+            "sharding": f"independent pairs x{n_gpus} (no collective)", "l2": "256 MiB memset between timed steps",
+            "seed": f"{wl['seed']:#x} + rank", "input": "file image -> dpx_parse_image (blob, index, packed 2-bit sidecar in page-locked memory)"}
 
 
 def bench_batched(C, cfg_no, steps, warmup, score_only=False, n_pairs=0, with_cpu=True, cpu_seconds=12.0, extras=False, gen_override=None, label=None):
@@ -408,11 +422,7 @@ def bench_batched(C, cfg_no, steps, warmup, score_only=False, n_pairs=0, with_cp
         wl["gen"] = gen_override
     n_pairs = n_pairs or wl["pairs"]
     want_strings = wl["strings"] and not score_only
-    ends = "" if (cfg_no == 2 and score_only) else (" + end coords" if cfg_no == 2 else "")
-    config = {"workload": (label or wl["title"]).format(pairs=n_pairs, ends=ends) + ("" if want_strings or not wl["strings"] else " [score only]"),
-              "baseline_config": cfg_no, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
-              "sharding": f"independent pairs x{world} (no collective)", "l2": "256 MiB memset between timed steps",
-              "seed": f"{wl['seed']:#x} + rank", "input": "file image -> dpx_parse_image (blob, index, packed 2-bit sidecar in page-locked memory)"}
+    config = batched_config(wl, cfg_no, n_pairs, world, score_only, label)
 
     key = (cfg_no, str(wl["gen"]), n_pairs, wl["seed"] + rank)
     if _INPUT_CACHE.get("key") != key:                      # the score-only variant of a config reuses the input just generated
@@ -632,9 +642,7 @@ def reference_batched(args, cfg_no):
     cores = os.cpu_count() or 1
     wl = dict(WORKLOADS[cfg_no])
     n_pairs = args.pairs or wl["pairs"]
-    ends = "" if (cfg_no == 2 and args.score_only) else (" + end coords" if cfg_no == 2 else "")
-    config = {"workload": wl["title"].format(pairs=n_pairs, ends=ends), "baseline_config": cfg_no, "pairs_per_gpu": n_pairs, "R": wl["R"], "Q": wl["Q"],
-              "sharding": f"independent pairs x{max(args.gpus, world)} (no collective)", "seed": f"{wl['seed']:#x} + rank"}
+    config = batched_config(wl, cfg_no, n_pairs, max(args.gpus, world), args.score_only)
     n_s = cpu_sample_size(wl, n_pairs, cores, seconds=8.0)
     blob, pairs = make_inputs(wl, n_s, wl["seed"])
     vals, secs = [], []

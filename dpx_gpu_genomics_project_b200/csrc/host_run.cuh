@@ -392,15 +392,17 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                     t.scores = b->d_scores; t.end_rc = b->d_end_rc;
                     { int r2 = add_event_pair(1, &s, &e); if (r2) return r2; }
                     CU(cudaEventRecord(s, bt_st));
-                    const int bt_blocks = (a.count + 127) / 128;
+                    // one thread walks one pair: small launches use one-warp blocks so that the walkers spread over every SM
+                    const int bt_threads = a.count < ctx->sm_count * 512 ? 32 : 128;
+                    const int bt_blocks = (a.count + bt_threads - 1) / bt_threads;
                     if (pl.packed) {
-                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, true><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, true><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
+                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, true><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
+                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, true><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
                     } else {
-                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
-                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, false><<<bt_blocks, 128, 0, bt_st>>>(t);
+                        if (algo == DPX_ALGO_LSW) pw_bt_kernel<DPX_ALGO_LSW, 8, false><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
+                        else if (aff) pw_bt_kernel<DPX_ALGO_ANW, 8, false><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
+                        else     pw_bt_kernel<DPX_ALGO_LNW, 8, false><<<bt_blocks, bt_threads, 0, bt_st>>>(t);
                     }
                     CU(cudaGetLastError());
                     CU(cudaEventRecord(e, bt_st));

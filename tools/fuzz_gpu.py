@@ -60,6 +60,8 @@ def main():
                 L = int(rng.integers(10, 60)); blob, pairs = synth.uniform_blob_pairs(n, L, int(rng.integers(10, 60)), seed_b)
             algo = int(rng.integers(4))
             w = dict(match=3, mismatch=-1, gap_open=-2)
+            if rng.integers(2):                                # registered input: every chunk uploads its slice of the sidecar
+                api.register_input(blob, pairs)
             if algo == api.ANW:
                 w.update(gap_open=-3, gap_extend=-1)
             if algo == api.BSW:
@@ -75,13 +77,15 @@ def main():
                 if strings:
                     assert res.strings == t, "strings"
                 kernels["big"] = kernels.get("big", 0) + 1
+                api.unregister_input(blob)
             except (AssertionError, api.DpxError) as ex:
+                api.unregister_input(blob)
                 failures.append(f"{type(ex).__name__}: {ex} :: {tag}")
                 print("FAIL", failures[-1], flush=True)
             cases += 1
             continue
         (blob, pairs), alpha, span, n = make_batch(rng, int(rng.integers(1 << 30)))
-        algo = int(rng.integers(4))
+        algo = int(rng.integers(5))
         m = int(rng.integers(1, 7)); x = -int(rng.integers(0, 6)); g = -int(rng.integers(1, 8))
         w = dict(match=m, mismatch=x, gap_open=g)
         if algo == api.ANW:
@@ -90,10 +94,21 @@ def main():
                 w["gap_extend"] = -1
         if algo == api.BSW:
             w["band"] = int(rng.choice([0, 1, 5, 16, 31, 32, 33, 64, 65, 96, 97, 150]))
+        if algo == api.ABSW:                                   # affine banded SW (not a reference algorithm; oracle: absw_pair)
+            w["gap_open"] = -int(rng.integers(0, 8)); w["gap_extend"] = -int(rng.integers(0, 4))
+            if w["gap_open"] == 0 and w["gap_extend"] == 0:
+                w["gap_extend"] = -1
+            w["band"] = int(rng.choice([0, 1, 5, 16, 33, 64, 150, 5000]))
         flags = api.OUT_SCORE | api.OUT_END_COORDS | (api.OUT_STRINGS if rng.integers(3) else 0)
         strings = bool(flags & api.OUT_STRINGS)
         tag = f"case {cases} seed {seed} algo {algo} w {w} flags {flags} alpha {alpha} span {span} n {n}"
         try:
+            native = None
+            if rng.integers(3) == 0:                           # through the library's parser: uploads come from the packed 2-bit sidecar
+                native = api.parse_image_native(synth.blob_to_file_bytes(blob) if len(blob) else b"")
+                if native.info["numPairs"] == len(pairs):
+                    blob, pairs = native.sequences, native.pairs
+                    tag += " sidecar" if api.input_sidecar(blob) is not None else " native"
             b = eng.upload(blob, pairs)
             b.run(api.make_params(algo, flags=flags, **w)); b.sync()
             kid = b.stats()["kernel_id"]

@@ -7,9 +7,9 @@ from dpx_gpu_genomics_project_b200 import api, synth
 eng = api.Engine(0)
 ALL = api.OUT_SCORE | api.OUT_END_COORDS | api.OUT_STRINGS
 eng.set_option("serial_chunks", 1)          # kernels one after the other: clean per-kernel captures
-# config 2: short-read kernel, 1M pairs
-blob, pairs = synth.uniform_blob_pairs(1_000_000, 150, 150, 0x5EED0002)
-b = eng.upload(blob, pairs)
+# config 2: short-read kernel, 1M pairs, uploaded from the parser's packed copy (as bench.py does)
+inp = api.parse_image_native(synth.uniform_file_bytes(1_000_000, 150, 150, 0x5EED0002))
+b = eng.upload(inp.sequences, inp.pairs)
 for _ in range(2):
     b.run(api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS)); b.sync()
 print("cfg2", b.stats()); b.free()

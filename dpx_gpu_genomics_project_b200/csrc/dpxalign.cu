@@ -768,7 +768,7 @@ int dpx_batch_upload(dpx_ctx* ctx, const char* sequences, size_t n_bytes, const 
     *out = nullptr;
     CU(cudaSetDevice(ctx->device));
     size_t p0 = 0;
-    if (const dpxhost_pack::Sidecar* sc = (n_pairs && !ctx->opt.no_sidecar) ? dpxhost_pack::find(sequences, pairs, n_pairs, &p0) : nullptr) {
+    if (const dpxhost_pack::Sidecar* sc = (n_pairs && !ctx->opt.no_sidecar) ? dpxhost_pack::find(sequences, n_bytes, pairs, n_pairs, &p0) : nullptr) {
         const int s = batch_from_sidecar(ctx, ctx->stream, 0, sc, p0, n_pairs, out);
         if (s != DPX_ERR_UNSUPPORTED) return s;
     }
@@ -1064,7 +1064,7 @@ static int align_batch_strings_pipelined(dpx_ctx* ctx, const dpx_params* params,
     constexpr int NL = 4;
     cudaStream_t lanes[NL] = {ctx->stream, ctx->aux_stream[0], ctx->aux_stream[1], ctx->aux_stream[2]};
     size_t sc_first = 0;
-    const dpxhost_pack::Sidecar* sc = ctx->opt.no_sidecar ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
+    const dpxhost_pack::Sidecar* sc = ctx->opt.no_sidecar ? nullptr : dpxhost_pack::find(sequences, n_bytes, pairs, n_pairs, &sc_first);
     std::vector<size_t> bound(nchunks + 1);
     for (size_t c = 0; c <= nchunks; ++c) bound[c] = n_pairs * c / nchunks;
     for (size_t c = 0; sc && c < nchunks; ++c)
@@ -1195,7 +1195,7 @@ static int align_batch_impl(dpx_ctx* ctx, const dpx_params* params, const char* 
     // Registered input (parser output / dpx_register_input): every chunk uploads its slice of the host-side 2-bit sidecar --
     // a quarter of the bytes, no device pass, no alphabet handshake with chunk 0.
     size_t sc_first = 0;
-    const dpxhost_pack::Sidecar* sc = (ctx->opt.no_sidecar || want_strings || n_pairs == 0) ? nullptr : dpxhost_pack::find(sequences, pairs, n_pairs, &sc_first);
+    const dpxhost_pack::Sidecar* sc = (ctx->opt.no_sidecar || want_strings || n_pairs == 0) ? nullptr : dpxhost_pack::find(sequences, n_bytes, pairs, n_pairs, &sc_first);
     size_t nbase = want_strings ? 1 : std::min<size_t>((size_t)(sc ? ctx->chunks_packed : ctx->chunks), n_pairs / min_chunk);
     if (want_strings && strings_blob && string_offsets && !ctx->opt.serial_strings && n_pairs >= 16384) {
         // >= 2048 pairs per chunk, at most 8 chunks.  Measured (tools/e2e_strings.py): config 3 (100 k pairs) 43.5 ms serial, 38.1 ms in 8

@@ -104,6 +104,17 @@ int dpx_multi_shard_bounds(const dpx_seq_pair* pairs, size_t n_pairs, int n_shar
     return DPX_OK;
 }
 
+// Boundaries for a call: a registered input whose pairs all have the same lengths (the parser knows) splits evenly without
+// touching the index; anything else takes the prefix-sum pass.
+static void shard_bounds_for(const char* sequences, const dpx_seq_pair* pairs, size_t n_pairs, int n_shards, size_t* bounds) {
+    size_t reg_pairs = 0;
+    if (sequences && dpx_input_sidecar(sequences, &reg_pairs, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr) == 2) {
+        for (int g = 0; g <= n_shards; ++g) bounds[g] = n_pairs * (size_t)g / (size_t)n_shards;
+        return;
+    }
+    dpx_multi_shard_bounds(pairs, n_pairs, n_shards, bounds);
+}
+
 void dpx_destroy_multi(dpx_multi* m) {
     if (!m) return;
     for (Worker* x : m->w) {
@@ -135,6 +146,11 @@ int dpx_create_multi(dpx_multi** out, const int* devices, int n_devices) {
     int st = DPX_OK;
     for (Worker* x : m->w) { x->wait(); if (x->create_status != DPX_OK && st == DPX_OK) st = x->create_status; }
     if (st != DPX_OK) { dpx_destroy_multi(m); return st; }
+    // Driver calls of different host threads of ONE process serialise on the runtime's locks (measured through bench.py's
+    // `2_multi_abi` leg: 12 chunks per device cost 4.7 / 7.6 / 17.3 ms per call on 2 / 4 / 8 GPUs, ~400 calls per device and call).
+    // With many devices each worker therefore runs its shard in few, large chunks: a third of the calls, most of the overlap.
+    if (n_devices >= 4)
+        for (Worker* x : m->w) { dpx_set_option(x->ctx, "chunks_packed", 3); dpx_set_option(x->ctx, "chunks", 4); }
     *out = m;
     return DPX_OK;
 }
@@ -159,7 +175,7 @@ int dpx_multi_align_batch(dpx_multi* m, const dpx_params* params, const char* se
     if (string_offsets) *string_offsets = nullptr;
     const int G = (int)m->w.size();
     std::vector<size_t> bounds((size_t)G + 1);
-    dpx_multi_shard_bounds(pairs, n_pairs, G, bounds.data());
+    shard_bounds_for(sequences, pairs, n_pairs, G, bounds.data());
     std::vector<int> status((size_t)G, DPX_OK);
     std::vector<char*> sb((size_t)G, nullptr); std::vector<size_t*> so((size_t)G, nullptr);
     std::vector<size_t> sbytes((size_t)G, 0);
@@ -214,7 +230,7 @@ int dpx_multi_align_batch_text(dpx_multi* m, const dpx_params* params, const cha
     *text = nullptr; *text_bytes = 0;
     const int G = (int)m->w.size();
     std::vector<size_t> bounds((size_t)G + 1);
-    dpx_multi_shard_bounds(pairs, n_pairs, G, bounds.data());
+    shard_bounds_for(sequences, pairs, n_pairs, G, bounds.data());
     std::vector<int> status((size_t)G, DPX_OK);
     std::vector<char*> tx((size_t)G, nullptr); std::vector<size_t> tb((size_t)G, 0);
     for (int g = 0; g < G; ++g) {

@@ -90,6 +90,17 @@ void pack_seq_lut(const uint8_t* src, int len, uint32_t* out, const uint8_t* cod
     if (k < len) out[w] = pack16_lut(src + k, len - k, code);
 }
 
+// Fingerprint of the blob's size, head and tail: together with the size check of the first and last pair in find() it keeps a
+// stale entry (memory released behind the library's back and reused for another input at the same address) from being used.
+// Only memory the CALLER just handed in is read.
+unsigned long long fingerprint_of(const char* blob, size_t n_bytes) {
+    unsigned long long h = 1469598103934665603ull ^ (unsigned long long)n_bytes;
+    auto mix = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; } };
+    const size_t k = std::min<size_t>(n_bytes, 64);
+    mix(blob, k); mix(blob + n_bytes - k, k);
+    return h;
+}
+
 }  // namespace
 
 int register_input(const char* blob, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs) {
@@ -189,19 +200,28 @@ int register_input(const char* blob, size_t n_bytes, const dpx_seq_pair* pairs, 
             }
         }
     });
+    s->fingerprint = fingerprint_of(blob, n_bytes);
     std::lock_guard<std::mutex> g(g_mu);
     g_by_blob[blob] = s; g_by_pairs[pairs] = s;
     return DPX_OK;
 }
 
-const Sidecar* find(const char* blob, const dpx_seq_pair* pairs, size_t n_pairs, size_t* first_pair) {
+const Sidecar* find(const char* blob, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs, size_t* first_pair) {
     std::lock_guard<std::mutex> g(g_mu);
     auto it = g_by_blob.find(blob);
-    if (it == g_by_blob.end()) return nullptr;
+    if (it == g_by_blob.end() || n_pairs == 0) return nullptr;
     const Sidecar* s = it->second;
-    if (pairs < s->pairs || pairs > s->pairs + s->n_pairs) return nullptr;
+    if (n_bytes != s->n_bytes || pairs < s->pairs || pairs > s->pairs + s->n_pairs) return nullptr;
     const size_t p0 = (size_t)(pairs - s->pairs);
     if (p0 + n_pairs > s->n_pairs) return nullptr;
+    if (fingerprint_of(blob, n_bytes) != s->fingerprint) return nullptr;          // not the bytes that were packed
+    auto same_sizes = [&](size_t i) {                                            // caller's pair i of its range vs. the packed record
+        const size_t k = p0 + i;
+        const int R = s->uniform ? s->R : (s->small ? (int)(s->sizes[k] & 0xffffu) : (int)s->sizes[2 * k]);
+        const int Q = s->uniform ? s->Q : (s->small ? (int)(s->sizes[k] >> 16) : (int)s->sizes[2 * k + 1]);
+        return pairs[i].referenceSize == R && pairs[i].querySize == Q;
+    };
+    if (!same_sizes(0) || !same_sizes(n_pairs - 1)) return nullptr;
     *first_pair = p0;
     return s;
 }

@@ -29,6 +29,7 @@ struct Sidecar {
     bool pinned = false;
     int max_r = 0, max_q = 0, min_r = 0, min_q = 0;
     unsigned long long cells = 0, sum_r = 0, sum_q = 0;
+    unsigned long long fingerprint = 0;   // of the blob's size, head and tail (see find())
 };
 
 // Builds and registers the sidecar of (blob, pairs).  Returns DPX_OK also when the input cannot be packed (> 4 symbols):
@@ -36,7 +37,7 @@ struct Sidecar {
 int register_input(const char* blob, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs);
 // Looks (blob, [pairs, pairs + n_pairs)) up: the pairs may be any sub-range of the registered index.  Returns the sidecar and
 // the position of pairs[0] in it, or nullptr.  The sidecar stays valid until the blob or the index is released.
-const Sidecar* find(const char* blob, const dpx_seq_pair* pairs, size_t n_pairs, size_t* first_pair);
+const Sidecar* find(const char* blob, size_t n_bytes, const dpx_seq_pair* pairs, size_t n_pairs, size_t* first_pair);
 const Sidecar* find_blob(const char* blob);
 // Called by dpx_free for every pointer it frees: drops the sidecar whose blob or index this is.
 void forget(const void* p);

@@ -184,3 +184,22 @@ def test_pipelined_strings_route_matches_the_serial_one(eng, algo, w):
     _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs), s, e, t, algo)
     _same(eng.align_batch(api.make_params(algo, flags=ALL, **w), inp.sequences, inp.pairs[700:17700]), s[700:17700], e[700:17700], t[700:17700], algo)
     inp.free()
+
+
+def test_stale_registration_is_not_used(eng):
+    """The packed copy belongs to the bytes that were registered: if the blob's head / tail or the sizes of the first / last pair of
+    the call no longer match (memory reused for another input at the same address, or edited in place), uploads fall back to the bytes."""
+    blob, pairs = synth.uniform_blob_pairs(300, 60, 60, 77)
+    blob = blob.copy(); pairs = pairs.copy()
+    api.register_input(blob, pairs)
+    p = api.make_params(api.LSW, flags=SE)
+    s0, e0, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False)
+    _same(eng.align_batch(p, blob, pairs), s0, e0, None, api.LSW)
+    blob[pairs["referenceIdx"][0]: pairs["referenceIdx"][0] + 60] = blob[pairs["queryIdx"][0]: pairs["queryIdx"][0] + 60]    # pair 0 now matches itself
+    s1, e1, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False)
+    assert s1[0] == 180 and s1[0] != s0[0]
+    _same(eng.align_batch(p, blob, pairs), s1, e1, None, api.LSW)
+    pairs["querySize"][-1] = 31                                                       # an edited index (last pair of the call)
+    s2, e2, _ = ol.align_batch(ol.params(ol.LSW), blob, pairs, strings=False)
+    _same(eng.align_batch(p, blob, pairs), s2, e2, None, api.LSW)
+    api.unregister_input(blob)

@@ -34,7 +34,7 @@ static int dispatch_wf(dpx_ctx* ctx, cudaStream_t st, int algo, bool tb, int K, 
 template <int G, int K>
 static int run_short(dpx_ctx* ctx, dpx_batch* b, SrArgs a, bool track, bool wide) {
     const int gpb = 128 / G;
-    a.bnd_stride = b->max_r + G + 2;
+    a.bnd_stride = b->max_r + 2 * G + 4;                       // G words of slack in front (shortread.cuh: bnd)
     a.rsel_stride = (b->max_r + 2 * G + 18 + 1) & ~1;          // the table is written 16 entries (one packed word) at a time
     const size_t smem = (size_t)gpb * ((size_t)a.bnd_stride * 4 + (size_t)a.rsel_stride * 2);
     auto launch = [&](auto kern) -> int {
@@ -63,13 +63,13 @@ static bool short_eligible(const dpx_batch* b, const dpx_params* p, int* B_out, 
     if (m - g > 127 || x - g < -128 || x - g > 127 || g < -4096) return false;
     if (b->max_r > 4096 || b->max_q > 65535) return false;
     // 16 pair groups per block, each with a boundary row (4 B per column) and a column table (2 B): must fit one block's shared memory
-    if ((size_t)16 * ((size_t)(b->max_r + 10) * 4 + (size_t)(b->max_r + 36) * 2) > (size_t)227 * 1024) return false;
+    if ((size_t)16 * ((size_t)(b->max_r + 20) * 4 + (size_t)(b->max_r + 36) * 2) > (size_t)227 * 1024) return false;
     const int B = std::max(2, -g);
-    // position bits: (Hmax + B) << k < 32768; one of the k bits marks the upper row of a row pair, the other
+    // position bits: (Hmax + B) << k < 65536 (unsigned 16-bit keys); one of the k bits marks the upper row of a row pair, the other
     // k-1 count steps inside blocks of 2^(k-1) steps; at most 256 blocks per pass
     const long long top = (long long)m * std::min(b->max_r, b->max_q) + B;
     int k = 0;
-    while (k < 8 && (top << (k + 1)) < 32768) ++k;
+    while (k < 8 && (top << (k + 1)) < 65536) ++k;
     if (k < 3) return false;                  // below that the fold every 2^(k-1) steps costs more than it saves
     if (((long long)b->max_r + 16) >> (k - 1) >= 255) return false;
     *B_out = B; *wide = w; *kbits_out = k;

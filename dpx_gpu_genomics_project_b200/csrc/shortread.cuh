@@ -20,14 +20,16 @@
 //   hg  = h + G2                       plain 32-bit add: all values carry a bias B >= -gap, so the low half
 //                                      always carries into the high half and G2's high half is gap-1  (either pipe)
 //   key = h * 2^k + code               one IMAD on the FMA pipe: the (positive, biased) score moves up k bits in
-//                                      both halves; the low k bits are [upper row of the row pair : 1][2^(k-1)-1 -
-//                                      (step mod 2^(k-1)) : k-1]
-//   best= vimax3.s16x2(best, key_r, key_r+1)   one VIMNMX3 per TWO rows: highest score, then upper row, then
+//                                      both halves (UNSIGNED 16-bit keys: (Hmax + B) << k < 65536); the low k bits are
+//                                      [upper row of the row pair : 1][2^(k-1)-1 - (step mod 2^(k-1)) : k-1]; the two code
+//                                      words count down with one IMAD each per step
+//   best= vimax3.u16x2(best, key_r, key_r+1)   one VIMNMX3 per TWO rows: highest score, then upper row, then
 //                                      earliest step
-//   Every 2^(k-1) steps (warp-uniform) the row-pair registers are folded into one 32-bit key per pair and lane,
-//   (score | 31-row | 255-block | code): higher score, then smaller row, then earlier step — exactly the
-//   reference's first-strict-max-in-row-major rule; lanes / passes are merged with the same order.
-// => 3.5 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells).
+//   Every 2^(k-1) steps (warp-uniform; 64 steps for 150 bp reads at match 3) the row-pair registers are folded into one
+//   32-bit key per pair and lane, (score | 31-row | 255-block | code): higher score, then smaller row, then earlier step —
+//   exactly the reference's first-strict-max-in-row-major rule; lanes / passes are merged with the same order.  The fold
+//   spreads the three fields with masks (ALU) and multiplies by run-time powers of two (FMA pipe), two candidates per VIMNMX3.U32.
+// => 3.5 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells); 4 more ALU-pipe instructions per column step.
 // Registers hold hg = H + gap + B ("already gapped"), which is what the right and lower neighbours need;
 // the diagonal neighbour wants H, so the table holds score - gap.
 #pragma once
@@ -70,6 +72,20 @@ __device__ __forceinline__ uint32_t fma_add(uint32_t a, uint32_t one, uint32_t b
     return d;
 }
 
+// A plain 32-bit add that stays one (tools/sr_rowmix_bench.cu: next to the half-rate DPX / PRMT instructions a VIADD costs about one
+// clock per row less than the same add as an IMAD -- the two half-rate pipes do not overlap perfectly, a full-rate add slips in between).
+__device__ __forceinline__ uint32_t alu_add(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm volatile("add.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint32_t fma_mad(uint32_t a, uint32_t m, uint32_t b) {   // a * m + b, m a run-time value: stays an IMAD
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(m), "r"(b));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {       // PTX shl clamps the amount: n >= 32 gives 0
     uint32_t d;
     asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(v), "r"(n));
@@ -79,14 +95,14 @@ __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) {       //
 __device__ __forceinline__ uint32_t get2(const uint32_t* __restrict__ w, int k) { return (w[k >> 4] >> (2 * (k & 15))) & 3u; }
 
 template <int G, int K, bool TRACK, bool WIDE>
-__global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
+__global__ void __launch_bounds__(128, 4) sr_lsw_kernel(const SrArgs a) {
     extern __shared__ uint32_t sr_smem[];
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int GPW = 32 / G;                    // groups per warp
     constexpr int GPB = 128 / G;                   // groups per block
     const int lane = threadIdx.x & 31, gl = lane % G, gw = lane / G;
     const int gib = threadIdx.x / G;
-    uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride;
+    uint32_t* __restrict__ bnd = sr_smem + (size_t)gib * a.bnd_stride + G;        // bnd[j], j >= -G + 2 (the last lane's early steps land in front)
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(sr_smem + (size_t)GPB * a.bnd_stride) + (size_t)gib * a.rsel_stride;
     const uint32_t B2 = a.B2, Bg2 = a.Bg2, G2 = a.G2, one = a.one;
     const uint32_t xs4 = a.xs_byte * 0x01010101u, dms = (a.ms_byte ^ a.xs_byte) & 0xffu;      // xor: no byte carries, any signs
@@ -141,19 +157,27 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                 rsel[k + G] = (uint16_t)((k < RA) ? (nA | ((nA | 8u) << 4) | 0xcc00u) : 0xcc88u);
             }
         }
-        for (int c = gl; !WIDE && 16 * c < Rw + G + 2; c += G) {
-            const int k0 = 16 * c;
-            const uint32_t wA = (k0 < RA) ? refA[c] : 0u, wB = (k0 < RB) ? refB[c] : 0u;
-            const int nvA = RA - k0, nvB = RB - k0;                                         // bases of this word that exist
-            #pragma unroll
-            for (int t = 0; t < 16; ++t) {
-                const uint32_t nA = (t < nvA) ? ((wA >> (2 * t)) & 3u) : 8u;
-                const uint32_t nB = (t < nvB) ? (4u + ((wB >> (2 * t)) & 3u)) : 12u;
-                rsel[k0 + t + G] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
+        if (!WIDE) {
+            // words whose 16 bases exist in both pairs: every lane builds the two entries (2 gl, 2 gl + 1) of each word.  A byte
+            // of an entry is 0x11 * base + 0x80 (pair A) / + 0xc4 (pair B): the two 4-bit fields of a word are spread over four
+            // bytes by one multiplication (x + (x << 14), masked), the constant 0x11 by another.
+            const int nfull = min(RA, RB) >> 4;
+            uint32_t* __restrict__ rsel32 = reinterpret_cast<uint32_t*>(rsel + G) + gl;
+            #pragma unroll 4
+            for (int c = 0; c < nfull; ++c) {
+                const uint32_t x = (refA[c] >> (4 * gl)) & 0xfu, y = (refB[c] >> (4 * gl)) & 0xfu;
+                const uint32_t z = fma_mad(y, a.one << 8, x);
+                const uint32_t z2 = fma_mad(z, a.one * 0x4001u, 0u) & 0x03030303u;
+                rsel32[8 * c] = fma_mad(z2, a.one * 0x11u, 0xc480c480u);
+            }
+            // the rest, pads included, one entry at a time
+            for (int k = 16 * nfull + gl; k < Rw + G + 2; k += G) {
+                const uint32_t nA = (k < RA) ? get2(refA, k) : 8u;
+                const uint32_t nB = (k < RB) ? (4u + get2(refB, k)) : 12u;
+                rsel[k + G] = (uint16_t)(nA | ((nA | 8u) << 4) | (nB << 8) | ((nB | 8u) << 12));
             }
         }
-        if (passes > 1)
-            for (int e = gl; e < Rw + G + 2; e += G) bnd[e] = Bg2;
+        for (int e = gl; e < Rw + G + 2; e += G) bnd[e] = Bg2;                      // pass 0 reads the bias everywhere
         __syncwarp();
 
         int bestA = 0, rowA = 0, colA = 0, bestB = 0, rowB = 0, colB = 0;
@@ -181,16 +205,15 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
             for (int r = 0; r < (K + 1) / 2; ++r) best[r] = 0;
             uint32_t best2 = B2;                                 // !TRACK: one running max for all rows
             uint32_t bot = Bg2, topprev = Bg2;
-            const bool more = (p + 1 < passes);
+            const bool store_bot = (gl == G - 1) && (p + 1 < passes);       // j < 1 lands in the slack in front of the row
+            const uint32_t csdec = 0xfffefffFu;                             // -1 in both halves
 
 #define DPX_SR_STEP(S, OLD, NEW)                                                                         \
             {                                                                                            \
                 const int j = (S) - gl + 1;                                                              \
                 uint32_t top = __shfl_up_sync(FULL, bot, 1, G);                                          \
-                if (gl == 0) top = (p == 0) ? Bg2 : bnd[j];                                              \
+                if (gl == 0) top = bnd[j];                                                               \
                 const uint32_t rs = rsel[(S) - gl + G];                                                  \
-                const uint32_t csL = (uint32_t)(smask - ((S) & smask)) * 0x00010001u;                    \
-                const uint32_t csU = csL + (uint32_t)(smask + 1) * 0x00010001u;                          \
                 uint32_t keyprev = 0;                                                                    \
                 uint32_t upg = top, diag = topprev;                                                      \
                 topprev = top;                                                                           \
@@ -200,12 +223,12 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                     const uint32_t e = __viaddmax_s16x2(diag, sc, OLD[r]);   /* off the row chain */     \
                     const uint32_t h = __vimax3_s16x2(e, upg, B2);           /* chain: h -> hg -> h */   \
                     diag = OLD[r];                                                                       \
-                    NEW[r] = fma_add(h, one, G2);                                                        \
+                    NEW[r] = alu_add(h, G2);                                                              \
                     upg = NEW[r];                                                                        \
                     if (TRACK) {                                                                         \
                         const uint32_t key = fma_add(h, kmul, (r & 1) ? csL : csU);  /* IMAD, FMA pipe */\
-                        if (r & 1) best[r >> 1] = __vimax3_s16x2(best[r >> 1], keyprev, key);            \
-                        else if (r == K - 1) best[r >> 1] = __vmaxs2(best[r >> 1], key);                 \
+                        if (r & 1) best[r >> 1] = __vimax3_u16x2(best[r >> 1], keyprev, key);            \
+                        else if (r == K - 1) best[r >> 1] = __vmaxu2(best[r >> 1], key);                 \
                         keyprev = key;                                                                   \
                     } else {                                                                             \
                         if (r & 1) best2 = __vimax3_s16x2(best2, keyprev, h);                            \
@@ -214,12 +237,18 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                     }                                                                                    \
                 }                                                                                        \
                 bot = NEW[K - 1];                                                                        \
-                if (gl == G - 1 && more && j >= 1) bnd[j] = bot;                                         \
+                if (TRACK) { csL = fma_add(csL, one, csdec); csU = fma_add(csU, one, csdec); }           \
+                if (store_bot) bnd[j] = bot;                                                             \
             }
 
             const int bs = smask + 1;                            // steps per position block (even)
+            // field multipliers of the fold, run-time values so that the spreading stays on the FMA pipe
+            const uint32_t m12 = one << 12, m8 = one << 8, nrow = 0u - (one << (a.kbits + 8));
+            const uint32_t smA = 0xffffu & ~(uint32_t)kmask, rbit = (uint32_t)bs;
             for (int blk = 0; blk * bs < nsteps2; ++blk) {
                 const int s_end = min((blk + 1) * bs, nsteps2);
+                uint32_t csL = (uint32_t)smask * 0x00010001u;    // step code of the lower row, counts down; the upper row's carries the row bit
+                uint32_t csU = csL + (uint32_t)bs * 0x00010001u;
                 #pragma unroll 1
                 for (int s = blk * bs; s < s_end; s += 2) {
                     DPX_SR_STEP(s, hgA, hgB)
@@ -228,15 +257,25 @@ __global__ void __launch_bounds__(128) sr_lsw_kernel(const SrArgs a) {
                 if (TRACK) {
                     // fold the row-pair registers into the lane keys (warp-uniform point).  lane key =
                     // score << (k+12) | (31 - row) << (k+7) | (255 - blk) << (k-1) | step code
-                    const uint32_t tagb = (uint32_t)(255 - blk) << (a.kbits - 1);
-                    const uint32_t rbit = (uint32_t)(smask + 1);
+                    const uint32_t tag0 = ((uint32_t)(255 - blk) << (a.kbits - 1)) | (30u << (a.kbits + 7));
+                    uint32_t cA[(K + 1) / 2], cB[(K + 1) / 2];
                     #pragma unroll
                     for (int q = 0; q < (K + 1) / 2; ++q) {
-                        const uint32_t tag = tagb | ((uint32_t)(30 - 2 * q) << (a.kbits + 7));   // lower row of the pair; the row bit adds 1
-                        const uint32_t lo = best[q] & 0xffffu, hi = best[q] >> 16;
-                        laneKeyA = max(laneKeyA, (((lo & ~(uint32_t)kmask) << 12) | ((lo & rbit) << 8) | (lo & (uint32_t)smask)) + tag);
-                        laneKeyB = max(laneKeyB, (((hi & ~(uint32_t)kmask) << 12) | ((hi & rbit) << 8) | (hi & (uint32_t)smask)) + tag);
+                        const uint32_t tag = fma_mad((uint32_t)q, nrow, tag0);               // 30 - 2q: lower row of the pair; the row bit adds 1
+                        const uint32_t x = best[q], y = x >> 16;
+                        cA[q] = fma_mad(x & smA, m12, fma_mad(x & rbit, m8, fma_add(x & (uint32_t)smask, one, tag)));
+                        cB[q] = fma_mad(y & smA, m12, fma_mad(y & rbit, m8, fma_add(y & (uint32_t)smask, one, tag)));
                     }
+                    #pragma unroll
+                    for (int q = 0; q + 1 < (K + 1) / 2; q += 2) {
+                        laneKeyA = __vimax3_u32(laneKeyA, cA[q], cA[q + 1]);
+                        laneKeyB = __vimax3_u32(laneKeyB, cB[q], cB[q + 1]);
+                    }
+                    if (((K + 1) / 2) & 1) {
+                        laneKeyA = max(laneKeyA, cA[(K + 1) / 2 - 1]);
+                        laneKeyB = max(laneKeyB, cB[(K + 1) / 2 - 1]);
+                    }
+                    // (best[] runs on: a key that survives from an earlier block was folded there with a better block tag)
                 }
             }
 #undef DPX_SR_STEP

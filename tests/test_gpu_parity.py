@@ -216,10 +216,10 @@ def _staged(eng, blob, pairs, params):
 
 
 def _short_eligible(R, Q, w):
-    """Mirror of short_eligible() in csrc/dpxalign.cu: int16 range with k >= 3 position bits, <= 255 step blocks."""
+    """Mirror of short_eligible() in csrc/dpxalign.cu: unsigned 16-bit keys with k >= 3 position bits, <= 255 step blocks."""
     top = w["match"] * min(R, Q) + max(2, -w["gap_open"])
     k = 0
-    while k < 8 and (top << (k + 1)) < 32768:
+    while k < 8 and (top << (k + 1)) < 65536:
         k += 1
     return k >= 3 and R <= 4096 and ((R + 16) >> (k - 1)) < 255
 

@@ -143,13 +143,20 @@ def measured_peaks():
 
 
 def sass_counts(key):
-    """ALU-pipe and issued instructions per cell of a kernel's hot loop, from the committed SASS counts."""
+    """Clocks of an SM sub-partition per cell (one warp instruction = 32 lanes) that the kernel's hot loop needs on the ALU pipe, on
+    the FMA pipe and at the issue port, from the committed SASS counts (tools/sass_counts.py states the measured per-instruction model)."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
         k = d[key]
-        return k["alu_per_cell"], k["issue_per_cell"]
+        return {"alu_clk_per_cell": k["alu_clk_per_cell"], "fma_clk_per_cell": k["fma_clk_per_cell"], "issued_instr_per_cell": k["issue_per_cell"],
+                "half_rate_alu_instr_per_cell": k["half_rate_alu_per_cell"]}
     except Exception:
-        return None, None
+        return None
+
+
+def issue_roof_cells_per_clk_per_sm(m):
+    """4 sub-partitions x 32 lanes over the busiest of the three resources."""
+    return 128.0 / max(m["alu_clk_per_cell"], m["fma_clk_per_cell"], m["issued_instr_per_cell"])
 
 
 def make_inputs(wl, n_pairs, seed):
@@ -347,12 +354,12 @@ def bench_long(C, steps, warmup, with_cpu):
     peaks, _ = measured_peaks()
     f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
     roofline = {"bound": "dpx_issue", "achieved": value, "unit": "GCUPS", "kernel": LONG["kernel"], "traffic": None, "kernel_ms": ms_per_step}
-    alu_pc, issue_pc = sass_counts(LONG["sass"])
-    if alu_pc:
+    mix = sass_counts(LONG["sass"])
+    if mix:
         # the steady loop's instruction mix is the same at every lane width the table kernels use; the roof is the whole machine's
-        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * C.sms * world * f_mhz * 1e6 / 1e9
+        peak = issue_roof_cells_per_clk_per_sm(mix) * C.sms * world * f_mhz * 1e6 / 1e9
         roofline.update({"peak": peak, "frac": value / peak,
-                         "model": {"alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc, "sms": C.sms, "gpus": world, "sm_mhz": f_mhz, "sass_key": LONG["sass"],
+                         "model": {**mix, "sms": C.sms, "gpus": world, "sm_mhz": f_mhz, "sass_key": LONG["sass"],
                                    "note": "a systolic chain of warps, each row step a dependent chain: latency- and fill-bound below the issue roofline"}})
     out = {"metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
@@ -572,21 +579,20 @@ def bench_batched(C, cfg_no, steps, warmup, score_only=False, n_pairs=0, with_cp
     sass_key = wl["sass"].format(track=not score_only)
     if cfg_no != 2 and not want_strings:
         sass_key = sass_key.replace("traceback=True", "traceback=False")
-    alu_pc, issue_pc = sass_counts(sass_key)
+    mix = sass_counts(sass_key)
     kern_ms = fill_ms if fill_ms > 0 else ms_per_step          # the dominant kernel = the fill kernel(s) of one step
     kernel_gcups = cells / (kern_ms * 1e-3) / 1e9
     roofline = {"bound": "dpx_issue", "achieved": kernel_gcups, "unit": "GCUPS", "kernel": wl["kernel"].split(" (+")[0], "traffic": None,
                 "kernel_ms": kern_ms}
-    if alu_pc:
+    if mix:
         # real cells only: slots a kernel spends on padding (config 4: 129 diagonals on 160 slots; ragged duos) count against frac
-        peak = min(64.0 / alu_pc, 128.0 / issue_pc) * C.sms * f_mhz * 1e6 / 1e9
+        peak = issue_roof_cells_per_clk_per_sm(mix) * C.sms * f_mhz * 1e6 / 1e9
         roofline.update({"peak": peak, "frac": kernel_gcups / peak,
-                         "model": {"alu_pipe_lanes_per_clk_per_sm": 64, "issue_lanes_per_clk_per_sm": 128,
-                                   "alu_instr_per_cell": alu_pc, "issued_instr_per_cell": issue_pc,
+                         "model": {**mix, "clocks_per_warp_instruction": "ALU pipe 2 (plain adds 1); FMA pipe: IMAD 2; issue 1",
                                    "sms": C.sms, "sm_mhz": f_mhz, "sass_key": sass_key,
                                    "source": "profiles/sass_counts.json (the kernel's own SASS hot loop) + profiles/r02_dpx_microbench.json"}})
         if cfg_no == 2:
-            floor = 1.5                                  # PRMT + 2 packed DPX per cell pair: the least this recurrence can issue on the ALU pipe
+            floor = 1.5                                  # PRMT + 2 packed DPX per cell pair, 2 clocks each: the least this recurrence needs on the ALU pipe
             roofline["frac_of_floor_roof"] = kernel_gcups / (64.0 / floor * C.sms * f_mhz * 1e6 / 1e9)
             roofline["model"]["alu_floor_instr_per_cell"] = floor
     if cfg_no == 2:

@@ -20,7 +20,8 @@
 //           Dc = D' & ~2 (code 1), Ic = I' & ~1 (code 2)
 //           h' = vimax3(ds, Dc, Ic)          code 0 DIAG < 1 UP < 2 LEFT: exactly the reference's LEFT > UP > DIAG ties
 //           Ho = (h' | 3) + 4*goe            "H + open + extend", code 3: what the right / lower / diagonal neighbours need
-//   => per cell-pair 10 ALU-pipe (PRMT, 3 DPX, 3 LOP3 clean, 3 LOP3 to bank the 4-bit code) + 6 FMA-pipe instructions.
+//   => per cell-pair, with traceback: PRMT, 3 DPX, 4 LOP3 (clean D / I, the code, the two open flags in one) on the ALU pipe and
+//      5 IMAD (ds, two to bank the 4-bit code, two for Ho = (h' - code) + 4*goe + 3); without: PRMT, 3 DPX, one LOP3 and 2 IMAD.
 //   Linear  m  = viaddmax(Hg[diag], tab, Hg[up])   diag code 0 / up code 1;  h' = viaddmax(Hg[left], 1, m)  left code 2
 //           Hg = (h' | 3) + 4g - 2           "H + gap", code 1
 //   => per cell-pair 5 ALU-pipe + 3 FMA-pipe instructions.
@@ -36,7 +37,7 @@
 // biased positive (>= the largest |constant|), so adding a negative constant ALWAYS carries out of the low half (the
 // constant's high half is pre-decremented) and adding a table entry (>= 0) NEVER does.
 //
-// Traceback: CB = 4 bits per cell (Gotoh: dir | D-open << 2 | I-open << 3) or 2 (linear: dir); each lane-step banks K
+// Traceback: CB = 4 bits per cell (Gotoh: dir | I-open << 2 | D-open << 3) or 2 (linear: dir); each lane-step banks K
 // cells per pair into W = K*CB/16 words whose low / high halves belong to pair A / B (row r of the block sits in
 // word r / (16/CB), nibble or bit pair (16/CB - 1 - r % (16/CB))), stored [pass][step][w][lane]: one warp store = one
 // 128-byte line.  Algorithmic traceback bytes per cell: 0.5 (Gotoh), 0.25 (linear).
@@ -47,7 +48,7 @@
 namespace dpx {
 
 constexpr uint32_t PW_DIAG = 0, PW_UP = 1, PW_LEFT = 2;     // direction codes of this kernel family
-constexpr uint32_t PW_DOPEN = 4, PW_IOPEN = 8;
+constexpr uint32_t PW_IOPEN = 4, PW_DOPEN = 8;              // = 4 * (D' & I' & 3): see the Gotoh step
 constexpr uint32_t PW_SW_DIAG = 0, PW_SW_LEFT = 1, PW_SW_UP = 2, PW_SW_STOP = 3;   // Smith-Waterman codes of this family
 
 struct PwGeom {
@@ -243,15 +244,18 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
                             const uint32_t ds = fma_add(diag, one, sc);                                              \
                             const uint32_t Dn = pw_addmax<PACKED>(upD, ext2, up);                                     \
                             const uint32_t In = pw_addmax<PACKED>(Ic[r], ext2, OLD[r]);                               \
-                            const uint32_t Dc = Dn & ~REP2, Icn = In & ~REP1;                            \
+                            /* the codes only matter to the traceback: without it D / I keep whatever code won (the 4X part is the \
+                               same either way, and (h' | 3) below renormalises what the neighbours read) */                        \
+                            const uint32_t Dc = TB ? (Dn & ~REP2) : Dn, Icn = TB ? (In & ~REP1) : In;                        \
                             h = pw_max3<PACKED>(ds, Dc, Icn);                                                         \
                             upD = Dc; Ic[r] = Icn;                                                                   \
-                            if (TB) {   /* nibble = dir + 4 * (D opened) + 8 * (I opened): Dn - Dc = 2 * opened, In - Icn = opened */ \
+                            if (TB) {   /* nibble = dir + 4 * (I opened) + 8 * (D opened).  D' ends in 01 (extend) or 11 (open),   \
+                                           I' in 10 or 11: D' & I' & 3 = 2 * (D opened) + (I opened), one LOP3 */          \
                                 const uint32_t t = h & REP3;                                                  \
+                                const uint32_t f = Dn & In & REP3;                                            \
                                 acc[r / CPH] = fma_add(acc[r / CPH], sixteen, t);                                    \
-                                acc[r / CPH] = fma_add(fma_add(Dc, minus1, Dn), two, acc[r / CPH]);                  \
-                                acc[r / CPH] = fma_add(fma_add(Icn, minus1, In), eight, acc[r / CPH]);               \
-                                NEW[r] = fma_add(h | REP3, one, addc);                                        \
+                                acc[r / CPH] = fma_add(f, four, acc[r / CPH]);                                       \
+                                NEW[r] = fma_add(fma_add(t, minus1, h), one, addc3);   /* (h' | 3) + addc without a LOP3: the ALU pipe is the full one */ \
                             }                                                                                        \
                         } else if constexpr (SW) {                                                                   \
                             const uint32_t m = pw_addmax<PACKED>(diag, sc, OLD[r]);          /* diag 0 / left 1 */    \

@@ -25,7 +25,9 @@ enum Op { MAX_S32, VIMAX3_S32, VIADDMAX_S32, VIADDMAX_S32_RELU, VIMAX3_S32_RELU,
           VIMAX_S16X2, VIMAX3_S16X2, VIADDMAX_S16X2, VIADDMAX_S16X2_RELU, VIMAX3_S16X2_RELU, VIBMAX_S16X2_PRED,
           IADD, IADD3, LOP3, PRMT, IMAD, SHF, ISETP_SEL, SHFL_UP,
           MIX_VIADDMAX_IMAD, MIX_VIADDMAX16_IMAD, MIX_VIADDMAX_LOP3, MIX_PRMT_IMAD, MIX_2DPX_1IMAD, LDS32,
-          CHAIN_RELU_IMAD, CHAIN_SHFL_RELU, OP_COUNT };
+          CHAIN_RELU_IMAD, CHAIN_SHFL_RELU,
+          MIX_DPX16_LOP3, MIX_DPX16_VIADD, MIX_DPX32_VIADD, MIX_DPX16_VIMNMX16, MIX_2DPX16_VIADD, MIX_PRMT_DPX16, VIMAX3_U16X2, MIX_DPX16_VIADD_IMAD,
+          LOP3_VOL, MIX_DPX16_LOP3_VOL, MIX_DPX16_2LOP3_VOL, MIX_IMAD_LOP3_VOL, MIX_IMAD_VIADD, OP_COUNT };
 
 static const char* op_name[OP_COUNT] = {
     "max.s32 (VIMNMX)", "__vimax3_s32 (VIMNMX3)", "__viaddmax_s32 (VIADDMNMX)", "__viaddmax_s32_relu (VIADDMNMX.RELU)",
@@ -35,8 +37,12 @@ static const char* op_name[OP_COUNT] = {
     "IADD (a+b)", "IADD3 (a+b+c)", "LOP3 (a^b^c)", "PRMT (__byte_perm)", "IMAD (a*b+c)", "SHF (funnelshift)", "ISETP+SEL",
     "SHFL.UP", "mix: 1 VIADDMNMX + 1 IMAD", "mix: 1 VIADDMNMX.S16x2 + 1 IMAD", "mix: 1 VIADDMNMX + 1 LOP3",
     "mix: 1 PRMT + 1 IMAD", "mix: 2 VIADDMNMX + 1 IMAD", "LDS.32 (conflict-free)",
-    "chain: VIADDMNMX.RELU -> IMAD (cross-pipe round trip)", "chain: SHFL.UP -> VIADDMNMX.RELU" };
-static const int op_results_per_iter[OP_COUNT] = {1,1,1,1,1,1, 1,1,1,1,1,1, 1,1,1,1,1,1,1, 1, 2,2,2,2,3, 1, 2, 2};
+    "chain: VIADDMNMX.RELU -> IMAD (cross-pipe round trip)", "chain: SHFL.UP -> VIADDMNMX.RELU",
+    "mix: 1 VIADDMNMX.S16x2 + 1 LOP3", "mix: 1 VIADDMNMX.S16x2 + 1 VIADD", "mix: 1 VIADDMNMX + 1 VIADD", "mix: 1 VIADDMNMX.S16x2 + 1 VIMNMX.S16x2",
+    "mix: 2 VIADDMNMX.S16x2 + 1 VIADD", "mix: 1 PRMT + 1 VIADDMNMX.S16x2", "__vimax3_u16x2 (VIMNMX3.U16x2)", "mix: 1 VIADDMNMX.S16x2 + 1 VIADD + 1 IMAD",
+    "LOP3 (asm volatile, majority)", "mix: 1 VIADDMNMX.S16x2 + 1 LOP3 (volatile)", "mix: 1 VIADDMNMX.S16x2 + 2 LOP3 (volatile)",
+    "mix: 1 IMAD + 1 LOP3 (volatile)", "mix: 1 IMAD + 1 VIADD" };
+static const int op_results_per_iter[OP_COUNT] = {1,1,1,1,1,1, 1,1,1,1,1,1, 1,1,1,1,1,1,1, 1, 2,2,2,2,3, 1, 2, 2, 2,2,2,2,3,2,1,3, 1,2,3,2,2};
 
 template <int OP, int CH>
 __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t* out, long long* t_first, long long* t_last) {
@@ -81,6 +87,20 @@ __global__ void __launch_bounds__(1024) bench(uint32_t seed, uint32_t* out, long
             if (OP == MIX_2DPX_1IMAD)     { x[k] = (uint32_t)__viaddmax_s32((int)x[k], (int)c, (int)b); x[k] = (uint32_t)__viaddmax_s32((int)x[k], (int)a, (int)c); y[k] = y[k] * c + a; }
             if (OP == LDS32)              x[k] = sm[(x[k] + threadIdx.x) & 1023u] ;
             if (OP == CHAIN_RELU_IMAD)    { x[k] = (uint32_t)__viaddmax_s32_relu((int)x[k], (int)c, (int)y[k]); x[k] = x[k] * c + b; }
+            if (OP == MIX_DPX16_LOP3)     { x[k] = __viaddmax_s16x2(x[k], c, b); y[k] = (y[k] ^ a) & c; }
+            if (OP == MIX_DPX16_VIADD)    { x[k] = __viaddmax_s16x2(x[k], c, b); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); }
+            if (OP == MIX_DPX32_VIADD)    { x[k] = (uint32_t)__viaddmax_s32((int)x[k], (int)c, (int)b); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); }
+            if (OP == MIX_DPX16_VIMNMX16) { x[k] = __viaddmax_s16x2(x[k], c, b); asm volatile("max.s16x2 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); }
+            if (OP == MIX_2DPX16_VIADD)   { x[k] = __viaddmax_s16x2(x[k], c, b); x[k] = __vimax3_s16x2(x[k], a, c); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); }
+            if (OP == MIX_PRMT_DPX16)     { x[k] = __viaddmax_s16x2(x[k], c, b); y[k] = __byte_perm(y[k], b, c); }
+            if (OP == VIMAX3_U16X2)       x[k] = __vimax3_u16x2(x[k], y[k], c);
+            if (OP == MIX_DPX16_VIADD_IMAD){ x[k] = __viaddmax_s16x2(x[k], c, b); asm volatile("add.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); y[k] = y[k] * c + b; }
+            if (OP == LOP3_VOL)           asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(x[k]) : "r"(y[k]), "r"(c));
+            if (OP == MIX_DPX16_LOP3_VOL) { x[k] = __viaddmax_s16x2(x[k], c, b); asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(y[k]) : "r"(a), "r"(c)); }
+            if (OP == MIX_DPX16_2LOP3_VOL){ x[k] = __viaddmax_s16x2(x[k], c, b); asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(y[k]) : "r"(a), "r"(c));
+                                            asm volatile("lop3.b32 %0, %0, %1, %2, 0xd4;" : "+r"(y[k]) : "r"(b), "r"(c)); }
+            if (OP == MIX_IMAD_LOP3_VOL)  { x[k] = x[k] * c + b; asm volatile("lop3.b32 %0, %0, %1, %2, 0xe8;" : "+r"(y[k]) : "r"(a), "r"(c)); }
+            if (OP == MIX_IMAD_VIADD)     { x[k] = x[k] * c + b; asm volatile("add.u32 %0, %0, %1;" : "+r"(y[k]) : "r"(a)); }
             if (OP == CHAIN_SHFL_RELU)    { x[k] = __shfl_up_sync(0xffffffffu, x[k], 1); x[k] = (uint32_t)__viaddmax_s32_relu((int)x[k], (int)c, (int)y[k]); }
         }
     }

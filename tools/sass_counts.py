@@ -1,7 +1,17 @@
-"""Counts the instructions of each fill kernel's hot loop in the built libdpxalign.so and splits them by
-issue pipe (measured model, profiles/r01_dpx_microbench*.json: ALU pipe incl. DPX 64 lanes/clk/SM, FMA pipe
-64 lanes/clk/SM, issue 128 lanes/clk/SM).  Output: profiles/sass_counts.json, read by bench.py for the
-DPX-issue roofline (I_cell counted from the committed SASS inner loop).
+"""Counts the instructions of each fill kernel's hot loop in the built libdpxalign.so and turns them into clocks of an SM
+sub-partition per loop trip with the measured model of profiles/r02_dpx_microbench.json (r02, second version):
+  * ALU pipe: 2 clocks per warp instruction -- DPX (VIMNMX3*, VIADDMNMX*), PRMT, SHF, LEA, LOP3, ISETP, SEL all run at 63.9
+    lanes/clk/SM, alone and in any mix ("1 PRMT + 1 VIADDMNMX.S16x2", "1 VIADDMNMX.S16x2 + 1 LOP3 (volatile)": 63.9 for the pair
+    = 4 clocks; the first LOP3 measurement had been folded by the compiler) -- except plain adds: "1 VIADDMNMX + 1 VIADD" = 85.3
+    lanes/clk/SM = 3 clocks per pair, so VIADD / IADD3 count 1;
+  * FMA pipe: IMAD* 2 clocks (63.9 lanes/clk/SM);
+  * issue: 1 clock per warp instruction.
+A loop trip cannot take less than the largest of the three; bench.py turns that into the roofline (I_cell counted
+from the committed SASS inner loop).  The two pipes do not overlap perfectly: next to packed DPX instructions an IMAD costs 0.3 - 0.9 clocks
+("1 VIADDMNMX.S16x2 + 1 IMAD" = 100.5 lanes/clk/SM = 2.55 clocks per pair); tools/sr_rowmix_bench.cu measures that for the
+short-read kernel's exact mix (8.9 clocks per row of 7 + 1 ALU-pipe clocks and one IMAD).  The model leaves it out, so `frac`
+is against an upper bound.
+Output: profiles/sass_counts.json.
 
 usage: python tools/sass_counts.py [libdpxalign.so] [out.json]"""
 import collections
@@ -19,6 +29,9 @@ OTHER = ("LDS", "STS", "LDG", "STG", "LDC", "LDCU", "SHFL", "BRA", "ATOM", "RED"
          "UIADD3", "UISETP", "UMOV", "ULEA", "ULOP3", "USHF", "UIMAD", "USEL", "UPRMT", "UFLO", "UPOPC", "LDSM", "MATCH", "CALL", "RET")
 
 
+FULL_RATE_ALU = ("VIADD", "IADD3", "IADD")
+
+
 def pipe(op):
     base = op.split(".")[0]
     if base in FMA_PIPE:
@@ -26,6 +39,14 @@ def pipe(op):
     if base in OTHER:
         return "other"
     return "alu"
+
+
+def alu_clocks(op):
+    """Clocks of the ALU pipe one warp instruction takes (module docstring)."""
+    base = op.split(".")[0]
+    if pipe(op) != "alu":
+        return 0
+    return 1 if base in FULL_RATE_ALU else 2
 
 
 # kernel-name regex -> (label, cells per inner-loop trip as a function of template ints)
@@ -79,15 +100,21 @@ def main():
             for op, c in hist.items():
                 by_pipe[pipe(op)] += c
             cells = info.pop("cells"); info.pop("largest", None)
+            alu_clk = sum(alu_clocks(op) * c for op, c in hist.items())
+            fma_clk = 2 * by_pipe["fma"]
             key = label + ":" + ",".join(f"{k}={v}" for k, v in info.items())
             res[key] = dict(mangled=name, loop_instructions=len(body), cells_per_trip=cells, dpx_instructions=dpx,
                             alu_pipe=by_pipe["alu"], fma_pipe=by_pipe["fma"], other=by_pipe["other"],
                             alu_per_cell=by_pipe["alu"] / cells, fma_per_cell=by_pipe["fma"] / cells,
-                            issue_per_cell=len(body) / cells, histogram=dict(hist.most_common()), **info)
+                            issue_per_cell=len(body) / cells,
+                            alu_clk_per_cell=alu_clk / cells, fma_clk_per_cell=fma_clk / cells,
+                            half_rate_alu_per_cell=sum(c for op, c in hist.items() if alu_clocks(op) == 2) / cells,
+                            bound_clk_per_cell=max(alu_clk, fma_clk, len(body)) / cells,
+                            histogram=dict(hist.most_common()), **info)
     with open(out, "w") as f:
         json.dump(res, f, indent=1, sort_keys=True)
     for k, v in sorted(res.items()):
-        print(f"{k:70s} instr/cell {v['issue_per_cell']:.2f}  alu/cell {v['alu_per_cell']:.2f}  fma/cell {v['fma_per_cell']:.2f}")
+        print(f"{k:70s} clk/cell: issue {v['issue_per_cell']:.2f}  alu {v['alu_clk_per_cell']:.2f}  fma {v['fma_clk_per_cell']:.2f}")
 
 
 if __name__ == "__main__":

@@ -20,6 +20,7 @@ WANT = ["Kernel Name", "gpu__time_duration.sum", "launch__grid_size", "launch__b
         "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+        "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio",
         "sm__cycles_elapsed.max", "sm__cycles_active.avg"]
 
 

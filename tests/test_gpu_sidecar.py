@@ -134,7 +134,8 @@ def test_stripe_mode_compares_bytes_exactly_like_the_reference(eng):
 def _device_sets():
     import torch
     n = torch.cuda.device_count()
-    sets = [[0], [0, 0, 0]]                       # three workers on one GPU: the sharding / stitching code without needing three GPUs
+    # several workers on one GPU: the sharding / stitching code without needing several GPUs (four: the few-large-chunks setting)
+    sets = [[0], [0, 0, 0], [0, 0, 0, 0]]
     if n > 1:
         sets.append(list(range(n)))
     return sets

@@ -10,7 +10,8 @@
 // one __shfl_up per column step, i.e. one shuffle per K cell-pairs.  G*K rows are one pass; longer queries
 // take several passes with the last lane's row handed over through a per-group shared-memory row.
 //
-// Arithmetic (per cell-pair; measured pipe model in profiles/: ALU/DPX 64 lanes/clk/SM, FMA pipe another 64):
+// Arithmetic (per cell-pair; measured pipe model, DESIGN.md section 3: ALU pipe 2 clocks per warp instruction, plain adds 1, IMAD 2
+// on the FMA pipe and about one clock next to packed DPX work):
 //   s   = prmt(ta[r], tb[r], rsel)     per-row tables: byte c of ta / tb = (score - gap) of this row's base against reference code c
 //                                      for pair A / pair B; the column's selector picks both and sign-extends them (ALU)
 //   [WIDE: alphabets of 5..8 symbols -- the reference's data sets use '0'..'4' -- need all eight bytes of (ta, tb) for ONE pair:
@@ -18,7 +19,8 @@
 //   e   = __viaddmax_s16x2(diag, s, left) max(diag + s, left)   — independent of the row above (VIADDMNMX.S16x2)
 //   h   = __vimax3_s16x2(e, up, B2)       ReLU against the bias B (= zero)                     (VIMNMX3.S16x2)
 //   hg  = h + G2                       plain 32-bit add: all values carry a bias B >= -gap, so the low half
-//                                      always carries into the high half and G2's high half is gap-1  (either pipe)
+//                                      always carries into the high half and G2's high half is gap-1  (VIADD: 1 clock; as an IMAD
+//                                      the step took 0.9 clocks per row longer, tools/sr_rowmix_bench.cu)
 //   key = h * 2^k + code               one IMAD on the FMA pipe: the (positive, biased) score moves up k bits in
 //                                      both halves (UNSIGNED 16-bit keys: (Hmax + B) << k < 65536); the low k bits are
 //                                      [upper row of the row pair : 1][2^(k-1)-1 - (step mod 2^(k-1)) : k-1]; the two code
@@ -29,7 +31,7 @@
 //   32-bit key per pair and lane, (score | 31-row | 255-block | code): higher score, then smaller row, then earlier step —
 //   exactly the reference's first-strict-max-in-row-major rule; lanes / passes are merged with the same order.  The fold
 //   spreads the three fields with masks (ALU) and multiplies by run-time powers of two (FMA pipe), two candidates per VIMNMX3.U32.
-// => 3.5 ALU-pipe + 3 FMA-pipe instructions per cell-pair (2 cells); 4 more ALU-pipe instructions per column step.
+// => 3.5 two-clock ALU-pipe instructions + 1 VIADD + 1 IMAD per cell-pair (2 cells) = 8.9 clocks measured; one IADD3 per column step.
 // Registers hold hg = H + gap + B ("already gapped"), which is what the right and lower neighbours need;
 // the diagonal neighbour wants H, so the table holds score - gap.
 #pragma once

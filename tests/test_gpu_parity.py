@@ -432,3 +432,27 @@ def test_fasta_pairs_align_like_the_same_pairs_in_the_reference_format(eng, tmp_
         res = eng.align_batch(api.make_params(algo, flags=ALL), p.sequences, p.pairs)
         s, e, t = ol.align_batch(ol.params(algo), blob, pairs)
         assert (res.scores == s).all() and res.strings == t
+
+
+@pytest.mark.parametrize("L", [84, 85, 169, 170, 340, 341])
+def test_short_read_keys_at_the_position_bit_thresholds(eng, L):
+    """The end-cell keys are unsigned 16-bit: (3 L + 2) << k < 65536 picks k = 8 / 7 / 6 / 5 at L <= 84 / 169 / 340 / ...  Identical
+    and nearly identical pairs drive the score -- and with it bit 15 of the keys -- to the top of each range, on both sides of a
+    threshold; shifted copies put the maximum into every lane and block."""
+    rng = np.random.default_rng(L)
+    seqs = []
+    for k in range(96):
+        r = rng.integers(0, 4, L).astype(np.uint8) + ord("0")
+        q = r.copy()
+        if k % 3 == 1:
+            q[rng.integers(0, L, max(1, L // 40))] = ord("0")
+        if k % 3 == 2:
+            q = np.concatenate([q[k % 17:], rng.integers(0, 4, k % 17).astype(np.uint8) + ord("0")])
+        seqs.append((r.tobytes(), q.tobytes()))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(seqs))
+    w = dict(match=3, mismatch=-1, gap_open=-2)
+    res, st = _staged(eng, blob, pairs, api.make_params(api.LSW, flags=api.OUT_SCORE | api.OUT_END_COORDS, **w))
+    assert st["kernel_id"] == 2
+    s, e, _ = ol.align_batch(ol.params(ol.LSW, **w), blob, pairs, strings=False, threads=8)
+    assert (res.scores == s).all() and int(s.max()) == 3 * L
+    assert (res.end_row_col == e).all()

@@ -579,6 +579,8 @@ def bench_batched(C, cfg_no, steps, warmup, score_only=False, n_pairs=0, with_cp
     sass_key = wl["sass"].format(track=not score_only)
     if cfg_no != 2 and not want_strings:
         sass_key = sass_key.replace("traceback=True", "traceback=False")
+        if cfg_no == 3:
+            sass_key = sass_key.replace("K=8", "K=16")         # Gotoh without traceback keeps 16 rows per lane (host_run.cuh: pairwf_eligible)
     mix = sass_counts(sass_key)
     kern_ms = fill_ms if fill_ms > 0 else ms_per_step          # the dominant kernel = the fill kernel(s) of one step
     if not want_strings:

@@ -111,6 +111,7 @@ struct DpxOptions {
     int long_bt_tiles = 0;     // long-pair traceback: tiles per round; 0 = 2 per SM
     int no_pairwf = 0;         // skip the packed pair-wavefront kernels (general wavefront instead)
     int pairwf_int32 = 0;      // pair-wavefront kernels in int32 even when int16x2 would fit
+    int pairwf_k8 = 0;         // Gotoh pair-wavefront kernel with 8 rows per lane even where 16 would be taken
     int no_bandkernel = 0;     // skip the band-on-a-warp kernel
     int no_shortread = 0;      // skip the short-read kernel
     int serial_chunks = 0;     // traceback chunk pipeline: one buffer, chunks in series (times the fill kernel alone)
@@ -328,6 +329,7 @@ int dpx_set_option(dpx_ctx* ctx, const char* name, long long value) {
     else if (k == "long_bt_tiles") { if (value < 0 || value > 4096) return DPX_ERR_INVALID; o.long_bt_tiles = (int)value; }
     else if (k == "no_pairwf") o.no_pairwf = value != 0;
     else if (k == "pairwf_int32") o.pairwf_int32 = value != 0;
+    else if (k == "pairwf_k8") o.pairwf_k8 = value != 0;
     else if (k == "no_bandkernel") o.no_bandkernel = value != 0;
     else if (k == "no_shortread") o.no_shortread = value != 0;
     else if (k == "serial_chunks") o.serial_chunks = value != 0;

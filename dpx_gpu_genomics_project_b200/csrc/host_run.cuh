@@ -129,17 +129,27 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     const long long tm = 4 * (m - open) - code, tx = 4 * (x - open) - code;
     if (tm < 0 || tm > 127 || tx < 0 || tx > 127) return false;     // table bytes are sign-extended by the selector
     if (b->max_r > 12000) return false;                          // the per-warp column table (2 B per column, 4 warps per block) must leave 2 blocks per SM
-    const int K = 8;
-    const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
-    // lowest value any stored quantity can take (gaps-only path bounds H from below; Smith-Waterman: H >= 0) and the highest score
-    const long long lo = sw ? go - 2
-                       : aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
-                             : (Qp + Rp + 1) * go + std::min<long long>(x, 0) - 2;
-    const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
-    const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
-    const long long B = -4 * lo + margin;
-    const bool packed = !wide && 4 * hi + B + 16 <= 32767 && !b->ctx->opt.pairwf_int32;     // else one pair per warp in int32
-    if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
+    // rows per lane: 8; packed Gotoh WITHOUT traceback on queries of more than one 256-row pass takes 16 (the per-step work that does
+    // not depend on the rows -- shuffles, selector load, predicates: a fifth of the step at 8 rows -- is paid half as often).  With
+    // traceback the 16-row kernel needs 165 registers: three blocks per SM fill the register file, the walk of the previous chunk
+    // finds no room beside the fill and the chunk pipeline of section 5 stalls (measured: fill alone 34.0 ms instead of 35.4, the
+    // pipelined step 46.4 instead of 36.5), so that path stays at 8.
+    int K = (aff && !wide && b->max_q > 256 && !(p->flags & DPX_OUT_STRINGS) && !b->ctx->opt.pairwf_k8) ? 16 : 8;
+    bool packed = false; long long B = 0;
+    for (;;) {
+        const long long Qp = (long long)((b->max_q + 32 * K - 1) / (32 * K)) * 32 * K, Rp = (long long)b->max_r + 34;
+        // lowest value any stored quantity can take (gaps-only path bounds H from below; Smith-Waterman: H >= 0) and the highest score
+        const long long lo = sw ? go - 2
+                           : aff ? 2 * go + (Qp + Rp) * ge + open + std::min<long long>(x, 0) + ge - 2
+                                 : (Qp + Rp + 1) * go + std::min<long long>(x, 0) - 2;
+        const long long hi = std::max<long long>(m, 0) * std::min(Qp, Rp);
+        const long long margin = 4 * std::max<long long>(std::max(-open, -ge), 1) + 16;
+        B = -4 * lo + margin;
+        packed = !wide && 4 * hi + B + 16 <= 32767 && !b->ctx->opt.pairwf_int32;     // else one pair per warp in int32
+        if (!packed && 4 * hi + B + 16 > (1ll << 30)) return false;
+        if (K == 16 && !packed) { K = 8; continue; }                               // the 16-row instantiation exists for packed Gotoh only
+        break;
+    }
     pl->K = K; pl->packed = packed; pl->wide = wide;
     pl->lut_lo = (uint32_t)tx; pl->lut_hi = (uint32_t)tm;
     auto pk = [&](long long v) { return packed ? (uint32_t)(v & 0xffff) * 0x00010001u : (uint32_t)v; };
@@ -157,9 +167,9 @@ static bool pairwf_eligible(const dpx_batch* b, const dpx_params* p, PwPlan* pl)
     return true;
 }
 
-template <int ALGO, bool TB, bool PACKED, bool GBND, bool WIDE = false>
+template <int ALGO, bool TB, bool PACKED, bool GBND, bool WIDE = false, int K = 8>
 static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots) {
-    auto kern = pw_nw_kernel<ALGO, TB, 8, PACKED, GBND, WIDE>;
+    auto kern = pw_nw_kernel<ALGO, TB, K, PACKED, GBND, WIDE>;
     CU(max_dyn_smem(ctx, kern));
     int per_sm = 0;
     CU(occupancy(ctx, &per_sm, kern, 128, smem));
@@ -170,7 +180,11 @@ static int launch_pairwf_w(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_
     return DPX_OK;
 }
 template <int ALGO, bool TB>
-static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots, bool packed) {
+static int launch_pairwf(dpx_ctx* ctx, cudaStream_t st, const PwArgs& a, size_t smem, int n_slots, bool packed, int K = 8) {
+    if constexpr (ALGO == DPX_ALGO_ANW && !TB) {
+        if (K == 16 && packed && !a.codes)
+            return a.bnd_global ? launch_pairwf_w<ALGO, TB, true, true, false, 16>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, true, false, false, 16>(ctx, st, a, smem, n_slots);
+    }
     if (a.codes) return a.bnd_global ? launch_pairwf_w<ALGO, TB, false, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false, true>(ctx, st, a, smem, n_slots);
     if (a.bnd_global) return packed ? launch_pairwf_w<ALGO, TB, true, true>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, true>(ctx, st, a, smem, n_slots);
     return packed ? launch_pairwf_w<ALGO, TB, true, false>(ctx, st, a, smem, n_slots) : launch_pairwf_w<ALGO, TB, false, false>(ctx, st, a, smem, n_slots);
@@ -373,7 +387,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
                 const int n_slots = pl.packed ? (a.count + 1) / 2 : a.count;
                 int r;
                 if (algo == DPX_ALGO_LSW) r = launch_pairwf<DPX_ALGO_LSW, true>(ctx, fst, a, smem, n_slots, pl.packed);
-                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots, pl.packed);
+                else if (aff) r = want_strings ? launch_pairwf<DPX_ALGO_ANW, true>(ctx, fst, a, smem, n_slots, pl.packed, pl.K) : launch_pairwf<DPX_ALGO_ANW, false>(ctx, fst, a, smem, n_slots, pl.packed, pl.K);
                 else     r = want_strings ? launch_pairwf<DPX_ALGO_LNW, true>(ctx, fst, a, smem, n_slots, pl.packed) : launch_pairwf<DPX_ALGO_LNW, false>(ctx, fst, a, smem, n_slots, pl.packed);
                 if (r) return r;
                 CU(cudaEventRecord(e, fst));

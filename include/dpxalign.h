@@ -116,6 +116,7 @@ int         dpx_set_stream(dpx_ctx* ctx, void* cuda_stream);
  *   "serial_chunks" 0/1      traceback chunks in series on one buffer              "trace" 0/1        chunk timeline on stderr
  *   "no_sidecar" 0/1         ignore the parser's packed copy, upload raw bytes     "no_shortread" / "no_pairwf" / "no_bandkernel" /
  *   "pairwf_int32" 0/1       kernel selection overrides (fall back to the next kernel family; still CUDA, never the CPU)
+ *   "pairwf_k8" 0/1          Gotoh fill with 8 rows per lane where the library would take 16 (no traceback, queries above 256 rows)
  *   "long_k" (0,2,..32) "long_cap" "long_notable" "long_bt_tiles"   long-pair lane width / forced passes / byte-compare kernel / tiles per round */
 int         dpx_set_option(dpx_ctx* ctx, const char* name, long long value);
 /* Binds the calling host thread to the CPUs local to a CUDA device (its NUMA node) so that page-locked buffers allocated

@@ -89,6 +89,30 @@ def test_multi_pass_queries(eng, algo):
     _check(eng, algo, blob, pairs, KERNEL_PAIR, **WEIGHTS[algo][0])
 
 
+def test_gotoh_scores_with_16_and_8_rows_per_lane_agree(eng):
+    """Without traceback the Gotoh fill keeps 16 rows per lane for queries above 256 rows (two 512-row passes for 1000 rows instead
+    of four 256-row ones; the D / I codes stay uncleaned).  Rows around the pass edges of both geometries, every weight set, against the
+    oracle and against the 8-row kernel."""
+    pp = []
+    rng = synth.Rng(16)
+    for (R, Q) in [(300, 257), (400, 511), (200, 512), (513, 513), (90, 1023), (1024, 1025), (700, 1536), (33, 2000)]:
+        r = synth.random_seq(rng, R)
+        q = synth.mutate(rng, r, 0.05, 0.02, 0.02)[:Q]
+        pp.append((r, q + synth.random_seq(rng, Q - len(q))))
+    blob, pairs = ol.parse_image(synth.pairs_to_file_bytes(pp))
+    flags = api.OUT_SCORE | api.OUT_END_COORDS
+    for w in WEIGHTS[api.ANW]:
+        s, e, _ = ol.align_batch(ol.params(ol.ANW, **w), blob, pairs, strings=False, threads=8)
+        got16 = eng.align_batch(api.make_params(api.ANW, flags=flags, **w), blob, pairs)
+        eng.set_option("pairwf_k8", 1)
+        try:
+            got8 = eng.align_batch(api.make_params(api.ANW, flags=flags, **w), blob, pairs)
+        finally:
+            eng.set_option("pairwf_k8", 0)
+        assert (got16.scores == s).all() and (got8.scores == s).all()
+        assert (got16.end_row_col == e).all() and (got8.end_row_col == e).all()
+
+
 @pytest.mark.parametrize("algo", [api.LNW, api.ANW, api.LSW])
 def test_config3_shape(eng, algo):
     """BASELINE config 3 shape (1000 x 1000, mutated 2% / 0.5% / 0.5%), a small batch with an odd pair count."""

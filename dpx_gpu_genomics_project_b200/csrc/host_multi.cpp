@@ -146,10 +146,11 @@ int dpx_create_multi(dpx_multi** out, const int* devices, int n_devices) {
     int st = DPX_OK;
     for (Worker* x : m->w) { x->wait(); if (x->create_status != DPX_OK && st == DPX_OK) st = x->create_status; }
     if (st != DPX_OK) { dpx_destroy_multi(m); return st; }
-    // Driver calls of different host threads of ONE process serialise on the runtime's locks (measured through bench.py's
-    // `2_multi_abi` leg: 12 chunks per device cost 4.7 / 7.6 / 17.3 ms per call on 2 / 4 / 8 GPUs, ~400 calls per device and call).
-    // With many devices each worker therefore runs its shard in few, large chunks: a third of the calls, most of the overlap.
-    if (n_devices >= 4)
+    // Chunks per worker and call (dpx_multi_set_option overrides).  A process that owns 4 GPUs alone runs the 12-chunk pipeline of
+    // dpx_align_batch best (tools/multi_trace.py 4 4000000: 3.52 ms per 4 M pairs at 12 chunks, 3.91 at 3, 5.21 at 1).  At 8 devices the
+    // only measurement is from inside a torchrun job (bench.py, `2_multi_abi`): 17.3 ms at 12 chunks, 4.29 at 3 -- ~400 driver calls
+    // per worker and call from 8 threads of one process do not stay cheap -- so from 8 devices up a worker takes few, large chunks.
+    if (n_devices >= 8)
         for (Worker* x : m->w) { dpx_set_option(x->ctx, "chunks_packed", 3); dpx_set_option(x->ctx, "chunks", 4); }
     *out = m;
     return DPX_OK;

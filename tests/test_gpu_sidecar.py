@@ -134,8 +134,8 @@ def test_stripe_mode_compares_bytes_exactly_like_the_reference(eng):
 def _device_sets():
     import torch
     n = torch.cuda.device_count()
-    # several workers on one GPU: the sharding / stitching code without needing several GPUs (four: the few-large-chunks setting)
-    sets = [[0], [0, 0, 0], [0, 0, 0, 0]]
+    # several workers on one GPU: the sharding / stitching code without needing several GPUs (eight: the few-large-chunks setting)
+    sets = [[0], [0, 0, 0], [0] * 8]
     if n > 1:
         sets.append(list(range(n)))
     return sets

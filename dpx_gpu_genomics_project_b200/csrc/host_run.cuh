@@ -352,7 +352,7 @@ static int batch_run(dpx_batch* b, const dpx_params* p) {
             PwArgs a{};
             a.packed = b->d_packed; a.pk_off = b->d_pk_off; a.pk_stride = b->pk_stride; a.pairs = b->d_pairs; a.order = b->d_order;
             a.lut_lo = pl.lut_lo; a.lut_hi = pl.lut_hi; a.ext2 = pl.ext2; a.addc = pl.addc; a.addc3 = pl.addc3; a.minus1 = 0xffffffffu; a.zero2 = pl.zero2;
-            a.one = 1u; a.two = 2u; a.four = 4u; a.eight = 8u; a.sixteen = 16u;
+            a.one = 1u; a.four = 4u; a.sixteen = 16u;
             a.b0 = pl.b0; a.b1 = pl.b1; a.bstep = pl.bstep; a.dec_sub = pl.dec_sub; a.dec_add = pl.dec_add;
             a.scores = b->d_scores; a.end_rc = b->d_end_rc; a.tb = b->d_tb; a.tb_stride = tbs;
             a.bnd_stride = b->max_r + 36; a.rsel_stride = (b->max_r + 68) & ~1;

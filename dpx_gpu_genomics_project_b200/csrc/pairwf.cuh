@@ -72,7 +72,7 @@ struct PwArgs {
     uint32_t addc3;                      // the same + 3                                                  (applied to h' - code)
     uint32_t minus1;                     // 0xffffffff: run-time multiplier for FMA-pipe subtractions
     uint32_t zero2;                      // Smith-Waterman: packed BIAS + 3 (H = 0 with the STOP code)
-    uint32_t one, two, four, eight, sixteen;   // run-time multipliers: keep shifts / adds on the FMA pipe as IMAD
+    uint32_t one, four, sixteen;         // run-time multipliers: keep shifts / adds on the FMA pipe as IMAD
     int b0, b1, bstep;                   // border(idx) = idx == 0 ? b0 : b1 + bstep * idx   (stored form, one half)
     int dec_sub, dec_add;                // score = ((half - dec_sub) >> 2) + dec_add
     int32_t* scores;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) pw_nw_kernel(const PwArgs a) {
     uint16_t* __restrict__ rsel = reinterpret_cast<uint16_t*>(pw_smem + (GBND ? 0 : (size_t)4 * a.bnd_stride * (AFF ? 2 : 1))) + (size_t)wib * a.rsel_stride;
     const uint32_t one = a.one, ext2 = a.ext2, addc = a.addc, addc3 = a.addc3, minus1 = a.minus1, zero2 = a.zero2;
     const uint32_t ms1 = a.lut_hi & 0xffu, xs4 = (a.lut_lo & 0xffu) * 0x01010101u;     // table entries: match, mismatch
-    const uint32_t two = a.two, four = a.four, eight = a.eight, sixteen = a.sixteen;
+    const uint32_t four = a.four, sixteen = a.sixteen;
     const int n_slots = PACKED ? (a.count + 1) >> 1 : a.count;     // packed: two pairs per warp; unpacked (int32): one
     const PwGeom geo = PwGeom::make(K, CB);
 

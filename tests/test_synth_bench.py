@@ -67,3 +67,25 @@ def test_config5_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["metric"] == "GCUPS" and line["scaling"] == "strong" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["config"]["baseline_config"] == 5
+
+
+def test_every_roofline_key_of_the_bench_is_in_the_committed_sass_counts():
+    """bench.py takes a kernel's clocks per cell from profiles/sass_counts.json by key; a renamed template parameter or a missing
+    instantiation would silently drop the roofline from the line.  Every key the default run can ask for must be there, with the
+    three resources of the model, and the bound must be the largest of them."""
+    bench = _bench()
+    keys = []
+    for no, wl in bench.WORKLOADS.items():
+        for track in (True, False):
+            k = wl["sass"].format(track=track)
+            keys.append(k)
+            if no != 2:
+                k2 = k.replace("traceback=True", "traceback=False")
+                keys.append(k2.replace("K=8", "K=16") if no == 3 else k2)
+    keys.append(bench.LONG["sass"])
+    for k in set(keys):
+        m = bench.sass_counts(k)
+        assert m is not None, k
+        assert m["alu_clk_per_cell"] > 0 and m["issued_instr_per_cell"] > 0 and m["fma_clk_per_cell"] >= 0
+        assert abs(bench.issue_roof_cells_per_clk_per_sm(m) - 128.0 / max(m["alu_clk_per_cell"], m["fma_clk_per_cell"], m["issued_instr_per_cell"])) < 1e-9
+        assert 0 < m["half_rate_alu_instr_per_cell"] * 2 <= m["alu_clk_per_cell"] + 1e-9
